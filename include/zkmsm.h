@@ -1,0 +1,148 @@
+/* zkmsm.h -- C ABI of the B200-native MSM / Groth16-prove path for zk-toolkit's BLS12-381.
+ *
+ * The reference (exfinen/zk-toolkit, Rust) has no FFI for its own curve code; its seams are
+ * ordinary methods.  Each entry point below names the reference method it replaces
+ * (paths relative to the reference's src/).  The call style -- one-time create, opaque
+ * handles, out-parameters, integer status -- follows the reference's only native binding,
+ * the mcl backend (building_block/mcl/mcl_initializer.rs:8-15, mcl_g1.rs:64-86).
+ *
+ * Data layout at this boundary (all host memory unless a name says `_device`):
+ *   Fq element : 12 x uint32, little-endian limbs, canonical value in [0, q)
+ *   Fr scalar  :  8 x uint32, little-endian limbs, value < 2^255 (reference scalars are Fr
+ *                 elements, i.e. < r; prime_field_elem.rs:263-272 reduces on construction)
+ *   G1 point   : 24 x uint32 = x | y                  (g1_point.rs:33-36  Rational{x,y})
+ *   G2 point   : 48 x uint32 = x.u0 | x.u1 | y.u0 | y.u1   (g2_point.rs:31-34; NB the
+ *                 reference's Fq2::new takes (u1, u0), fq2.rs:22)
+ *   AtInfinity : a separate flag byte per point (nullable array = no point is infinity);
+ *                results return it in *out_is_inf and zero the coordinates.
+ *
+ * Semantics kept from the reference: n = 0 gives AtInfinity
+ * (polynomial.rs:276); only the first n loaded points are used (polynomial.rs:277); n larger
+ * than the point set is an error where the reference panics (polynomial.rs:278); scalar 0 or
+ * point AtInfinity contributes nothing (macros.rs:11,44-52); P+P and P+(-P) inside the sum are
+ * exact (macros.rs:53-108); the result is the canonical affine point (g1_point.rs:163-174).
+ *
+ * Threading: one caller at a time per context (the reference is single-threaded).
+ * There is NO CPU fallback: every call fails with ZKMSM_ERR_NO_DEVICE / ZKMSM_ERR_CUDA when no
+ * sm_100 device is usable.
+ */
+#ifndef ZKMSM_H
+#define ZKMSM_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ZKMSM_OK 0
+#define ZKMSM_ERR_INVALID_ARG (-1)
+#define ZKMSM_ERR_CUDA (-2)
+#define ZKMSM_ERR_SCALAR_RANGE (-3)   /* a scalar had bit 255 set */
+#define ZKMSM_ERR_NO_DEVICE (-4)
+#define ZKMSM_ERR_TOO_FEW_POINTS (-5) /* n > points loaded; the reference panics, polynomial.rs:278 */
+#define ZKMSM_ERR_NOMEM (-6)
+
+/* zkmsm_*_load_points flags */
+#define ZKMSM_PRECOMPUTE 1u /* also store 2^(c w) P for every window w (CRS-style static sets) */
+
+typedef struct zkmsm_ctx zkmsm_ctx;       /* one CUDA device + stream + workspace */
+typedef struct zkmsm_points zkmsm_points; /* device-resident point set (G1 or G2) */
+
+const char* zkmsm_version(void);
+
+/* One-time init for one device, like MclInitializer::init (mcl_initializer.rs:8-15). */
+int zkmsm_create(int device, zkmsm_ctx** out);
+int zkmsm_destroy(zkmsm_ctx* ctx);
+/* Run on the caller's CUDA stream (cudaStream_t) instead of the context's own; NULL restores it. */
+int zkmsm_set_stream(zkmsm_ctx* ctx, void* cuda_stream);
+/* Text of the last error on this context (never NULL). */
+const char* zkmsm_last_error(const zkmsm_ctx* ctx);
+/* Override the window width c for later MSMs / precomputed loads (0 = automatic). */
+int zkmsm_set_window(zkmsm_ctx* ctx, unsigned c);
+
+/* Pinned host memory for scalars / points (optional; any host pointer is accepted). */
+int zkmsm_host_alloc(size_t bytes, void** out);
+int zkmsm_host_free(void* p);
+
+/* ---- point sets: the `powers: &[G1Point]` / `&[G2Point]` argument of
+ * Polynomial::eval_with_g{1,2}_hidings (field/polynomial.rs:272-293), i.e. the CRS vectors
+ * crs.g1.xi, crs.g2.xi, crs.g1.xt_by_delta, crs.g1.uvw_wit (groth16/zktoolkit_based/crs.rs:17-34),
+ * uploaded once and kept resident. */
+int zkmsm_g1_load_points(zkmsm_ctx* ctx, const uint32_t* xy, const uint8_t* inf_flags, size_t n,
+                         unsigned flags, zkmsm_points** out);
+int zkmsm_g2_load_points(zkmsm_ctx* ctx, const uint32_t* xy, const uint8_t* inf_flags, size_t n,
+                         unsigned flags, zkmsm_points** out);
+int zkmsm_points_free(zkmsm_ctx* ctx, zkmsm_points* pts);
+size_t zkmsm_points_len(const zkmsm_points* pts);
+/* Copy a point set back as canonical affine limbs (+ flags, nullable). */
+int zkmsm_points_read(zkmsm_ctx* ctx, const zkmsm_points* pts, size_t first, size_t n, uint32_t* xy,
+                      uint8_t* inf_flags);
+
+/* ---- the MSM: Polynomial::eval_with_g1_hidings (polynomial.rs:272-281) and
+ * eval_with_g2_hidings (:284-293); also the inline loop `sum += &crs.g1.uvw_wit[i] * ai`
+ * (groth16/zktoolkit_based/prover.rs:128-131).  result = sum_{i<n} scalars[i] * points[i]. */
+int zkmsm_g1_msm(zkmsm_ctx* ctx, const zkmsm_points* pts, const uint32_t* scalars, size_t n,
+                 uint32_t out_xy[24], int* out_is_inf);
+int zkmsm_g2_msm(zkmsm_ctx* ctx, const zkmsm_points* pts, const uint32_t* scalars, size_t n,
+                 uint32_t out_xy[48], int* out_is_inf);
+/* Same with scalars already in device memory (n x 8 uint32). */
+int zkmsm_g1_msm_device(zkmsm_ctx* ctx, const zkmsm_points* pts, const uint32_t* scalars_device, size_t n,
+                        uint32_t out_xy[24], int* out_is_inf);
+int zkmsm_g2_msm_device(zkmsm_ctx* ctx, const zkmsm_points* pts, const uint32_t* scalars_device, size_t n,
+                        uint32_t out_xy[48], int* out_is_inf);
+/* One call with everything in host memory: upload points, multiply, free
+ * (exactly the (coeffs, powers) -> point shape of polynomial.rs:272-293). */
+int zkmsm_g1_msm_oneshot(zkmsm_ctx* ctx, const uint32_t* xy, const uint8_t* inf_flags, const uint32_t* scalars,
+                         size_t n, uint32_t out_xy[24], int* out_is_inf);
+int zkmsm_g2_msm_oneshot(zkmsm_ctx* ctx, const uint32_t* xy, const uint8_t* inf_flags, const uint32_t* scalars,
+                         size_t n, uint32_t out_xy[48], int* out_is_inf);
+
+/* Stream-ordered halves of the above, for pipelining and device-side timing:
+ * enqueue all kernels (no host synchronisation), later fetch the result. */
+int zkmsm_g1_msm_enqueue(zkmsm_ctx* ctx, const zkmsm_points* pts, const uint32_t* scalars_device, size_t n);
+int zkmsm_g2_msm_enqueue(zkmsm_ctx* ctx, const zkmsm_points* pts, const uint32_t* scalars_device, size_t n);
+int zkmsm_g1_msm_result(zkmsm_ctx* ctx, uint32_t out_xy[24], int* out_is_inf);
+int zkmsm_g2_msm_result(zkmsm_ctx* ctx, uint32_t out_xy[48], int* out_is_inf);
+/* Number of kernels the last enqueue launched. */
+int zkmsm_last_launch_count(const zkmsm_ctx* ctx);
+
+/* ---- multi-GPU: each rank multiplies its shard and exports one partial point (opaque
+ * little-endian blob: 48 words for G1, 96 for G2); any rank adds the gathered partials.
+ * Replaces the running `sum` of polynomial.rs:276-280 across shards. */
+#define ZKMSM_G1_PARTIAL_WORDS 48
+#define ZKMSM_G2_PARTIAL_WORDS 96
+int zkmsm_g1_msm_partial(zkmsm_ctx* ctx, const zkmsm_points* pts, const uint32_t* scalars, size_t n,
+                         uint32_t out_partial[ZKMSM_G1_PARTIAL_WORDS]);
+int zkmsm_g2_msm_partial(zkmsm_ctx* ctx, const zkmsm_points* pts, const uint32_t* scalars, size_t n,
+                         uint32_t out_partial[ZKMSM_G2_PARTIAL_WORDS]);
+int zkmsm_g1_msm_partial_device(zkmsm_ctx* ctx, const zkmsm_points* pts, const uint32_t* scalars_device, size_t n,
+                                uint32_t* out_partial_device);
+int zkmsm_g1_combine(zkmsm_ctx* ctx, const uint32_t* partials, size_t k, uint32_t out_xy[24], int* out_is_inf);
+int zkmsm_g2_combine(zkmsm_ctx* ctx, const uint32_t* partials, size_t k, uint32_t out_xy[48], int* out_is_inf);
+int zkmsm_g1_combine_device(zkmsm_ctx* ctx, const uint32_t* partials_device, size_t k, uint32_t out_xy[24],
+                            int* out_is_inf);
+
+/* ---- vector scalar multiplication of one base point: `&G1Point * &Fq1`
+ * (impl_scalar_mul_point!, curves/macros.rs:2-32) for n scalars at once, as CRS::new does
+ * (crs.rs:88-116).  Scalars are full 256-bit raw integers, not reduced (macros.rs:10-21). */
+int zkmsm_g1_mul_base(zkmsm_ctx* ctx, const uint32_t base_xy[24], const uint32_t* scalars, size_t n,
+                      uint32_t* out_xy, uint8_t* out_inf_flags);
+int zkmsm_g2_mul_base(zkmsm_ctx* ctx, const uint32_t base_xy[48], const uint32_t* scalars, size_t n,
+                      uint32_t* out_xy, uint8_t* out_inf_flags);
+/* Same, leaving the products on the device as a point set. */
+int zkmsm_g1_points_from_scalars(zkmsm_ctx* ctx, const uint32_t base_xy[24], const uint32_t* scalars, size_t n,
+                                 unsigned flags, zkmsm_points** out);
+int zkmsm_g2_points_from_scalars(zkmsm_ctx* ctx, const uint32_t base_xy[48], const uint32_t* scalars, size_t n,
+                                 unsigned flags, zkmsm_points** out);
+
+/* ---- diagnostics: integer-multiply throughput of this device (roofline denominator).
+ * variant 0: independent IMAD.WIDE.U32 chains; 1: carry-chained IMAD.WIDE.U32.X (mad.lo.cc/
+ * madc.hi.cc pairs); 2: 32-bit IMAD.  Returns limb products per second. */
+int zkmsm_bench_imad(zkmsm_ctx* ctx, int variant, int iters, double* out_lp_per_s, double* out_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZKMSM_H */

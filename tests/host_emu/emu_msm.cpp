@@ -1,0 +1,95 @@
+// TEST INFRASTRUCTURE ONLY: runs the identical MSM pipeline of csrc/msm.cuh (same bodies, same
+// launch sequence) on the CPU, one logical thread after another, with ptx.cuh's instruction
+// emulation.  Lets `pytest -m "not gpu"` check the pipeline logic (recoding, counting sort,
+// chunked accumulation, fix-up, reduction, Horner, precomputed slabs) against the oracle on a
+// machine with no GPU.  Never linked into, nor reachable from, the product library.
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#include "../../zk-toolkit_b200/csrc/msm.cuh"
+
+using namespace zk;
+
+struct HostExec {
+  int launches = 0;
+  template <class Body, class... Args>
+  void launch(uint32_t nthreads, Args... args) {
+    for (uint32_t t = 0; t < nthreads; t++) Body::run(t, args...);
+    launches++;
+  }
+  void zero(void* p, size_t bytes) { memset(p, 0, bytes); }
+};
+
+template <class C>
+static int emu_msm(const uint32_t* xy, const uint8_t* inf, const uint32_t* scalars, uint32_t n, uint32_t npts,
+                   uint32_t c, int precomp, uint32_t L, uint32_t K, uint32_t* out_xy, uint32_t* out_inf,
+                   uint32_t* out_xyzz) {
+  typedef typename C::F F;
+  HostExec ex;
+  if (c == 0) c = msm_pick_c(precomp ? npts : n, precomp != 0);
+  uint32_t W = msm_windows(c);
+  std::vector<Affine<F>> pts((size_t)npts * (precomp ? W : 1) + 1);
+  ex.launch<LoadPoints<C>>(npts, npts, xy, inf, pts.data());
+  if (precomp) ex.launch<PrecomputeSlabs<C>>(npts, npts, npts, c, W, pts.data());
+  if (n == 0) { *out_inf = 1; memset(out_xy, 0, 4 * C::AFF_LIMBS); return 0; }
+  MsmPlan p = msm_plan(n, c, precomp != 0, npts);
+  if (L) { p.L = L; p.acc_threads = (p.max_entries + L - 1) / L; }
+  if (K) p.K = K;
+  std::vector<uint32_t> hist(p.nb), offsets(p.nb + 1), segsum((p.nb + SCAN_SEG - 1) / SCAN_SEG + 1), err(1);
+  std::vector<Entry> entries(p.max_entries + 1);
+  std::vector<XYZZ<F>> buckets(p.nb), partials(p.acc_threads), reduced((size_t)p.nwin * (p.B / p.K));
+  // poison what the pipeline must overwrite before reading
+  memset(buckets.data(), 0xAB, sizeof(XYZZ<F>) * buckets.size());
+  memset(partials.data(), 0xCD, sizeof(XYZZ<F>) * partials.size());
+  MsmBuffers<C> b;
+  b.hist_cursor = hist.data(); b.offsets = offsets.data(); b.segsum = segsum.data(); b.entries = entries.data();
+  b.bucket_sums = buckets.data(); b.partials = partials.data(); b.reduced = reduced.data(); b.err = err.data();
+  XYZZ<F> xyzz;
+  msm_launch<C>(ex, p, b, (const Affine<F>*)pts.data(), scalars, out_xyzz ? &xyzz : (XYZZ<F>*)nullptr,
+                out_xyzz ? (uint32_t*)nullptr : out_xy, out_xyzz ? (uint32_t*)nullptr : out_inf);
+  if (out_xyzz) memcpy(out_xyzz, &xyzz, sizeof(xyzz));
+  return err[0] ? -3 : 0;
+}
+
+extern "C" {
+int emu_g1_msm(const uint32_t* xy, const uint8_t* inf, const uint32_t* scalars, uint32_t n, uint32_t npts, uint32_t c,
+               int precomp, uint32_t L, uint32_t K, uint32_t* out_xy, uint32_t* out_inf) {
+  return emu_msm<G1>(xy, inf, scalars, n, npts, c, precomp, L, K, out_xy, out_inf, nullptr);
+}
+int emu_g2_msm(const uint32_t* xy, const uint8_t* inf, const uint32_t* scalars, uint32_t n, uint32_t npts, uint32_t c,
+               int precomp, uint32_t L, uint32_t K, uint32_t* out_xy, uint32_t* out_inf) {
+  return emu_msm<G2>(xy, inf, scalars, n, npts, c, precomp, L, K, out_xy, out_inf, nullptr);
+}
+// k shards -> k partials -> CombinePartials (the multi-GPU path, one "rank" after another)
+int emu_g1_msm_sharded(const uint32_t* xy, const uint32_t* scalars, uint32_t n, uint32_t k, uint32_t* out_xy,
+                       uint32_t* out_inf) {
+  std::vector<XYZZ<Fp>> parts(k);
+  for (uint32_t r = 0; r < k; r++) {
+    uint32_t lo = (uint64_t)n * r / k, hi = (uint64_t)n * (r + 1) / k;
+    if (hi == lo) { memset(&parts[r], 0, sizeof(XYZZ<Fp>)); continue; }
+    uint32_t dummy[24], dinf;
+    int rc = emu_msm<G1>(xy + 24 * (size_t)lo, nullptr, scalars + 8 * (size_t)lo, hi - lo, hi - lo, 0, 0, 0, 0, dummy, &dinf,
+                         (uint32_t*)&parts[r]);
+    if (rc) return rc;
+  }
+  HostExec ex;
+  ex.launch<CombinePartials<G1>>(1u, k, (const XYZZ<Fp>*)parts.data(), out_xy, out_inf);
+  return 0;
+}
+// `base * k_i` for a vector of raw 256-bit scalars (FixedBaseMul path)
+int emu_g1_mul_base(const uint32_t* base_xy, const uint32_t* scalars, uint32_t n, uint32_t* out_xy, uint8_t* out_inf) {
+  HostExec ex;
+  std::vector<XYZZ<Fp>> chain(256);
+  std::vector<Affine<Fp>> table(256), out(n + 1);
+  ex.launch<BaseTableChain<G1>>(1u, base_xy, chain.data());
+  ex.launch<BaseTableAffine<G1>>(256u, (const XYZZ<Fp>*)chain.data(), table.data());
+  ex.launch<FixedBaseMul<G1>>(n, n, scalars, (const Affine<Fp>*)table.data(), out.data());
+  ex.launch<StorePoints<G1>>(n, n, (const Affine<Fp>*)out.data(), out_xy, out_inf);
+  return 0;
+}
+void emu_plan(uint32_t n, uint32_t c, int precomp, uint32_t* out) {
+  if (c == 0) c = msm_pick_c(n, precomp != 0);
+  MsmPlan p = msm_plan(n, c, precomp != 0, n);
+  memcpy(out, &p, sizeof(p));
+}
+}

@@ -1,0 +1,153 @@
+"""The MSM pipeline of csrc/msm.cuh, executed on the CPU (tests/host_emu/emu_msm.cpp runs the same
+kernel bodies in the same launch order), against the T0 oracle.  Covers the edge cases of
+SURVEY.md Appendix B; the GPU versions of these checks are in test_gpu_msm.py."""
+import ctypes
+import os
+import random
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import zkt_oracle as O
+from tests import util as U
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+EMU = os.path.join(HERE, "host_emu")
+u32p = ctypes.POINTER(ctypes.c_uint32)
+u8p = ctypes.POINTER(ctypes.c_uint8)
+
+
+@pytest.fixture(scope="module")
+def lib():
+    so = os.path.join(EMU, "libemu_msm.so")
+    subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-o", so, os.path.join(EMU, "emu_msm.cpp")])
+    return ctypes.CDLL(so)
+
+
+def ptr(a, t=u32p):
+    return a.ctypes.data_as(t) if a is not None else None
+
+
+def emu_g1(lib, pts, scalars, n=None, c=0, precomp=0, L=0, K=0):
+    xy, inf = U.g1_points_to_array(pts)
+    sc = U.scalars_to_array(scalars)
+    n = len(scalars) if n is None else n
+    out = np.zeros(24, dtype=np.uint32)
+    oinf = ctypes.c_uint32(0)
+    rc = lib.emu_g1_msm(ptr(xy), ptr(inf, u8p), ptr(sc), n, len(pts), c, precomp, L, K, ptr(out), ctypes.byref(oinf))
+    return rc, U.g1_from_array(out, oinf.value)
+
+
+def emu_g2(lib, pts, scalars, c=0, precomp=0):
+    xy, inf = U.g2_points_to_array(pts)
+    sc = U.scalars_to_array(scalars)
+    out = np.zeros(48, dtype=np.uint32)
+    oinf = ctypes.c_uint32(0)
+    rc = lib.emu_g2_msm(ptr(xy), ptr(inf, u8p), ptr(sc), len(scalars), len(pts), c, precomp, 0, 0, ptr(out), ctypes.byref(oinf))
+    return rc, U.g2_from_array(out, oinf.value)
+
+
+@pytest.fixture(scope="module")
+def g1_set():
+    rnd = random.Random(42)
+    dlogs = [rnd.randrange(1, O.R) for _ in range(48)]
+    return dlogs, [O.scalar_mul(O.G1_GEN, k) for k in dlogs]
+
+
+def test_emu_g1_small_vs_oracle_msm(lib, g1_set):
+    dlogs, pts = g1_set
+    rnd = random.Random(1)
+    for n in (1, 2, 3, 7, 16):
+        sc = U.rand_scalars(rnd, n)
+        rc, got = emu_g1(lib, pts[:n], sc)
+        assert rc == 0
+        assert got == O.msm(pts[:n], sc)          # the reference's serial loop
+
+
+@pytest.mark.parametrize("c,precomp,L,K", [(0, 0, 0, 0), (4, 0, 3, 2), (7, 0, 5, 8), (5, 1, 4, 4), (8, 1, 0, 0), (13, 0, 0, 0)])
+def test_emu_g1_window_variants(lib, g1_set, c, precomp, L, K):
+    dlogs, pts = g1_set
+    rnd = random.Random(c * 10 + precomp)
+    sc = U.rand_scalars(rnd, len(pts))
+    rc, got = emu_g1(lib, pts, sc, c=c, precomp=precomp, L=L, K=K)
+    assert rc == 0
+    assert got == U.expected_from_dlogs(O.G1_GEN, dlogs, sc)
+
+
+def test_emu_g1_edge_cases(lib, g1_set):
+    dlogs, pts = g1_set
+    n = 12
+    P, D = pts[:n], dlogs[:n]
+    exp = lambda sc, d=D: U.expected_from_dlogs(O.G1_GEN, d, sc)
+    # n = 0 -> AtInfinity (polynomial.rs:276)
+    assert emu_g1(lib, P, []) == (0, O.INF)
+    # scalar 0 contributes nothing; all-zero -> AtInfinity (macros.rs:11,15)
+    assert emu_g1(lib, P, [0] * n) == (0, O.INF)
+    sc = [0, 1, O.R - 1, 2, 0, O.R - 2, 1, 1, 5, 0, 7, O.R - 1]
+    assert emu_g1(lib, P, sc) == (0, exp(sc))
+    # all-equal scalars: one bucket per window holds every point
+    sc = [0x1234567890ABCDEF1234567890ABCDEF] * n
+    assert emu_g1(lib, P, sc, c=6, L=4) == (0, exp(sc))
+    # duplicate points (P+P inside a bucket -> tangent case, macros.rs:57-108)
+    dup = [P[0]] * n
+    sc = [3] * n
+    assert emu_g1(lib, dup, sc, c=5) == (0, O.scalar_mul(P[0], 3 * n))
+    # P and -P with equal scalars cancel (macros.rs:53-56)
+    pm = [P[0], O.point_neg(P[0]), P[1], O.point_neg(P[1])]
+    assert emu_g1(lib, pm, [9, 9, 11, 11], c=4) == (0, O.INF)
+    assert emu_g1(lib, pm, [9, 9, 11, 10], c=4) == (0, P[1])
+    # AtInfinity among the points (macros.rs:44-52)
+    withinf = [P[0], O.INF, P[1], O.INF]
+    assert emu_g1(lib, withinf, [5, 6, 7, 8]) == (0, O.msm(withinf, [5, 6, 7, 8]))
+    # more points than scalars: extra points ignored (polynomial.rs:277)
+    sc = [5, 6, 7]
+    assert emu_g1(lib, P, sc, n=3) == (0, exp(sc, D[:3]))
+    assert emu_g1(lib, P, sc, n=3, precomp=1, c=6) == (0, exp(sc, D[:3]))
+    # scalar >= 2^255 is rejected, never silently wrong
+    rc, _ = emu_g1(lib, P[:2], [1 << 255, 1])
+    assert rc == -3
+    # largest accepted scalars
+    sc = [(1 << 255) - 1, (1 << 255) - 19]
+    assert emu_g1(lib, P[:2], sc) == (0, O.msm(P[:2], sc))
+    # r * P = AtInfinity
+    assert emu_g1(lib, P[:1], [O.R]) == (0, O.INF)
+
+
+def test_emu_g1_sharded_partials_match_single(lib, g1_set):
+    dlogs, pts = g1_set
+    rnd = random.Random(5)
+    sc = U.rand_scalars(rnd, len(pts))
+    xy, _ = U.g1_points_to_array(pts)
+    s = U.scalars_to_array(sc)
+    exp = U.expected_from_dlogs(O.G1_GEN, dlogs, sc)
+    for k in (1, 2, 3, 8):
+        out = np.zeros(24, dtype=np.uint32)
+        oinf = ctypes.c_uint32(0)
+        assert lib.emu_g1_msm_sharded(ptr(xy), ptr(s), len(pts), k, ptr(out), ctypes.byref(oinf)) == 0
+        assert U.g1_from_array(out, oinf.value) == exp
+
+
+def test_emu_g1_mul_base_matches_reference_scalar_mul(lib):
+    # `g * k` (macros.rs:2-32) incl. raw scalars >= r and the g1_point.rs:352-371 multiples
+    ks = [0, 1, 2, 3, 12345, 1234567, 1234567890123456789, 123456789012345678901234567890,
+          O.R - 1, O.R, O.R + 5, (1 << 256) - 1]
+    base = np.array(O.g1_to_limbs(O.G1_GEN), dtype=np.uint32)
+    sc = U.scalars_to_array(ks)
+    out = np.zeros((len(ks), 24), dtype=np.uint32)
+    oinf = np.zeros(len(ks), dtype=np.uint8)
+    assert lib.emu_g1_mul_base(ptr(base), ptr(sc), len(ks), ptr(out), ptr(oinf, u8p)) == 0
+    for i, k in enumerate(ks):
+        assert U.g1_from_array(out[i], oinf[i]) == O.scalar_mul(O.G1_GEN, k), k
+
+
+def test_emu_g2_msm(lib):
+    rnd = random.Random(9)
+    dlogs = [rnd.randrange(1, O.R) for _ in range(6)]
+    pts = [O.scalar_mul(O.G2_GEN, k) for k in dlogs]
+    sc = U.rand_scalars(rnd, len(pts))
+    for c, pre in ((0, 0), (5, 1)):
+        rc, got = emu_g2(lib, pts, sc, c=c, precomp=pre)
+        assert rc == 0
+        assert got == U.expected_from_dlogs(O.G2_GEN, dlogs, sc)
+    assert emu_g2(lib, pts[:3], [4, 5, 6])[1] == O.msm(pts[:3], [4, 5, 6])

@@ -1,0 +1,255 @@
+// Montgomery prime-field arithmetic on 32-bit limbs for sm_100a.
+//
+// Replaces the reference's BigUint field ops on the MSM path
+// (src/building_block/field/prime_field_elem.rs:278-335 plus/minus/times/sq,
+// :448-457 negate, :379-436 inv) for the two BLS12-381 fields of params.rs:9,14:
+// Fq (381 bit, 12 limbs) and Fr (255 bit, 8 limbs).
+//
+// Representation: a*R mod p, R = 2^(32 N), little-endian limbs, ALWAYS fully reduced
+// to [0, p) so that zero / equality tests are exact limb comparisons.
+//
+// Multiplication is operand-scanning Montgomery with the running sum split into two
+// accumulators whose 64-bit digits sit at even resp. odd limb offsets.  Every limb
+// product a_j*b_i is then a 64-bit-aligned add into one of them, i.e. one
+// IMAD.WIDE.U32.X on a carry chain; nothing ever has to be split into lo/hi halves.
+// Cost per modmul with N = 12: 2*N*N = 288 IMAD.WIDE + N IMAD (the m_i) on the fma pipe
+// and ~90 IADD3/LOP3 on the alu pipe.  Limb-product (LP) count used by the roofline
+// in DESIGN.md: 2 N^2 + N = 300.
+#pragma once
+#include "ptx.cuh"
+#include "constants.cuh"
+
+namespace zk {
+
+struct FqCfg {
+  static constexpr int N = 12;
+  static constexpr uint32_t INV = FQ_INV;
+  ZK_HD static uint32_t p(int i) { return FQ_P[i]; }
+  ZK_HD static uint32_t one(int i) { return FQ_ONE[i]; }
+  ZK_HD static uint32_t r2(int i) { return FQ_R2[i]; }
+  ZK_HD static uint32_t pm2(int i) { return FQ_PM2[i]; }
+};
+
+struct FrCfg {
+  static constexpr int N = 8;
+  static constexpr uint32_t INV = FR_INV;
+  ZK_HD static uint32_t p(int i) { return FR_P[i]; }
+  ZK_HD static uint32_t one(int i) { return FR_ONE[i]; }
+  ZK_HD static uint32_t r2(int i) { return FR_R2[i]; }
+  ZK_HD static uint32_t pm2(int i) { return FR_PM2[i]; }
+};
+
+template <class Cfg>
+struct alignas(16) Mont {
+  static constexpr int N = Cfg::N;
+  typedef Cfg cfg;
+  uint32_t v[Cfg::N];
+};
+
+typedef Mont<FqCfg> Fp;
+typedef Mont<FrCfg> Fr;
+
+// ---------------------------------------------------------------- small helpers
+template <class C> ZK_HD void fset_zero(Mont<C>& r) {
+#pragma unroll
+  for (int i = 0; i < C::N; i++) r.v[i] = 0;
+}
+template <class C> ZK_HD void fset_one(Mont<C>& r) {
+#pragma unroll
+  for (int i = 0; i < C::N; i++) r.v[i] = C::one(i);
+}
+template <class C> ZK_HD bool fis_zero(const Mont<C>& a) {
+  uint32_t o = 0;
+#pragma unroll
+  for (int i = 0; i < C::N; i++) o |= a.v[i];
+  return o == 0;
+}
+template <class C> ZK_HD bool feq(const Mont<C>& a, const Mont<C>& b) {
+  uint32_t o = 0;
+#pragma unroll
+  for (int i = 0; i < C::N; i++) o |= a.v[i] ^ b.v[i];
+  return o == 0;
+}
+
+// r = (t >= p) ? t - p : t, for t < 2p
+template <class C> ZK_HD void freduce_once(Mont<C>& r, const uint32_t* t) {
+  uint32_t d[C::N];
+  d[0] = ptx::sub_cc(t[0], C::p(0));
+#pragma unroll
+  for (int i = 1; i < C::N; i++) d[i] = ptx::subc_cc(t[i], C::p(i));
+  uint32_t borrow = ptx::subc(0, 0);  // all-ones when t < p
+#pragma unroll
+  for (int i = 0; i < C::N; i++) r.v[i] = (t[i] & borrow) | (d[i] & ~borrow);
+}
+
+// ---------------------------------------------------------------- add / sub / neg
+template <class C> ZK_HD void fadd(Mont<C>& r, const Mont<C>& a, const Mont<C>& b) {
+  uint32_t t[C::N];
+  t[0] = ptx::add_cc(a.v[0], b.v[0]);
+#pragma unroll
+  for (int i = 1; i < C::N - 1; i++) t[i] = ptx::addc_cc(a.v[i], b.v[i]);
+  t[C::N - 1] = ptx::addc(a.v[C::N - 1], b.v[C::N - 1]);  // p has >= 1 spare top bit: no carry out
+  freduce_once(r, t);
+}
+
+template <class C> ZK_HD void fsub(Mont<C>& r, const Mont<C>& a, const Mont<C>& b) {
+  uint32_t t[C::N];
+  t[0] = ptx::sub_cc(a.v[0], b.v[0]);
+#pragma unroll
+  for (int i = 1; i < C::N; i++) t[i] = ptx::subc_cc(a.v[i], b.v[i]);
+  uint32_t borrow = ptx::subc(0, 0);  // all-ones when a < b: add p back
+  r.v[0] = ptx::add_cc(t[0], C::p(0) & borrow);
+#pragma unroll
+  for (int i = 1; i < C::N - 1; i++) r.v[i] = ptx::addc_cc(t[i], C::p(i) & borrow);
+  r.v[C::N - 1] = ptx::addc(t[C::N - 1], C::p(C::N - 1) & borrow);
+}
+
+template <class C> ZK_HD void fdbl(Mont<C>& r, const Mont<C>& a) { fadd(r, a, a); }
+
+// -a, with -0 = 0 (prime_field_elem.rs:448-457)
+template <class C> ZK_HD void fneg(Mont<C>& r, const Mont<C>& a) {
+  uint32_t nz = fis_zero(a) ? 0u : 0xffffffffu;
+  uint32_t t[C::N];
+  t[0] = ptx::sub_cc(C::p(0), a.v[0]);
+#pragma unroll
+  for (int i = 1; i < C::N - 1; i++) t[i] = ptx::subc_cc(C::p(i), a.v[i]);
+  t[C::N - 1] = ptx::subc(C::p(C::N - 1), a.v[C::N - 1]);
+#pragma unroll
+  for (int i = 0; i < C::N; i++) r.v[i] = t[i] & nz;
+}
+
+// r = neg ? -a : a
+template <class C> ZK_HD void fcneg(Mont<C>& r, const Mont<C>& a, bool neg) {
+  Mont<C> n;
+  fneg(n, a);
+  uint32_t m = neg ? 0xffffffffu : 0u;
+#pragma unroll
+  for (int i = 0; i < C::N; i++) r.v[i] = (n.v[i] & m) | (a.v[i] & ~m);
+}
+
+// ---------------------------------------------------------------- Montgomery multiplication
+namespace detail {
+
+// acc[0..n) = x[0], x[2], .. , x[n-2] times y as consecutive 64-bit digits (no accumulate)
+template <int n> ZK_HD void row_mul(uint32_t* acc, const uint32_t* x, uint32_t y) {
+#pragma unroll
+  for (int j = 0; j < n; j += 2) {
+    acc[j] = ptx::mul_lo(x[j], y);
+    acc[j + 1] = ptx::mul_hi(x[j], y);
+  }
+}
+
+// acc[0..n) += (x[0], x[2], ..) * y on one carry chain; the chain's carry-out stays in CC
+template <int n, class X> ZK_HD void row_mad(uint32_t* acc, X x, uint32_t y) {
+  acc[0] = ptx::mad_lo_cc(x(0), y, acc[0]);
+  acc[1] = ptx::madc_hi_cc(x(0), y, acc[1]);
+#pragma unroll
+  for (int j = 2; j < n; j += 2) {
+    acc[j] = ptx::madc_lo_cc(x(j), y, acc[j]);
+    acc[j + 1] = ptx::madc_hi_cc(x(j), y, acc[j + 1]);
+  }
+}
+
+// acc = (acc >> 64) + (x[0], x[2], ..) * y, consuming the carry already in CC; no carry-out
+template <int n, class X> ZK_HD void row_mad_shift(uint32_t* acc, X x, uint32_t y) {
+#pragma unroll
+  for (int j = 0; j < n - 2; j += 2) {
+    acc[j] = ptx::madc_lo_cc(x(j), y, acc[j + 2]);
+    acc[j + 1] = ptx::madc_hi_cc(x(j), y, acc[j + 3]);
+  }
+  acc[n - 2] = ptx::madc_lo_cc(x(n - 2), y, 0);
+  acc[n - 1] = ptx::madc_hi(x(n - 2), y, 0);
+}
+
+template <class C> struct ModEven { ZK_HD uint32_t operator()(int j) const { return C::p(j); } };
+template <class C> struct ModOdd { ZK_HD uint32_t operator()(int j) const { return C::p(j + 1); } };
+struct Arr {
+  const uint32_t* p;
+  ZK_HD uint32_t operator()(int j) const { return p[j]; }
+};
+
+// One operand-scanning step: T = (T + a*bi + m*p) / 2^32 in split form.
+// On entry (not first) the running sum is  lo + hi*2^32  where `lo` still holds the previous
+// step's even digits (its limb 0 is zero, limb 1 is the odd leftover) and `hi` the odd digits.
+// The division by 2^32 is the renaming: hi becomes the new even accumulator E, lo>>64 the new odd O.
+template <class C> ZK_HD void mont_step(uint32_t* E, uint32_t* O, const uint32_t* a, uint32_t bi, bool first) {
+  constexpr int n = C::N;
+  if (first) {
+    row_mul<n>(O, a + 1, bi);
+    row_mul<n>(E, a, bi);
+  } else {
+    E[0] = ptx::add_cc(E[0], O[1]);
+    row_mad_shift<n>(O, Arr{a + 1}, bi);
+    row_mad<n>(E, Arr{a}, bi);
+    O[n - 1] = ptx::addc(O[n - 1], 0);
+  }
+  uint32_t m = E[0] * C::INV;
+  row_mad<n>(O, ModOdd<C>(), m);       // cannot carry out: total < 2^(32(n+1))
+  row_mad<n>(E, ModEven<C>(), m);
+  O[n - 1] = ptx::addc(O[n - 1], 0);
+}
+
+}  // namespace detail
+
+// Translation units off the hot loop define ZK_FMUL_NOINLINE: the multiplication becomes a real
+// call there (smaller code, much faster to compile); the hot accumulate kernel inlines it.
+#if defined(ZK_FMUL_NOINLINE) && defined(__CUDACC__)
+#define ZK_FMUL_ATTR __host__ __device__ __noinline__
+#else
+#define ZK_FMUL_ATTR ZK_HD
+#endif
+
+template <class C> ZK_FMUL_ATTR void fmul(Mont<C>& r, const Mont<C>& a, const Mont<C>& b) {
+  constexpr int n = C::N;
+  static_assert(n % 2 == 0, "even limb count");
+  uint32_t even[n], odd[n];
+#pragma unroll
+  for (int i = 0; i < n; i += 2) {
+    detail::mont_step<C>(even, odd, a.v, b.v[i], i == 0);
+    detail::mont_step<C>(odd, even, a.v, b.v[i + 1], false);
+  }
+  // last step used E = odd, O = even; E[0] == 0.  result = O + (E >> 32)  (< 2p)
+  uint32_t t[n];
+  t[0] = ptx::add_cc(even[0], odd[1]);
+#pragma unroll
+  for (int i = 1; i < n - 1; i++) t[i] = ptx::addc_cc(even[i], odd[i + 1]);
+  t[n - 1] = ptx::addc(even[n - 1], 0);
+  freduce_once(r, t);
+}
+
+template <class C> ZK_HD void fsqr(Mont<C>& r, const Mont<C>& a) { fmul(r, a, a); }
+
+// ---------------------------------------------------------------- conversions, inverse
+// canonical limbs (< p) -> Montgomery form
+template <class C> ZK_HD void fto_mont(Mont<C>& r, const uint32_t* canon) {
+  Mont<C> a, r2;
+#pragma unroll
+  for (int i = 0; i < C::N; i++) { a.v[i] = canon[i]; r2.v[i] = C::r2(i); }
+  fmul(r, a, r2);
+}
+// Montgomery form -> canonical limbs in [0, p)
+template <class C> ZK_HD void ffrom_mont(uint32_t* canon, const Mont<C>& a) {
+  Mont<C> one, r;
+  fset_zero(one);
+  one.v[0] = 1;
+  fmul(r, a, one);
+#pragma unroll
+  for (int i = 0; i < C::N; i++) canon[i] = r.v[i];
+}
+
+// a^(p-2) by left-to-right square-and-multiply (replaces the extended-Euclid inverse of
+// prime_field_elem.rs:379-432; same value since p is prime).  inv(0) = 0.
+template <class C> ZK_HD void finv(Mont<C>& r, const Mont<C>& a) {
+  Mont<C> acc;
+  fset_one(acc);
+  for (int i = C::N - 1; i >= 0; i--) {
+    uint32_t w = C::pm2(i);
+    for (int b = 31; b >= 0; b--) {
+      fsqr(acc, acc);
+      if ((w >> b) & 1) fmul(acc, acc, a);
+    }
+  }
+  r = acc;
+}
+
+}  // namespace zk

@@ -1,0 +1,59 @@
+// Kernel launch plumbing.  A pipeline stage is a "body" struct with
+//   static void run(uint32_t tid, Args...);
+// launched over nthreads logical threads by Launch<Body>::go.  The argument types are taken
+// from Body::run's own signature, so the only key of a launcher is the body type: translation
+// units that own a kernel define ZK_DEFINE_LAUNCH and explicitly instantiate
+//   template struct zk::LaunchBase<Body, decltype(Body::run)>;
+// every other translation unit only sees the declaration and links against it.  That keeps the
+// heavy field-arithmetic kernels in their own files, compiled in parallel.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace zk {
+
+static constexpr uint32_t kBlock = 128;
+
+template <class Body, class... A>
+__global__ void __launch_bounds__(kBlock) body_kernel(uint32_t nthreads, A... a) {
+  uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid < nthreads) Body::run(tid, a...);
+}
+
+template <class Body, class Sig> struct LaunchBase;
+template <class Body, class... A> struct LaunchBase<Body, void(uint32_t, A...)> {
+  static cudaError_t go(cudaStream_t st, uint32_t nthreads, A... a)
+#ifdef ZK_DEFINE_LAUNCH
+  {
+    body_kernel<Body, A...><<<(nthreads + kBlock - 1) / kBlock, kBlock, 0, st>>>(nthreads, a...);
+    return cudaGetLastError();
+  }
+#else
+      ;
+#endif
+};
+template <class Body> struct Launch : LaunchBase<Body, decltype(Body::run)> {};
+
+#define ZK_INSTANTIATE_KERNEL(...) template struct zk::LaunchBase<__VA_ARGS__, decltype(__VA_ARGS__::run)>
+
+// Exec policy for msm_launch (msm.cuh): stream-ordered CUDA launches
+struct CudaExec {
+  cudaStream_t st;
+  int launches;
+  cudaError_t err;
+  explicit CudaExec(cudaStream_t s) : st(s), launches(0), err(cudaSuccess) {}
+  template <class Body, class... Args>
+  void launch(uint32_t nthreads, Args... args) {
+    if (nthreads == 0 || err != cudaSuccess) return;
+    cudaError_t e = Launch<Body>::go(st, nthreads, args...);
+    launches++;
+    if (e != cudaSuccess) err = e;
+  }
+  void zero(void* p, size_t bytes) {
+    if (err != cudaSuccess || bytes == 0) return;
+    cudaError_t e = cudaMemsetAsync(p, 0, bytes, st);
+    if (e != cudaSuccess) err = e;
+  }
+};
+
+}  // namespace zk

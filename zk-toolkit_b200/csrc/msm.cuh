@@ -1,0 +1,456 @@
+// Pippenger multi-scalar multiplication  sum_i s_i * P_i  for sm_100a.
+//
+// Replaces the reference's serial loop `sum = sum + (&powers[i] * &self.coeffs[i])`
+// (Polynomial::eval_with_g1_hidings / eval_with_g2_hidings,
+// src/building_block/field/polynomial.rs:272-293) and the LSB-first affine double-and-add
+// it calls per term (impl_scalar_mul_point!, src/building_block/curves/macros.rs:2-32).
+//
+// Pipeline (every stage is a kernel "body": one logical thread = one call of Body::run):
+//   1 RecodeCount   scalar -> W signed c-bit digits; histogram of bucket sizes (atomics)
+//   2 Scan*         exclusive scan of the histogram -> bucket offsets, scatter cursors
+//   3 Scatter       counting sort: (bucket, +-point index) pairs grouped by bucket
+//   4 Accumulate    fixed-size chunks of L sorted pairs per thread, XYZZ mixed adds; a bucket
+//                   that spans several chunks leaves one head sum + per-chunk partial sums
+//   5 BucketFixup   per bucket: head + partials -> bucket sum (empty bucket -> infinity)
+//   6 BucketReduce  per K consecutive buckets: sum_j (j+1) * bucket_j by running sums
+//   7 PairSum       pairwise tree over the chunk results of each window -> window sums
+//   8 Finish        Horner over windows (c doublings each), to canonical affine
+//
+// Work is independent of the scalar distribution: stage 4 always runs ceil(total/L) threads of
+// <= L mixed adds, so all-equal scalars or duplicate points cost no more than random ones
+// (the group law in ec.cuh is complete, so P+P and P+(-P) inside a bucket are exact).
+//
+// "Precomputed" point sets (built once when the CRS is loaded) hold 2^(c w) P_i for every
+// window w; then all windows share ONE bucket set and stage 8 needs no doublings.
+//
+// The bodies are plain functions of (tid, args) so that tests/host_emu can run the identical
+// pipeline on the CPU (test infrastructure only); the product launches them as CUDA kernels.
+#pragma once
+#include "ec.cuh"
+
+namespace zk {
+
+#if defined(__CUDA_ARCH__)
+ZK_D uint32_t zk_atomic_add(uint32_t* p, uint32_t v) { return atomicAdd(p, v); }
+ZK_D void zk_atomic_or(uint32_t* p, uint32_t v) { atomicOr(p, v); }
+#else
+inline uint32_t zk_atomic_add(uint32_t* p, uint32_t v) { uint32_t o = *p; *p = o + v; return o; }
+inline void zk_atomic_or(uint32_t* p, uint32_t v) { *p |= v; }
+#endif
+
+struct G1 { typedef Fp F; static constexpr int AFF_LIMBS = 24; };
+struct G2 { typedef Fp2 F; static constexpr int AFF_LIMBS = 48; };
+
+static constexpr int SCALAR_LIMBS = 8;
+static constexpr uint32_t ERR_SCALAR_RANGE = 1u;  // a scalar had bit 255 set
+
+struct MsmPlan {
+  uint32_t n;          // terms
+  uint32_t c;          // window bits
+  uint32_t W;          // windows = floor(255 / c) + 1
+  uint32_t B;          // buckets per window = 2^(c-1)
+  uint32_t nwin;       // bucket sets: W, or 1 with precomputed points
+  uint32_t nb;         // total buckets = nwin * B
+  uint32_t precomp;    // 1: points array holds W slabs of `stride` points, slab w = 2^(c w) P
+  uint32_t stride;     // points per slab
+  uint32_t L;          // sorted pairs per accumulate thread
+  uint32_t K;          // buckets per reduce thread (power of two, divides B)
+  uint32_t max_entries;   // n * W
+  uint32_t acc_threads;   // ceil(max_entries / L)
+};
+
+// ---------------------------------------------------------------- signed-digit recoding
+// digits d_w in [-(2^(c-1) - 1), 2^(c-1)], sum_w d_w 2^(c w) = scalar (scalar < 2^255)
+struct Digits {
+  const uint32_t* s;
+  uint32_t c, carry;
+  ZK_HD Digits(const uint32_t* scalar, uint32_t c_) : s(scalar), c(c_), carry(0) {}
+  ZK_HD int32_t next(uint32_t w) {
+    uint32_t bit = w * c, limb = bit >> 5, sh = bit & 31;
+    uint32_t v = 0;
+    if (limb < SCALAR_LIMBS) {
+      v = s[limb] >> sh;
+      if (sh + c > 32 && limb + 1 < SCALAR_LIMBS) v |= s[limb + 1] << (32 - sh);
+    }
+    v = (v & ((1u << c) - 1)) + carry;
+    if (v > (1u << (c - 1))) { carry = 1; return (int32_t)v - (int32_t)(1u << c); }
+    carry = 0;
+    return (int32_t)v;
+  }
+};
+
+struct RecodeCount {
+  static ZK_HD void run(uint32_t tid, MsmPlan p, const uint32_t* scalars, uint32_t* hist, uint32_t* err) {
+    if (tid >= p.n) return;
+    uint32_t s[SCALAR_LIMBS];
+#pragma unroll
+    for (int i = 0; i < SCALAR_LIMBS; i++) s[i] = scalars[(size_t)tid * SCALAR_LIMBS + i];
+    if (s[SCALAR_LIMBS - 1] >> 31) { zk_atomic_or(err, ERR_SCALAR_RANGE); return; }
+    Digits dg(s, p.c);
+    for (uint32_t w = 0; w < p.W; w++) {
+      int32_t d = dg.next(w);
+      if (d == 0) continue;
+      uint32_t mag = (uint32_t)(d < 0 ? -d : d) - 1;
+      zk_atomic_add(&hist[(p.precomp ? 0 : w * p.B) + mag], 1u);
+    }
+  }
+};
+
+// ---------------------------------------------------------------- exclusive scan (3 small kernels)
+static constexpr uint32_t SCAN_SEG = 256;
+
+struct ScanLocal {  // thread t: sum of hist[t*SEG .. (t+1)*SEG)
+  static ZK_HD void run(uint32_t tid, uint32_t nb, const uint32_t* hist, uint32_t* segsum) {
+    uint32_t beg = tid * SCAN_SEG;
+    if (beg >= nb) return;
+    uint32_t end = beg + SCAN_SEG < nb ? beg + SCAN_SEG : nb, s = 0;
+    for (uint32_t i = beg; i < end; i++) s += hist[i];
+    segsum[tid] = s;
+  }
+};
+struct ScanTop {  // one thread: exclusive scan of the segment sums; grand total -> offsets[nb]
+  static ZK_HD void run(uint32_t tid, uint32_t nseg, uint32_t nb, uint32_t* segsum, uint32_t* offsets) {
+    if (tid != 0) return;
+    uint32_t run = 0;
+    for (uint32_t i = 0; i < nseg; i++) { uint32_t v = segsum[i]; segsum[i] = run; run += v; }
+    offsets[nb] = run;
+  }
+};
+struct ScanApply {  // offsets[] and the scatter cursors (cursor aliases hist)
+  static ZK_HD void run(uint32_t tid, uint32_t nb, uint32_t* hist_cursor, const uint32_t* segsum, uint32_t* offsets) {
+    uint32_t beg = tid * SCAN_SEG;
+    if (beg >= nb) return;
+    uint32_t end = beg + SCAN_SEG < nb ? beg + SCAN_SEG : nb, run = segsum[tid];
+    for (uint32_t i = beg; i < end; i++) { uint32_t v = hist_cursor[i]; offsets[i] = run; hist_cursor[i] = run; run += v; }
+  }
+};
+
+// ---------------------------------------------------------------- counting-sort scatter
+struct alignas(8) Entry { uint32_t key, val; };  // val = point index | sign << 31
+
+struct Scatter {
+  static ZK_HD void run(uint32_t tid, MsmPlan p, const uint32_t* scalars, uint32_t* cursor, Entry* entries) {
+    if (tid >= p.n) return;
+    uint32_t s[SCALAR_LIMBS];
+#pragma unroll
+    for (int i = 0; i < SCALAR_LIMBS; i++) s[i] = scalars[(size_t)tid * SCALAR_LIMBS + i];
+    if (s[SCALAR_LIMBS - 1] >> 31) return;
+    Digits dg(s, p.c);
+    for (uint32_t w = 0; w < p.W; w++) {
+      int32_t d = dg.next(w);
+      if (d == 0) continue;
+      uint32_t neg = d < 0, mag = (uint32_t)(neg ? -d : d) - 1;
+      uint32_t key = (p.precomp ? 0 : w * p.B) + mag;
+      uint32_t idx = p.precomp ? w * p.stride + tid : tid;
+      uint32_t pos = zk_atomic_add(&cursor[key], 1u);
+      Entry e; e.key = key; e.val = idx | (neg << 31);
+      entries[pos] = e;
+    }
+  }
+};
+
+// ---------------------------------------------------------------- bucket accumulation
+template <class C> struct Accumulate {
+  typedef typename C::F F;
+  static ZK_HD void run(uint32_t tid, MsmPlan p, const uint32_t* offsets, const Entry* entries,
+                        const Affine<F>* points, XYZZ<F>* bucket_sums, XYZZ<F>* partials) {
+    uint32_t total = offsets[p.nb];
+    uint64_t beg64 = (uint64_t)tid * p.L;
+    if (beg64 >= total) return;
+    uint32_t beg = (uint32_t)beg64, end = beg + p.L < total ? beg + p.L : total;
+    uint32_t key = entries[beg].key;
+    bool head = beg == 0 || entries[beg - 1].key != key;   // segment starts its bucket?
+    XYZZ<F> acc;
+    set_inf(acc);
+    for (uint32_t pos = beg; pos < end; pos++) {
+      Entry e = entries[pos];
+      if (e.key != key) {
+        if (head) bucket_sums[key] = acc; else partials[tid] = acc;
+        set_inf(acc);
+        key = e.key;
+        head = true;
+      }
+      Affine<F> q = points[e.val & 0x7fffffffu];
+      affine_cneg(q, (e.val >> 31) != 0);
+      xyzz_madd(acc, q);
+    }
+    if (head) bucket_sums[key] = acc; else partials[tid] = acc;
+  }
+};
+
+template <class C> struct BucketFixup {
+  typedef typename C::F F;
+  static ZK_HD void run(uint32_t tid, MsmPlan p, const uint32_t* offsets, XYZZ<F>* bucket_sums, const XYZZ<F>* partials) {
+    if (tid >= p.nb) return;
+    uint32_t beg = offsets[tid], end = offsets[tid + 1];
+    if (beg == end) { XYZZ<F> z; set_inf(z); bucket_sums[tid] = z; return; }
+    uint32_t t0 = beg / p.L, t1 = (end - 1) / p.L;
+    if (t1 == t0) return;
+    XYZZ<F> acc = bucket_sums[tid];
+    for (uint32_t t = t0 + 1; t <= t1; t++) { XYZZ<F> q = partials[t]; xyzz_add(acc, q); }
+    bucket_sums[tid] = acc;
+  }
+};
+
+// p = s * p for a small scalar (left-to-right double-and-add)
+template <class F> ZK_HD void xyzz_mul_small(XYZZ<F>& p, uint32_t s) {
+  if (s == 0) { set_inf(p); return; }
+  XYZZ<F> base = p;
+  int top = 31;
+  while (!((s >> top) & 1)) top--;
+  for (int b = top - 1; b >= 0; b--) {
+    xyzz_dbl(p);
+    if ((s >> b) & 1) xyzz_add(p, base);
+  }
+}
+
+// thread (win, k): out = sum_{i<K} (k K + i + 1) * bucket[win*B + k*K + i]
+template <class C> struct BucketReduce {
+  typedef typename C::F F;
+  static ZK_HD void run(uint32_t tid, MsmPlan p, const XYZZ<F>* bucket_sums, XYZZ<F>* out) {
+    uint32_t chunks = p.B / p.K;
+    if (tid >= p.nwin * chunks) return;
+    uint32_t win = tid / chunks, k = tid % chunks;
+    const XYZZ<F>* b = bucket_sums + (size_t)win * p.B + (size_t)k * p.K;
+    XYZZ<F> run, acc;
+    set_inf(run);
+    set_inf(acc);
+    for (int i = (int)p.K - 1; i >= 0; i--) {
+      XYZZ<F> q = b[i];
+      xyzz_add(run, q);
+      xyzz_add(acc, run);
+    }
+    xyzz_mul_small(run, k * p.K);
+    xyzz_add(acc, run);
+    out[tid] = acc;
+  }
+};
+
+// level of the pairwise tree: arr is nwin rows of `m` points (row pitch `pitch`); row[i] += row[i + half]
+template <class C> struct PairSum {
+  typedef typename C::F F;
+  static ZK_HD void run(uint32_t tid, uint32_t nwin, uint32_t pitch, uint32_t m, uint32_t half, XYZZ<F>* arr) {
+    if (tid >= nwin * half) return;
+    uint32_t win = tid / half, i = tid % half;
+    if (i + half >= m) return;
+    XYZZ<F>* row = arr + (size_t)win * pitch;
+    XYZZ<F> a = row[i], b = row[i + half];
+    xyzz_add(a, b);
+    row[i] = a;
+  }
+};
+
+template <class F> ZK_HD void store_canonical(uint32_t* out, const Affine<F>& a);
+template <> ZK_HD void store_canonical<Fp>(uint32_t* out, const Affine<Fp>& a) {
+  ffrom_mont(out, a.x); ffrom_mont(out + 12, a.y);
+}
+template <> ZK_HD void store_canonical<Fp2>(uint32_t* out, const Affine<Fp2>& a) {
+  ffrom_mont(out, a.x.c0); ffrom_mont(out + 12, a.x.c1); ffrom_mont(out + 24, a.y.c0); ffrom_mont(out + 36, a.y.c1);
+}
+template <class F> ZK_HD void load_canonical(Affine<F>& a, const uint32_t* in);
+template <> ZK_HD void load_canonical<Fp>(Affine<Fp>& a, const uint32_t* in) {
+  fto_mont(a.x, in); fto_mont(a.y, in + 12);
+}
+template <> ZK_HD void load_canonical<Fp2>(Affine<Fp2>& a, const uint32_t* in) {
+  fto_mont(a.x.c0, in); fto_mont(a.x.c1, in + 12); fto_mont(a.y.c0, in + 24); fto_mont(a.y.c1, in + 36);
+}
+
+// Horner over the window sums (row w of arr, element 0), then optional canonical affine output.
+// out_xyzz (Montgomery XYZZ, for multi-GPU partials) and out_affine (canonical limbs + flag) may be null.
+template <class C> struct Finish {
+  typedef typename C::F F;
+  static ZK_HD void run(uint32_t tid, uint32_t nwin, uint32_t pitch, uint32_t c, const XYZZ<F>* arr,
+                        XYZZ<F>* out_xyzz, uint32_t* out_affine, uint32_t* out_inf) {
+    if (tid != 0) return;
+    XYZZ<F> acc = arr[(size_t)(nwin - 1) * pitch];
+    for (int w = (int)nwin - 2; w >= 0; w--) {
+      for (uint32_t i = 0; i < c; i++) xyzz_dbl(acc);
+      XYZZ<F> q = arr[(size_t)w * pitch];
+      xyzz_add(acc, q);
+    }
+    if (out_xyzz) *out_xyzz = acc;
+    if (out_affine) {
+      Affine<F> a;
+      xyzz_to_affine(a, acc);
+      store_canonical<F>(out_affine, a);
+      *out_inf = is_inf(acc) ? 1u : 0u;
+    }
+  }
+};
+
+// sum of k XYZZ partial results (multi-GPU combine) -> canonical affine
+template <class C> struct CombinePartials {
+  typedef typename C::F F;
+  static ZK_HD void run(uint32_t tid, uint32_t k, const XYZZ<F>* parts, uint32_t* out_affine, uint32_t* out_inf) {
+    if (tid != 0) return;
+    XYZZ<F> acc;
+    set_inf(acc);
+    for (uint32_t i = 0; i < k; i++) { XYZZ<F> q = parts[i]; xyzz_add(acc, q); }
+    Affine<F> a;
+    xyzz_to_affine(a, acc);
+    store_canonical<F>(out_affine, a);
+    *out_inf = is_inf(acc) ? 1u : 0u;
+  }
+};
+
+// ---------------------------------------------------------------- point-set preparation
+// canonical affine limbs (+ optional infinity flags) -> Montgomery affine, slab 0
+template <class C> struct LoadPoints {
+  typedef typename C::F F;
+  static ZK_HD void run(uint32_t tid, uint32_t n, const uint32_t* canon, const uint8_t* inf, Affine<F>* out) {
+    if (tid >= n) return;
+    Affine<F> a;
+    if (inf && inf[tid]) set_inf(a);
+    else load_canonical<F>(a, canon + (size_t)tid * C::AFF_LIMBS);
+    out[tid] = a;
+  }
+};
+
+// slab w = 2^c * slab (w-1), w = 1 .. W-1 (one thread per point walks all levels)
+template <class C> struct PrecomputeSlabs {
+  typedef typename C::F F;
+  static ZK_HD void run(uint32_t tid, uint32_t n, uint32_t stride, uint32_t c, uint32_t W, Affine<F>* pts) {
+    if (tid >= n) return;
+    Affine<F> a = pts[tid];
+    for (uint32_t w = 1; w < W; w++) {
+      if (!is_inf(a)) {
+        XYZZ<F> x;
+        xyzz_mdbl(x, a);
+        for (uint32_t i = 1; i < c; i++) xyzz_dbl(x);
+        xyzz_to_affine(a, x);
+      }
+      pts[(size_t)w * stride + tid] = a;
+    }
+  }
+};
+
+// ---------------------------------------------------------------- fixed-base scalar multiplication
+// (the reference's `g * k`, impl_scalar_mul_point!, macros.rs:2-32, for many k at once; used for
+//  CRS-style point generation, crs.rs:88-116)
+// table[j] = 2^j * base, j < 256, built by one thread then converted to affine in parallel
+template <class C> struct BaseTableChain {
+  typedef typename C::F F;
+  static ZK_HD void run(uint32_t tid, const uint32_t* base_canon, XYZZ<F>* chain) {
+    if (tid != 0) return;
+    Affine<F> a;
+    load_canonical<F>(a, base_canon);
+    XYZZ<F> x;
+    from_affine(x, a);
+    for (int j = 0; j < 256; j++) { chain[j] = x; xyzz_dbl(x); }
+  }
+};
+template <class C> struct BaseTableAffine {
+  typedef typename C::F F;
+  static ZK_HD void run(uint32_t tid, const XYZZ<F>* chain, Affine<F>* table) {
+    if (tid >= 256) return;
+    Affine<F> a;
+    xyzz_to_affine(a, chain[tid]);
+    table[tid] = a;
+  }
+};
+// out[i] = scalars[i] * base as Montgomery affine ((0,0) for infinity); full 256-bit scalars
+template <class C> struct FixedBaseMul {
+  typedef typename C::F F;
+  static ZK_HD void run(uint32_t tid, uint32_t n, const uint32_t* scalars, const Affine<F>* table, Affine<F>* out) {
+    if (tid >= n) return;
+    XYZZ<F> acc;
+    set_inf(acc);
+    for (int limb = 0; limb < SCALAR_LIMBS; limb++) {
+      uint32_t w = scalars[(size_t)tid * SCALAR_LIMBS + limb];
+      for (int b = 0; b < 32; b++) {
+        if ((w >> b) & 1) { Affine<F> q = table[limb * 32 + b]; xyzz_madd(acc, q); }
+      }
+    }
+    Affine<F> a;
+    xyzz_to_affine(a, acc);
+    out[tid] = a;
+  }
+};
+// Montgomery affine -> canonical limbs + infinity flags (inverse of LoadPoints)
+template <class C> struct StorePoints {
+  typedef typename C::F F;
+  static ZK_HD void run(uint32_t tid, uint32_t n, const Affine<F>* in, uint32_t* canon, uint8_t* inf) {
+    if (tid >= n) return;
+    Affine<F> a = in[tid];
+    store_canonical<F>(canon + (size_t)tid * C::AFF_LIMBS, a);
+    if (inf) inf[tid] = is_inf(a) ? 1 : 0;
+  }
+};
+
+// ---------------------------------------------------------------- planning
+inline uint32_t msm_windows(uint32_t c) { return 255 / c + 1; }
+
+// cost model in mixed-add units: n*W accumulate + ~5 add-equivalents per bucket (fix-up, two
+// running-sum adds at 1.4x a mixed add each), used only to pick c
+inline uint32_t msm_pick_c(uint32_t n, bool precomp) {
+  uint32_t best = 8;
+  double best_cost = 1e300;
+  for (uint32_t c = 3; c <= 22; c++) {
+    double W = msm_windows(c), B = (double)(1u << (c - 1));
+    double cost = W * n + 5.0 * B * (precomp ? 1.0 : W);
+    if (cost < best_cost) { best_cost = cost; best = c; }
+  }
+  return best;
+}
+
+inline MsmPlan msm_plan(uint32_t n, uint32_t c, bool precomp, uint32_t stride) {
+  MsmPlan p;
+  p.n = n;
+  p.c = c;
+  p.W = msm_windows(c);
+  p.B = 1u << (c - 1);
+  p.precomp = precomp ? 1 : 0;
+  p.nwin = precomp ? 1 : p.W;
+  p.nb = p.nwin * p.B;
+  p.stride = stride;
+  p.max_entries = n * p.W;
+  p.L = p.max_entries >= (1u << 23) ? 32 : (p.max_entries >= (1u << 21) ? 16 : 8);
+  p.K = p.B >= 4096 ? 16 : (p.B >= 16 ? 8 : p.B);
+  p.acc_threads = (p.max_entries + p.L - 1) / p.L;
+  if (p.acc_threads == 0) p.acc_threads = 1;
+  return p;
+}
+
+// device buffers one MSM needs (sizes in elements), all owned by the caller
+template <class C> struct MsmBuffers {
+  typedef typename C::F F;
+  uint32_t* hist_cursor;   // nb
+  uint32_t* offsets;       // nb + 1
+  uint32_t* segsum;        // ceil(nb / SCAN_SEG)
+  Entry* entries;          // max_entries
+  XYZZ<F>* bucket_sums;    // nb
+  XYZZ<F>* partials;       // acc_threads
+  XYZZ<F>* reduced;        // nwin * (B / K)
+  uint32_t* err;           // 1
+};
+
+// The launch sequence.  Exec::launch<Body>(nthreads, args...) runs Body::run(tid, args...) for
+// tid in [0, nthreads); Exec::zero(ptr, bytes) clears device memory (both stream-ordered).
+template <class C, class Exec>
+void msm_launch(Exec& ex, const MsmPlan& p, const MsmBuffers<C>& b, const Affine<typename C::F>* points,
+                const uint32_t* d_scalars, XYZZ<typename C::F>* out_xyzz, uint32_t* out_affine, uint32_t* out_inf) {
+  uint32_t nseg = (p.nb + SCAN_SEG - 1) / SCAN_SEG;
+  ex.zero(b.hist_cursor, sizeof(uint32_t) * p.nb);
+  ex.zero(b.err, sizeof(uint32_t));
+  ex.template launch<RecodeCount>(p.n, p, d_scalars, b.hist_cursor, b.err);
+  ex.template launch<ScanLocal>(nseg, p.nb, (const uint32_t*)b.hist_cursor, b.segsum);
+  ex.template launch<ScanTop>(1u, nseg, p.nb, b.segsum, b.offsets);
+  ex.template launch<ScanApply>(nseg, p.nb, b.hist_cursor, (const uint32_t*)b.segsum, b.offsets);
+  ex.template launch<Scatter>(p.n, p, d_scalars, b.hist_cursor, b.entries);
+  ex.template launch<Accumulate<C>>(p.acc_threads, p, (const uint32_t*)b.offsets, (const Entry*)b.entries, points,
+                                    b.bucket_sums, b.partials);
+  ex.template launch<BucketFixup<C>>(p.nb, p, (const uint32_t*)b.offsets, b.bucket_sums,
+                                     (const XYZZ<typename C::F>*)b.partials);
+  uint32_t chunks = p.B / p.K;
+  ex.template launch<BucketReduce<C>>(p.nwin * chunks, p, (const XYZZ<typename C::F>*)b.bucket_sums, b.reduced);
+  uint32_t m = chunks;
+  while (m > 1) {
+    uint32_t half = (m + 1) / 2;
+    ex.template launch<PairSum<C>>(p.nwin * half, p.nwin, chunks, m, half, b.reduced);
+    m = half;
+  }
+  ex.template launch<Finish<C>>(1u, p.nwin, chunks, p.c, (const XYZZ<typename C::F>*)b.reduced, out_xyzz, out_affine,
+                                out_inf);
+}
+
+}  // namespace zk

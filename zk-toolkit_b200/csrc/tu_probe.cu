@@ -1,0 +1,67 @@
+// integer-multiply throughput probe (roofline denominator)
+#include <cuda_runtime.h>
+#include "fp.cuh"
+using namespace zk;
+
+template <int VARIANT>
+__global__ void __launch_bounds__(256) imad_probe(uint32_t* sink, uint32_t seed, int iters) {
+  uint32_t x = seed ^ (blockIdx.x * blockDim.x + threadIdx.x), y = x * 2654435761u + 12345u;
+  if (VARIANT == 0) {          // 8 independent 64-bit accumulators: IMAD.WIDE.U32
+    uint64_t a[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) a[k] = x + k;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+      for (int r = 0; r < 4; r++) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a[k]) : "r"(x + k), "r"(y));
+      }
+    }
+    uint64_t s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) s ^= a[k];
+    if (s == 0x123456789ull) sink[0] = (uint32_t)s;
+  } else if (VARIANT == 1) {   // two interleaved 6-digit carry chains, as in fp.cuh's row_mad
+    uint32_t e[12], o[12], xs[6];
+#pragma unroll
+    for (int k = 0; k < 12; k++) { e[k] = x + k; o[k] = y + k; }
+#pragma unroll
+    for (int k = 0; k < 6; k++) xs[k] = x * (k + 3);
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+      for (int r = 0; r < 2; r++) {
+        detail::row_mad<12>(o, detail::Arr{xs}, y);
+        detail::row_mad<12>(e, detail::Arr{xs}, y + 1);
+        // fold the carry flag in so the chain cannot be dropped, and perturb the multiplier
+        y += ptx::addc(0, 0);
+      }
+    }
+    uint32_t s = 0;
+#pragma unroll
+    for (int k = 0; k < 12; k++) s ^= e[k] ^ o[k];
+    if (s == 0x12345678u) sink[0] = s;
+  } else {                     // 16 independent 32-bit IMAD
+    uint32_t a[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) a[k] = x + k;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+      for (int r = 0; r < 2; r++) {
+#pragma unroll
+        for (int k = 0; k < 16; k++) asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(a[k]) : "r"(a[k] | 1u), "r"(y));
+      }
+    }
+    uint32_t s = 0;
+#pragma unroll
+    for (int k = 0; k < 16; k++) s ^= a[k];
+    if (s == 0x12345678u) sink[0] = s;
+  }
+}
+
+
+extern "C" int zkmsm_probe_launch(int variant, int grid, int block, cudaStream_t st, uint32_t* sink, int iters) {
+  if (variant == 0) imad_probe<0><<<grid, block, 0, st>>>(sink, 7u, iters);
+  else if (variant == 1) imad_probe<1><<<grid, block, 0, st>>>(sink, 7u, iters);
+  else imad_probe<2><<<grid, block, 0, st>>>(sink, 7u, iters);
+  return (int)cudaGetLastError();
+}

@@ -1,0 +1,560 @@
+// C ABI (include/zkmsm.h) over the sm_100a kernels of msm.cuh.  No CPU compute path exists in
+// this library: without a usable CUDA device every entry point returns an error.
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+
+#include "../../include/zkmsm.h"
+#include "launch.cuh"
+#include "msm.cuh"
+
+using namespace zk;
+
+// ------------------------------------------------------------------------------------------------
+
+// ------------------------------------------------------------------------------------------------
+enum { WS_HIST, WS_OFFSETS, WS_SEGSUM, WS_ENTRIES, WS_BUCKETS, WS_PARTIALS, WS_REDUCED, WS_SCALARS, WS_MISC, WS_COUNT };
+
+struct alignas(16) ResultBlock {      // device + pinned host mirror
+  uint32_t xyzz[96];      // first: XYZZ<F> needs 16-byte alignment
+  uint32_t affine[48];
+  uint32_t inf;
+  uint32_t err;
+};
+
+struct zkmsm_ctx {
+  int device;
+  cudaStream_t own_stream, stream;
+  char err[512];
+  unsigned window_override;
+  void* ws[WS_COUNT];
+  size_t ws_bytes[WS_COUNT];
+  ResultBlock* d_res;
+  ResultBlock* h_res;
+  int last_launches;
+  int pending;          // 0 none, 1 kernels enqueued, 2 trivially infinity (n == 0)
+  int pending_words;    // 24 or 48
+};
+
+struct zkmsm_points {
+  int curve;            // 1 = G1, 2 = G2
+  int device;
+  size_t n;             // points per slab
+  unsigned c, W;        // window layout of the slabs (precomputed sets)
+  bool precomp;
+  void* d_pts;          // Affine<F>[W * n] (precomp) or Affine<F>[n]
+};
+
+static int fail(zkmsm_ctx* ctx, int code, const char* fmt, ...) {
+  if (ctx) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(ctx->err, sizeof(ctx->err), fmt, ap);
+    va_end(ap);
+  }
+  return code;
+}
+#define CU(ctx, call)                                                                                   \
+  do {                                                                                                  \
+    cudaError_t e__ = (call);                                                                           \
+    if (e__ != cudaSuccess) return fail(ctx, ZKMSM_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e__)); \
+  } while (0)
+
+static int ws_reserve(zkmsm_ctx* ctx, int slot, size_t bytes) {
+  if (bytes == 0) bytes = 16;
+  if (ctx->ws_bytes[slot] >= bytes) return ZKMSM_OK;
+  if (ctx->ws[slot]) {
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    CU(ctx, cudaFree(ctx->ws[slot]));
+    ctx->ws[slot] = nullptr;
+    ctx->ws_bytes[slot] = 0;
+  }
+  size_t want = bytes + bytes / 8;
+  cudaError_t e = cudaMalloc(&ctx->ws[slot], want);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    want = bytes;
+    e = cudaMalloc(&ctx->ws[slot], want);
+  }
+  if (e != cudaSuccess) return fail(ctx, ZKMSM_ERR_NOMEM, "cudaMalloc(%zu): %s", want, cudaGetErrorString(e));
+  ctx->ws_bytes[slot] = want;
+  return ZKMSM_OK;
+}
+
+extern "C" const char* zkmsm_version(void) { return "zkmsm 0.1 (sm_100a; BLS12-381 G1/G2 Pippenger, XYZZ, 12x32-bit Montgomery)"; }
+
+extern "C" int zkmsm_create(int device, zkmsm_ctx** out) {
+  if (!out) return ZKMSM_ERR_INVALID_ARG;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) { cudaGetLastError(); return ZKMSM_ERR_NO_DEVICE; }
+  if (device < 0 || device >= count) return ZKMSM_ERR_INVALID_ARG;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return ZKMSM_ERR_CUDA;
+  if (prop.major != 10) return ZKMSM_ERR_NO_DEVICE;  // the only code in this library is sm_100a SASS
+  zkmsm_ctx* ctx = new (std::nothrow) zkmsm_ctx();
+  if (!ctx) return ZKMSM_ERR_NOMEM;
+  memset(ctx, 0, sizeof(*ctx));
+  ctx->device = device;
+  strcpy(ctx->err, "ok");
+  if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaMalloc(&ctx->d_res, sizeof(ResultBlock)) != cudaSuccess ||
+      cudaMallocHost(&ctx->h_res, sizeof(ResultBlock)) != cudaSuccess) {
+    delete ctx;
+    return ZKMSM_ERR_CUDA;
+  }
+  ctx->stream = ctx->own_stream;
+  *out = ctx;
+  return ZKMSM_OK;
+}
+
+extern "C" int zkmsm_destroy(zkmsm_ctx* ctx) {
+  if (!ctx) return ZKMSM_ERR_INVALID_ARG;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (int i = 0; i < WS_COUNT; i++)
+    if (ctx->ws[i]) cudaFree(ctx->ws[i]);
+  cudaFree(ctx->d_res);
+  cudaFreeHost(ctx->h_res);
+  cudaStreamDestroy(ctx->own_stream);
+  delete ctx;
+  return ZKMSM_OK;
+}
+
+extern "C" int zkmsm_set_stream(zkmsm_ctx* ctx, void* s) {
+  if (!ctx) return ZKMSM_ERR_INVALID_ARG;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  ctx->stream = s ? (cudaStream_t)s : ctx->own_stream;
+  return ZKMSM_OK;
+}
+
+extern "C" const char* zkmsm_last_error(const zkmsm_ctx* ctx) { return ctx ? ctx->err : "null context"; }
+
+extern "C" int zkmsm_set_window(zkmsm_ctx* ctx, unsigned c) {
+  if (!ctx || (c != 0 && (c < 3 || c > 22))) return ZKMSM_ERR_INVALID_ARG;
+  ctx->window_override = c;
+  return ZKMSM_OK;
+}
+
+extern "C" int zkmsm_host_alloc(size_t bytes, void** out) {
+  if (!out) return ZKMSM_ERR_INVALID_ARG;
+  return cudaMallocHost(out, bytes ? bytes : 16) == cudaSuccess ? ZKMSM_OK : ZKMSM_ERR_CUDA;
+}
+extern "C" int zkmsm_host_free(void* p) { return cudaFreeHost(p) == cudaSuccess ? ZKMSM_OK : ZKMSM_ERR_CUDA; }
+
+extern "C" int zkmsm_last_launch_count(const zkmsm_ctx* ctx) { return ctx ? ctx->last_launches : 0; }
+
+// ------------------------------------------------------------------------------------------------
+// point sets
+template <class C>
+static int finish_point_set(zkmsm_ctx* ctx, zkmsm_points* ps, CudaExec& ex) {
+  typedef typename C::F F;
+  if (ps->precomp && ps->n > 0)
+    ex.template launch<PrecomputeSlabs<C>>((uint32_t)ps->n, (uint32_t)ps->n, (uint32_t)ps->n, ps->c, ps->W,
+                                           (Affine<F>*)ps->d_pts);
+  if (ex.err != cudaSuccess) return fail(ctx, ZKMSM_ERR_CUDA, "point set kernels: %s", cudaGetErrorString(ex.err));
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  return ZKMSM_OK;
+}
+
+template <class C>
+static int alloc_point_set(zkmsm_ctx* ctx, size_t n, unsigned flags, int curve, zkmsm_points** out) {
+  typedef typename C::F F;
+  if (!ctx || !out || n > (1u << 26)) return fail(ctx, ZKMSM_ERR_INVALID_ARG, "bad argument");
+  *out = nullptr;
+  CU(ctx, cudaSetDevice(ctx->device));
+  zkmsm_points* ps = new (std::nothrow) zkmsm_points();
+  if (!ps) return fail(ctx, ZKMSM_ERR_NOMEM, "host allocation");
+  ps->curve = curve;
+  ps->device = ctx->device;
+  ps->n = n;
+  ps->precomp = (flags & ZKMSM_PRECOMPUTE) != 0 && n > 0;
+  ps->c = ps->precomp ? (ctx->window_override ? ctx->window_override : msm_pick_c((uint32_t)n, true)) : 0;
+  ps->W = ps->precomp ? msm_windows(ps->c) : 1;
+  size_t slabs = ps->precomp ? ps->W : 1;
+  if ((uint64_t)slabs * n >= (1ull << 31)) { delete ps; return fail(ctx, ZKMSM_ERR_INVALID_ARG, "point set too large"); }
+  size_t bytes = sizeof(Affine<F>) * slabs * (n ? n : 1);
+  cudaError_t e = cudaMalloc(&ps->d_pts, bytes);
+  if (e != cudaSuccess) { delete ps; return fail(ctx, ZKMSM_ERR_NOMEM, "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e)); }
+  *out = ps;
+  return ZKMSM_OK;
+}
+
+template <class C>
+static int load_points_impl(zkmsm_ctx* ctx, const uint32_t* xy, const uint8_t* inf, size_t n, unsigned flags, int curve,
+                            zkmsm_points** out) {
+  typedef typename C::F F;
+  if (n > 0 && !xy) return fail(ctx, ZKMSM_ERR_INVALID_ARG, "null points");
+  int rc = alloc_point_set<C>(ctx, n, flags, curve, out);
+  if (rc) return rc;
+  zkmsm_points* ps = *out;
+  if (n == 0) return ZKMSM_OK;
+  size_t cbytes = sizeof(uint32_t) * C::AFF_LIMBS * n;
+  rc = ws_reserve(ctx, WS_MISC, cbytes + n);
+  if (rc) { zkmsm_points_free(ctx, ps); *out = nullptr; return rc; }
+  uint32_t* d_canon = (uint32_t*)ctx->ws[WS_MISC];
+  uint8_t* d_inf = inf ? (uint8_t*)ctx->ws[WS_MISC] + cbytes : nullptr;
+  CU(ctx, cudaMemcpyAsync(d_canon, xy, cbytes, cudaMemcpyHostToDevice, ctx->stream));
+  if (inf) CU(ctx, cudaMemcpyAsync(d_inf, inf, n, cudaMemcpyHostToDevice, ctx->stream));
+  CudaExec ex(ctx->stream);
+  ex.template launch<LoadPoints<C>>((uint32_t)n, (uint32_t)n, (const uint32_t*)d_canon, (const uint8_t*)d_inf,
+                                    (Affine<F>*)ps->d_pts);
+  rc = finish_point_set<C>(ctx, ps, ex);
+  if (rc) { zkmsm_points_free(ctx, ps); *out = nullptr; }
+  return rc;
+}
+
+extern "C" int zkmsm_g1_load_points(zkmsm_ctx* ctx, const uint32_t* xy, const uint8_t* inf, size_t n, unsigned flags,
+                                    zkmsm_points** out) {
+  return load_points_impl<G1>(ctx, xy, inf, n, flags, 1, out);
+}
+extern "C" int zkmsm_g2_load_points(zkmsm_ctx* ctx, const uint32_t* xy, const uint8_t* inf, size_t n, unsigned flags,
+                                    zkmsm_points** out) {
+  return load_points_impl<G2>(ctx, xy, inf, n, flags, 2, out);
+}
+
+extern "C" int zkmsm_points_free(zkmsm_ctx* ctx, zkmsm_points* ps) {
+  if (!ps) return ZKMSM_ERR_INVALID_ARG;
+  cudaSetDevice(ps->device);
+  if (ctx) cudaStreamSynchronize(ctx->stream);
+  if (ps->d_pts) cudaFree(ps->d_pts);
+  delete ps;
+  return ZKMSM_OK;
+}
+
+extern "C" size_t zkmsm_points_len(const zkmsm_points* ps) { return ps ? ps->n : 0; }
+
+template <class C>
+static int points_read_impl(zkmsm_ctx* ctx, const zkmsm_points* ps, size_t first, size_t n, uint32_t* xy, uint8_t* inf) {
+  typedef typename C::F F;
+  if (!ctx || !ps || first + n > ps->n || (n && !xy)) return fail(ctx, ZKMSM_ERR_INVALID_ARG, "bad argument");
+  if (n == 0) return ZKMSM_OK;
+  CU(ctx, cudaSetDevice(ctx->device));
+  size_t cbytes = sizeof(uint32_t) * C::AFF_LIMBS * n;
+  int rc = ws_reserve(ctx, WS_MISC, cbytes + n);
+  if (rc) return rc;
+  uint32_t* d_canon = (uint32_t*)ctx->ws[WS_MISC];
+  uint8_t* d_inf = (uint8_t*)ctx->ws[WS_MISC] + cbytes;
+  CudaExec ex(ctx->stream);
+  ex.template launch<StorePoints<C>>((uint32_t)n, (uint32_t)n, (const Affine<F>*)ps->d_pts + first, d_canon, d_inf);
+  if (ex.err != cudaSuccess) return fail(ctx, ZKMSM_ERR_CUDA, "StorePoints: %s", cudaGetErrorString(ex.err));
+  CU(ctx, cudaMemcpyAsync(xy, d_canon, cbytes, cudaMemcpyDeviceToHost, ctx->stream));
+  if (inf) CU(ctx, cudaMemcpyAsync(inf, d_inf, n, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  return ZKMSM_OK;
+}
+extern "C" int zkmsm_points_read(zkmsm_ctx* ctx, const zkmsm_points* ps, size_t first, size_t n, uint32_t* xy,
+                                 uint8_t* inf) {
+  if (!ps) return ZKMSM_ERR_INVALID_ARG;
+  return ps->curve == 1 ? points_read_impl<G1>(ctx, ps, first, n, xy, inf) : points_read_impl<G2>(ctx, ps, first, n, xy, inf);
+}
+
+// ------------------------------------------------------------------------------------------------
+// MSM
+template <class C>
+static int msm_enqueue_impl(zkmsm_ctx* ctx, const zkmsm_points* ps, const uint32_t* d_scalars, size_t n, int curve,
+                            bool want_affine, uint32_t* d_partial_out) {
+  typedef typename C::F F;
+  if (!ctx || !ps) return fail(ctx, ZKMSM_ERR_INVALID_ARG, "null argument");
+  if (ps->curve != curve) return fail(ctx, ZKMSM_ERR_INVALID_ARG, "point set is for the other group");
+  if (ps->device != ctx->device) return fail(ctx, ZKMSM_ERR_INVALID_ARG, "point set lives on another device");
+  if (n > ps->n) return fail(ctx, ZKMSM_ERR_TOO_FEW_POINTS, "%zu scalars but only %zu points", n, ps->n);
+  if (n > 0 && !d_scalars) return fail(ctx, ZKMSM_ERR_INVALID_ARG, "null scalars");
+  CU(ctx, cudaSetDevice(ctx->device));
+  ctx->pending_words = C::AFF_LIMBS;
+  ctx->last_launches = 0;
+  if (n == 0) {  // empty sum = AtInfinity (polynomial.rs:276)
+    ctx->pending = 2;
+    if (d_partial_out) CU(ctx, cudaMemsetAsync(d_partial_out, 0, sizeof(XYZZ<F>), ctx->stream));
+    return ZKMSM_OK;
+  }
+  unsigned c = ps->precomp ? ps->c : (ctx->window_override ? ctx->window_override : msm_pick_c((uint32_t)n, false));
+  MsmPlan p = msm_plan((uint32_t)n, c, ps->precomp, (uint32_t)ps->n);
+  int rc;
+  uint32_t nseg = (p.nb + SCAN_SEG - 1) / SCAN_SEG;
+  if ((rc = ws_reserve(ctx, WS_HIST, sizeof(uint32_t) * p.nb)) || (rc = ws_reserve(ctx, WS_OFFSETS, sizeof(uint32_t) * (p.nb + 1))) ||
+      (rc = ws_reserve(ctx, WS_SEGSUM, sizeof(uint32_t) * nseg)) || (rc = ws_reserve(ctx, WS_ENTRIES, sizeof(Entry) * (size_t)p.max_entries)) ||
+      (rc = ws_reserve(ctx, WS_BUCKETS, sizeof(XYZZ<F>) * (size_t)p.nb)) ||
+      (rc = ws_reserve(ctx, WS_PARTIALS, sizeof(XYZZ<F>) * (size_t)p.acc_threads)) ||
+      (rc = ws_reserve(ctx, WS_REDUCED, sizeof(XYZZ<F>) * (size_t)p.nwin * (p.B / p.K))))
+    return rc;
+  MsmBuffers<C> b;
+  b.hist_cursor = (uint32_t*)ctx->ws[WS_HIST];
+  b.offsets = (uint32_t*)ctx->ws[WS_OFFSETS];
+  b.segsum = (uint32_t*)ctx->ws[WS_SEGSUM];
+  b.entries = (Entry*)ctx->ws[WS_ENTRIES];
+  b.bucket_sums = (XYZZ<F>*)ctx->ws[WS_BUCKETS];
+  b.partials = (XYZZ<F>*)ctx->ws[WS_PARTIALS];
+  b.reduced = (XYZZ<F>*)ctx->ws[WS_REDUCED];
+  b.err = &ctx->d_res->err;
+  CudaExec ex(ctx->stream);
+  XYZZ<F>* d_xyzz = d_partial_out ? (XYZZ<F>*)d_partial_out : (XYZZ<F>*)ctx->d_res->xyzz;
+  msm_launch<C>(ex, p, b, (const Affine<F>*)ps->d_pts, d_scalars, want_affine ? (XYZZ<F>*)nullptr : d_xyzz,
+                want_affine ? ctx->d_res->affine : (uint32_t*)nullptr, want_affine ? &ctx->d_res->inf : (uint32_t*)nullptr);
+  ctx->last_launches = ex.launches;
+  if (ex.err != cudaSuccess) return fail(ctx, ZKMSM_ERR_CUDA, "msm launch: %s", cudaGetErrorString(ex.err));
+  ctx->pending = 1;
+  return ZKMSM_OK;
+}
+
+// wait for the enqueued MSM; copies the result block to pinned host memory
+static int msm_collect(zkmsm_ctx* ctx) {
+  if (ctx->pending == 0) return fail(ctx, ZKMSM_ERR_INVALID_ARG, "no MSM pending");
+  if (ctx->pending == 2) {
+    memset(ctx->h_res, 0, sizeof(ResultBlock));
+    ctx->h_res->inf = 1;
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->pending = 0;
+    return ZKMSM_OK;
+  }
+  CU(ctx, cudaMemcpyAsync(ctx->h_res, ctx->d_res, sizeof(ResultBlock), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->pending = 0;
+  if (ctx->h_res->err & ERR_SCALAR_RANGE) return fail(ctx, ZKMSM_ERR_SCALAR_RANGE, "a scalar has bit 255 set");
+  return ZKMSM_OK;
+}
+
+static int msm_result_impl(zkmsm_ctx* ctx, int words, uint32_t* out_xy, int* out_is_inf) {
+  if (!ctx || !out_xy || !out_is_inf) return fail(ctx, ZKMSM_ERR_INVALID_ARG, "null argument");
+  if (ctx->pending && ctx->pending_words != words) return fail(ctx, ZKMSM_ERR_INVALID_ARG, "pending MSM is for the other group");
+  CU(ctx, cudaSetDevice(ctx->device));
+  int rc = msm_collect(ctx);
+  if (rc) return rc;
+  *out_is_inf = ctx->h_res->inf ? 1 : 0;
+  if (ctx->h_res->inf) memset(out_xy, 0, sizeof(uint32_t) * words);
+  else memcpy(out_xy, ctx->h_res->affine, sizeof(uint32_t) * words);
+  return ZKMSM_OK;
+}
+
+static int upload_scalars(zkmsm_ctx* ctx, const uint32_t* scalars, size_t n, const uint32_t** d_out) {
+  *d_out = nullptr;
+  if (n == 0) return ZKMSM_OK;
+  if (!scalars) return fail(ctx, ZKMSM_ERR_INVALID_ARG, "null scalars");
+  CU(ctx, cudaSetDevice(ctx->device));
+  int rc = ws_reserve(ctx, WS_SCALARS, sizeof(uint32_t) * SCALAR_LIMBS * n);
+  if (rc) return rc;
+  CU(ctx, cudaMemcpyAsync(ctx->ws[WS_SCALARS], scalars, sizeof(uint32_t) * SCALAR_LIMBS * n, cudaMemcpyHostToDevice, ctx->stream));
+  *d_out = (const uint32_t*)ctx->ws[WS_SCALARS];
+  return ZKMSM_OK;
+}
+
+template <class C>
+static int msm_host_impl(zkmsm_ctx* ctx, const zkmsm_points* ps, const uint32_t* scalars, size_t n, int curve,
+                         uint32_t* out_xy, int* out_is_inf) {
+  if (!ctx || !ps || !out_xy || !out_is_inf) return fail(ctx, ZKMSM_ERR_INVALID_ARG, "null argument");
+  if (n > ps->n) return fail(ctx, ZKMSM_ERR_TOO_FEW_POINTS, "%zu scalars but only %zu points", n, ps->n);
+  const uint32_t* d_s;
+  int rc = upload_scalars(ctx, scalars, n, &d_s);
+  if (rc) return rc;
+  rc = msm_enqueue_impl<C>(ctx, ps, d_s, n, curve, true, nullptr);
+  if (rc) return rc;
+  return msm_result_impl(ctx, C::AFF_LIMBS, out_xy, out_is_inf);
+}
+
+extern "C" int zkmsm_g1_msm(zkmsm_ctx* ctx, const zkmsm_points* ps, const uint32_t* s, size_t n, uint32_t* out, int* inf) {
+  return msm_host_impl<G1>(ctx, ps, s, n, 1, out, inf);
+}
+extern "C" int zkmsm_g2_msm(zkmsm_ctx* ctx, const zkmsm_points* ps, const uint32_t* s, size_t n, uint32_t* out, int* inf) {
+  return msm_host_impl<G2>(ctx, ps, s, n, 2, out, inf);
+}
+extern "C" int zkmsm_g1_msm_enqueue(zkmsm_ctx* ctx, const zkmsm_points* ps, const uint32_t* ds, size_t n) {
+  return msm_enqueue_impl<G1>(ctx, ps, ds, n, 1, true, nullptr);
+}
+extern "C" int zkmsm_g2_msm_enqueue(zkmsm_ctx* ctx, const zkmsm_points* ps, const uint32_t* ds, size_t n) {
+  return msm_enqueue_impl<G2>(ctx, ps, ds, n, 2, true, nullptr);
+}
+extern "C" int zkmsm_g1_msm_result(zkmsm_ctx* ctx, uint32_t* out, int* inf) { return msm_result_impl(ctx, 24, out, inf); }
+extern "C" int zkmsm_g2_msm_result(zkmsm_ctx* ctx, uint32_t* out, int* inf) { return msm_result_impl(ctx, 48, out, inf); }
+extern "C" int zkmsm_g1_msm_device(zkmsm_ctx* ctx, const zkmsm_points* ps, const uint32_t* ds, size_t n, uint32_t* out, int* inf) {
+  int rc = msm_enqueue_impl<G1>(ctx, ps, ds, n, 1, true, nullptr);
+  return rc ? rc : msm_result_impl(ctx, 24, out, inf);
+}
+extern "C" int zkmsm_g2_msm_device(zkmsm_ctx* ctx, const zkmsm_points* ps, const uint32_t* ds, size_t n, uint32_t* out, int* inf) {
+  int rc = msm_enqueue_impl<G2>(ctx, ps, ds, n, 2, true, nullptr);
+  return rc ? rc : msm_result_impl(ctx, 48, out, inf);
+}
+
+template <class C>
+static int oneshot_impl(zkmsm_ctx* ctx, const uint32_t* xy, const uint8_t* inf, const uint32_t* scalars, size_t n, int curve,
+                        uint32_t* out_xy, int* out_is_inf) {
+  zkmsm_points* ps = nullptr;
+  int rc = load_points_impl<C>(ctx, xy, inf, n, 0, curve, &ps);
+  if (rc) return rc;
+  rc = msm_host_impl<C>(ctx, ps, scalars, n, curve, out_xy, out_is_inf);
+  zkmsm_points_free(ctx, ps);
+  return rc;
+}
+extern "C" int zkmsm_g1_msm_oneshot(zkmsm_ctx* ctx, const uint32_t* xy, const uint8_t* inf, const uint32_t* s, size_t n,
+                                    uint32_t* out, int* oinf) {
+  return oneshot_impl<G1>(ctx, xy, inf, s, n, 1, out, oinf);
+}
+extern "C" int zkmsm_g2_msm_oneshot(zkmsm_ctx* ctx, const uint32_t* xy, const uint8_t* inf, const uint32_t* s, size_t n,
+                                    uint32_t* out, int* oinf) {
+  return oneshot_impl<G2>(ctx, xy, inf, s, n, 2, out, oinf);
+}
+
+// ---- partials / combine
+template <class C>
+static int partial_impl(zkmsm_ctx* ctx, const zkmsm_points* ps, const uint32_t* scalars, size_t n, int curve, uint32_t* out) {
+  typedef typename C::F F;
+  if (!ctx || !ps || !out) return fail(ctx, ZKMSM_ERR_INVALID_ARG, "null argument");
+  if (n > ps->n) return fail(ctx, ZKMSM_ERR_TOO_FEW_POINTS, "%zu scalars but only %zu points", n, ps->n);
+  const uint32_t* d_s;
+  int rc = upload_scalars(ctx, scalars, n, &d_s);
+  if (rc) return rc;
+  rc = msm_enqueue_impl<C>(ctx, ps, d_s, n, curve, false, nullptr);
+  if (rc) return rc;
+  rc = msm_collect(ctx);
+  if (rc) return rc;
+  memcpy(out, ctx->h_res->xyzz, sizeof(XYZZ<F>));  // n == 0: zeros = infinity
+  return ZKMSM_OK;
+}
+extern "C" int zkmsm_g1_msm_partial(zkmsm_ctx* ctx, const zkmsm_points* ps, const uint32_t* s, size_t n, uint32_t* out) {
+  return partial_impl<G1>(ctx, ps, s, n, 1, out);
+}
+extern "C" int zkmsm_g2_msm_partial(zkmsm_ctx* ctx, const zkmsm_points* ps, const uint32_t* s, size_t n, uint32_t* out) {
+  return partial_impl<G2>(ctx, ps, s, n, 2, out);
+}
+extern "C" int zkmsm_g1_msm_partial_device(zkmsm_ctx* ctx, const zkmsm_points* ps, const uint32_t* ds, size_t n, uint32_t* d_out) {
+  if (!d_out) return fail(ctx, ZKMSM_ERR_INVALID_ARG, "null argument");
+  int rc = msm_enqueue_impl<G1>(ctx, ps, ds, n, 1, false, d_out);
+  if (rc) return rc;
+  ctx->pending = 0;  // result lives in the caller's buffer, stream-ordered
+  return ZKMSM_OK;
+}
+
+template <class C>
+static int combine_impl(zkmsm_ctx* ctx, const uint32_t* parts, bool on_device, size_t k, uint32_t* out_xy, int* out_is_inf) {
+  typedef typename C::F F;
+  if (!ctx || (k && !parts) || !out_xy || !out_is_inf || k > 4096) return fail(ctx, ZKMSM_ERR_INVALID_ARG, "bad argument");
+  CU(ctx, cudaSetDevice(ctx->device));
+  const XYZZ<F>* d_parts = (const XYZZ<F>*)parts;
+  if (!on_device && k) {
+    int rc = ws_reserve(ctx, WS_MISC, sizeof(XYZZ<F>) * k);
+    if (rc) return rc;
+    CU(ctx, cudaMemcpyAsync(ctx->ws[WS_MISC], parts, sizeof(XYZZ<F>) * k, cudaMemcpyHostToDevice, ctx->stream));
+    d_parts = (const XYZZ<F>*)ctx->ws[WS_MISC];
+  }
+  CU(ctx, cudaMemsetAsync(&ctx->d_res->err, 0, sizeof(uint32_t), ctx->stream));
+  CudaExec ex(ctx->stream);
+  ex.template launch<CombinePartials<C>>(1u, (uint32_t)k, d_parts, ctx->d_res->affine, &ctx->d_res->inf);
+  if (ex.err != cudaSuccess) return fail(ctx, ZKMSM_ERR_CUDA, "combine: %s", cudaGetErrorString(ex.err));
+  ctx->pending = 1;
+  ctx->pending_words = C::AFF_LIMBS;
+  return msm_result_impl(ctx, C::AFF_LIMBS, out_xy, out_is_inf);
+}
+extern "C" int zkmsm_g1_combine(zkmsm_ctx* ctx, const uint32_t* parts, size_t k, uint32_t* out, int* inf) {
+  return combine_impl<G1>(ctx, parts, false, k, out, inf);
+}
+extern "C" int zkmsm_g2_combine(zkmsm_ctx* ctx, const uint32_t* parts, size_t k, uint32_t* out, int* inf) {
+  return combine_impl<G2>(ctx, parts, false, k, out, inf);
+}
+extern "C" int zkmsm_g1_combine_device(zkmsm_ctx* ctx, const uint32_t* parts, size_t k, uint32_t* out, int* inf) {
+  return combine_impl<G1>(ctx, parts, true, k, out, inf);
+}
+
+// ------------------------------------------------------------------------------------------------
+// fixed-base vector scalar multiplication
+template <class C>
+static int base_table(zkmsm_ctx* ctx, const uint32_t* base_xy, CudaExec& ex, Affine<typename C::F>** table_out) {
+  typedef typename C::F F;
+  size_t need = sizeof(uint32_t) * C::AFF_LIMBS + 16 + sizeof(XYZZ<F>) * 256 + sizeof(Affine<F>) * 256;
+  int rc = ws_reserve(ctx, WS_REDUCED, need);
+  if (rc) return rc;
+  char* base = (char*)ctx->ws[WS_REDUCED];
+  XYZZ<F>* chain = (XYZZ<F>*)base;
+  Affine<F>* table = (Affine<F>*)(base + sizeof(XYZZ<F>) * 256);
+  uint32_t* d_base = (uint32_t*)(base + sizeof(XYZZ<F>) * 256 + sizeof(Affine<F>) * 256);
+  CU(ctx, cudaMemcpyAsync(d_base, base_xy, sizeof(uint32_t) * C::AFF_LIMBS, cudaMemcpyHostToDevice, ctx->stream));
+  ex.template launch<BaseTableChain<C>>(1u, (const uint32_t*)d_base, chain);
+  ex.template launch<BaseTableAffine<C>>(256u, (const XYZZ<F>*)chain, table);
+  *table_out = table;
+  return ZKMSM_OK;
+}
+
+template <class C>
+static int points_from_scalars_impl(zkmsm_ctx* ctx, const uint32_t* base_xy, const uint32_t* scalars, size_t n, unsigned flags,
+                                    int curve, zkmsm_points** out) {
+  typedef typename C::F F;
+  if (!ctx || !base_xy || !out || (n && !scalars)) return fail(ctx, ZKMSM_ERR_INVALID_ARG, "null argument");
+  int rc = alloc_point_set<C>(ctx, n, flags, curve, out);
+  if (rc) return rc;
+  zkmsm_points* ps = *out;
+  if (n == 0) return ZKMSM_OK;
+  const uint32_t* d_s;
+  rc = upload_scalars(ctx, scalars, n, &d_s);
+  CudaExec ex(ctx->stream);
+  Affine<F>* table = nullptr;
+  if (!rc) rc = base_table<C>(ctx, base_xy, ex, &table);
+  if (!rc) {
+    ex.template launch<FixedBaseMul<C>>((uint32_t)n, (uint32_t)n, d_s, (const Affine<F>*)table, (Affine<F>*)ps->d_pts);
+    rc = finish_point_set<C>(ctx, ps, ex);
+  }
+  if (rc) { zkmsm_points_free(ctx, ps); *out = nullptr; }
+  return rc;
+}
+extern "C" int zkmsm_g1_points_from_scalars(zkmsm_ctx* ctx, const uint32_t* base, const uint32_t* s, size_t n, unsigned flags,
+                                            zkmsm_points** out) {
+  return points_from_scalars_impl<G1>(ctx, base, s, n, flags, 1, out);
+}
+extern "C" int zkmsm_g2_points_from_scalars(zkmsm_ctx* ctx, const uint32_t* base, const uint32_t* s, size_t n, unsigned flags,
+                                            zkmsm_points** out) {
+  return points_from_scalars_impl<G2>(ctx, base, s, n, flags, 2, out);
+}
+
+template <class C>
+static int mul_base_impl(zkmsm_ctx* ctx, const uint32_t* base_xy, const uint32_t* scalars, size_t n, int curve, uint32_t* out_xy,
+                         uint8_t* out_inf) {
+  zkmsm_points* ps = nullptr;
+  if (n && !out_xy) return fail(ctx, ZKMSM_ERR_INVALID_ARG, "null output");
+  int rc = points_from_scalars_impl<C>(ctx, base_xy, scalars, n, 0, curve, &ps);
+  if (rc) return rc;
+  rc = zkmsm_points_read(ctx, ps, 0, n, out_xy, out_inf);
+  zkmsm_points_free(ctx, ps);
+  return rc;
+}
+extern "C" int zkmsm_g1_mul_base(zkmsm_ctx* ctx, const uint32_t* base, const uint32_t* s, size_t n, uint32_t* out, uint8_t* inf) {
+  return mul_base_impl<G1>(ctx, base, s, n, 1, out, inf);
+}
+extern "C" int zkmsm_g2_mul_base(zkmsm_ctx* ctx, const uint32_t* base, const uint32_t* s, size_t n, uint32_t* out, uint8_t* inf) {
+  return mul_base_impl<G2>(ctx, base, s, n, 2, out, inf);
+}
+
+// ------------------------------------------------------------------------------------------------
+// integer-multiply throughput probe (kernels in tu_probe.cu)
+extern "C" int zkmsm_probe_launch(int variant, int grid, int block, cudaStream_t st, uint32_t* sink, int iters);
+
+extern "C" int zkmsm_bench_imad(zkmsm_ctx* ctx, int variant, int iters, double* out_lp_per_s, double* out_ms) {
+  if (!ctx || !out_lp_per_s || iters <= 0 || variant < 0 || variant > 2) return fail(ctx, ZKMSM_ERR_INVALID_ARG, "bad argument");
+  CU(ctx, cudaSetDevice(ctx->device));
+  int sms = 0;
+  CU(ctx, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
+  int rc = ws_reserve(ctx, WS_MISC, 64);
+  if (rc) return rc;
+  dim3 grid(sms * 8), block(256);
+  const double per_iter[3] = {32.0, 24.0, 32.0};
+  cudaEvent_t e0, e1;
+  CU(ctx, cudaEventCreate(&e0));
+  CU(ctx, cudaEventCreate(&e1));
+  for (int rep = 0; rep < 2; rep++) {  // first pass warms up
+    CU(ctx, cudaEventRecord(e0, ctx->stream));
+    if (zkmsm_probe_launch(variant, (int)grid.x, (int)block.x, ctx->stream, (uint32_t*)ctx->ws[WS_MISC], iters))
+      return fail(ctx, ZKMSM_ERR_CUDA, "probe launch failed");
+    CU(ctx, cudaEventRecord(e1, ctx->stream));
+    CU(ctx, cudaEventSynchronize(e1));
+  }
+  CU(ctx, cudaGetLastError());
+  float ms = 0;
+  CU(ctx, cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  double ops = (double)grid.x * block.x * (double)iters * per_iter[variant];
+  *out_lp_per_s = ops / (ms * 1e-3);
+  if (out_ms) *out_ms = ms;
+  return ZKMSM_OK;
+}
