@@ -1,0 +1,231 @@
+"""Parity of the CUDA path (through the C ABI) with the T0 oracle and the reference's golden
+vectors.  Bit-exact: every comparison is on canonical affine coordinates."""
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+
+from oracle import zkt_oracle as O
+from tests import util as U
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def z():
+    import zk_toolkit_b200 as z
+    return z
+
+
+@pytest.fixture(scope="module")
+def ctx(z):
+    return z.default_context()
+
+
+def load(name):
+    with open(os.path.join(G, f"ref_{name}.json")) as f:
+        return json.load(f)
+
+
+def to_o1(p):
+    return O.INF if p.is_zero() else O.g1(p.x, p.y)
+
+
+def to_o2(p):
+    if p.is_zero():
+        return O.INF
+    c = p.coords
+    return O.g2(c[1], c[0], c[3], c[2])
+
+
+# ---------------------------------------------------------------- reference KATs through the GPU API
+def test_g1_kats_through_api(z):
+    k = load("g1")
+    g = z.G1Point.g()
+    gs = [z.G1Point.new(int(p["x"]), int(p["y"])) for p in k["g_multiples"]["points"]]
+    assert g + g == z.G1Point.new(int(k["add_same_point"]["x"]), int(k["add_same_point"]["y"]))   # g1_point.rs:223-237
+    for n in range(1, 11):                                                                         # :347-356
+        assert g * n == gs[n - 1]
+    for c in k["scalar_mul_gen_pubkey"]["cases"]:                                                  # :352-371
+        assert g * (int(c["multiple"]) % O.Q) == z.G1Point.new(int(c["x"]), int(c["y"]))
+    for a, b, c in k["add_different_points"]["cases"]:                                             # :389-412
+        assert gs[a - 1] + gs[b - 1] == gs[c - 1]
+    inf = z.G1Point.zero()
+    assert (g + (-g)).is_zero() and g + inf == g and inf + g == g and (inf + inf).is_zero()       # :239-296
+    assert (g * 0).is_zero() and (g * O.R).is_zero() and g * 1 == g
+    assert g * 2 == g + g and g * 3 == g + g + g                                                   # :203-221
+
+
+def test_g2_kats_through_api(z):
+    k = load("g2")
+    mk = lambda p: z.G2Point.new(int(p["x1"]), int(p["x0"]), int(p["y1"]), int(p["y0"]))
+    g = z.G2Point.g()
+    gs = [mk(p) for p in k["g_multiples"]["points"]]
+    assert g + g == mk(k["add_same_point"])                                                        # g2_point.rs:199-230
+    for n in range(1, 11):
+        assert g * n == gs[n - 1]
+    for c in k["scalar_mul_gen_pubkey"]["cases"]:
+        assert g * int(c["multiple"]) == mk(c)
+    for a, b, c in k["add_different_points"]["cases"]:
+        assert gs[a - 1] + gs[b - 1] == gs[c - 1]
+    inf = z.G2Point.zero()
+    assert (g + (-g)).is_zero() and g + inf == g and inf + g == g and (inf + inf).is_zero()
+    assert (g * O.R).is_zero()
+
+
+# ---------------------------------------------------------------- MSM vs the reference's serial loop
+@pytest.fixture(scope="module")
+def small_g1(z):
+    rnd = random.Random(42)
+    dlogs = [rnd.randrange(1, O.R) for _ in range(40)]
+    opts = [O.scalar_mul(O.G1_GEN, k) for k in dlogs]
+    pts = [z.G1Point.new(p[0].e, p[1].e) for p in opts]
+    return dlogs, opts, pts
+
+
+def test_msm_seam_small_vs_oracle(z, small_g1):
+    dlogs, opts, pts = small_g1
+    rnd = random.Random(1)
+    for n in (1, 2, 3, 7, 16):
+        sc = U.rand_scalars(rnd, n)
+        exp = O.msm(opts[:n], sc)
+        assert to_o1(z.Polynomial(sc).eval_with_g1_hidings(pts[:n])) == exp       # host slice, uploaded per call
+        dev = z.G1Points(pts[:n])
+        assert to_o1(z.Polynomial(sc).eval_with_g1_hidings(dev)) == exp
+    # polynomial.rs:1250-1285: 4 terms, toy scalars
+    g = z.G1Point.g()
+    pw = [g * 1, g * 2, g * 3, g * 4]
+    assert z.Polynomial([2, 3, 4, 5]).eval_with_g1_hidings(pw) == g * 40
+    with pytest.raises(IndexError):
+        z.Polynomial([1, 2, 3]).eval_with_g1_hidings(pw[:2])                  # polynomial.rs:278 panics
+    assert z.Polynomial([0]).eval_with_g1_hidings(pw).is_zero()
+
+
+def test_msm_edge_cases(z, ctx, small_g1):
+    dlogs, opts, pts = small_g1
+    n = 12
+    P, D, OP = pts[:n], dlogs[:n], opts[:n]
+    dev = z.G1Points(P)
+    pre = z.G1Points(P, precompute=True)
+
+    def run(s, points=dev, cnt=None):
+        out, inf = ctx.msm(points.set, z.scalars_to_array(s), n=cnt)
+        return U.g1_from_array(out, inf)
+
+    exp = lambda s, d=D: U.expected_from_dlogs(O.G1_GEN, d, s)
+    assert run([]) is O.INF                                                    # n = 0
+    assert run([0] * n) is O.INF
+    s = [0, 1, O.R - 1, 2, 0, O.R - 2, 1, 1, 5, 0, 7, O.R - 1]
+    assert run(s) == exp(s) == run(s, pre)
+    s = [0x1234567890ABCDEF1234567890ABCDEF] * n                               # all-equal scalars
+    assert run(s) == exp(s) == run(s, pre)
+    dup = z.G1Points([P[0]] * n)                                               # duplicate points -> doubling inside a bucket
+    assert run([3] * n, dup) == O.scalar_mul(OP[0], 3 * n)
+    pm = z.G1Points([P[0], -P[0], P[1], -P[1]])                                # P + (-P)
+    assert run([9, 9, 11, 11], pm) is O.INF
+    assert run([9, 9, 11, 10], pm) == OP[1]
+    wi = z.G1Points([P[0], z.G1Point.zero(), P[1], z.G1Point.zero()])          # AtInfinity inputs
+    assert run([5, 6, 7, 8], wi) == O.msm([OP[0], O.INF, OP[1], O.INF], [5, 6, 7, 8])
+    assert run([5, 6, 7], dev, 3) == exp([5, 6, 7], D[:3]) == run([5, 6, 7], pre, 3)   # extra points ignored
+    s = [(1 << 255) - 1, (1 << 255) - 19]
+    assert run(s, z.G1Points(P[:2])) == O.msm(OP[:2], s)
+    assert run([O.R], z.G1Points(P[:1])) is O.INF
+    with pytest.raises(z.ZkmsmError) as e:                                     # bit 255 set: rejected
+        run([1 << 255, 1], z.G1Points(P[:2]))
+    assert e.value.code == -3
+    with pytest.raises(z.ZkmsmError) as e:                                     # more scalars than points
+        ctx.msm(z.G1Points(P[:2]).set, z.scalars_to_array([1, 2, 3]))
+    assert e.value.code == -5
+
+
+@pytest.mark.parametrize("logn", [6, 10, 12, 16])
+@pytest.mark.parametrize("precompute", [False, True])
+def test_msm_random_vs_dlog_identity(z, ctx, logn, precompute):
+    """points = k_i * g made on the device (spot-checked against the oracle), so the full-size
+    result has a closed form: (sum s_i k_i mod r) * g, one oracle scalar multiplication."""
+    n = 1 << logn
+    rnd = random.Random(1000 + logn)
+    dlogs = [rnd.randrange(1, O.R) for _ in range(n)]
+    pts = z.G1Points.generator_multiples(dlogs, precompute=precompute)
+    for i in (0, 1, n // 2, n - 1):
+        assert to_o1(pts[i]) == O.scalar_mul(O.G1_GEN, dlogs[i])
+    for trial in range(2):
+        sc = U.rand_scalars(rnd, n)
+        out, inf = ctx.msm(pts.set, z.scalars_to_array(sc))
+        assert U.g1_from_array(out, inf) == U.expected_from_dlogs(O.G1_GEN, dlogs, sc)
+    # ragged: 2^k +- 1 terms of the same set
+    for m in (n - 1, n // 2 + 1):
+        sc = U.rand_scalars(rnd, m)
+        out, inf = ctx.msm(pts.set, z.scalars_to_array(sc))
+        assert U.g1_from_array(out, inf) == U.expected_from_dlogs(O.G1_GEN, dlogs[:m], sc)
+
+
+@pytest.mark.parametrize("c", [4, 9, 13, 16])
+def test_msm_forced_windows(z, ctx, c):
+    n = 3000
+    rnd = random.Random(c)
+    dlogs = [rnd.randrange(1, O.R) for _ in range(n)]
+    sc = U.rand_scalars(rnd, n)
+    exp = U.expected_from_dlogs(O.G1_GEN, dlogs, sc)
+    ctx.set_window(c)
+    try:
+        for pre in (False, True):
+            pts = z.G1Points.generator_multiples(dlogs, precompute=pre)
+            out, inf = ctx.msm(pts.set, z.scalars_to_array(sc))
+            assert U.g1_from_array(out, inf) == exp
+    finally:
+        ctx.set_window(0)
+
+
+def test_msm_sharded_partials(z, ctx):
+    """the multi-GPU path on one device: k shards -> k partial points -> combine; partition independent"""
+    n = 5000
+    rnd = random.Random(77)
+    dlogs = [rnd.randrange(1, O.R) for _ in range(n)]
+    sc = U.rand_scalars(rnd, n)
+    exp = U.expected_from_dlogs(O.G1_GEN, dlogs, sc)
+    sca = z.scalars_to_array(sc)
+    for k in (1, 2, 3, 8):
+        parts = []
+        for r in range(k):
+            lo, hi = n * r // k, n * (r + 1) // k
+            shard = z.G1Points.generator_multiples(dlogs[lo:hi])
+            parts.append(ctx.msm_partial(shard.set, sca[lo:hi]))
+        out, inf = ctx.combine(1, np.stack(parts))
+        assert U.g1_from_array(out, inf) == exp
+    out, inf = ctx.combine(1, np.zeros((3, 48), dtype=np.uint32))
+    assert inf
+
+
+def test_g2_msm(z, ctx):
+    rnd = random.Random(9)
+    n = 600
+    dlogs = [rnd.randrange(1, O.R) for _ in range(n)]
+    sc = U.rand_scalars(rnd, n)
+    exp = U.expected_from_dlogs(O.G2_GEN, dlogs, sc)
+    for pre in (False, True):
+        pts = z.G2Points.generator_multiples(dlogs, precompute=pre)
+        assert to_o2(pts[5]) == O.scalar_mul(O.G2_GEN, dlogs[5])
+        out, inf = ctx.msm(pts.set, z.scalars_to_array(sc))
+        assert U.g2_from_array(out, inf) == exp
+    small = [z.G2Point.g() * k for k in (1, 2, 3)]
+    got = z.Polynomial([4, 5, 6]).eval_with_g2_hidings(small)
+    assert to_o2(got) == O.scalar_mul(O.G2_GEN, 4 + 10 + 18)
+
+
+def test_enqueue_result_split_and_launch_count(z, ctx):
+    import torch
+    n = 4096
+    rnd = random.Random(3)
+    dlogs = [rnd.randrange(1, O.R) for _ in range(n)]
+    sc = U.rand_scalars(rnd, n)
+    pts = z.G1Points.generator_multiples(dlogs)
+    d_sc = torch.from_numpy(z.scalars_to_array(sc).view(np.int32)).cuda()
+    torch.cuda.synchronize()
+    ctx.msm_enqueue(pts.set, d_sc.data_ptr(), n)
+    assert ctx.last_launch_count() >= 8
+    out, inf = ctx.msm_result(1)
+    assert U.g1_from_array(out, inf) == U.expected_from_dlogs(O.G1_GEN, dlogs, sc)
