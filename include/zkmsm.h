@@ -107,6 +107,12 @@ int zkmsm_g1_msm_result(zkmsm_ctx* ctx, uint32_t out_xy[24], int* out_is_inf);
 int zkmsm_g2_msm_result(zkmsm_ctx* ctx, uint32_t out_xy[48], int* out_is_inf);
 /* Number of kernels the last enqueue launched. */
 int zkmsm_last_launch_count(const zkmsm_ctx* ctx);
+/* Per-kernel timing of the MSMs that follow: CUDA events on the launching stream around every
+ * launch.  zkmsm_profile_read waits for the stream and returns the number of launches of the last
+ * MSM, filling (nullable) names[i * name_stride], ms[i] and threads[i]. */
+int zkmsm_profile(zkmsm_ctx* ctx, int enable);
+int zkmsm_profile_read(zkmsm_ctx* ctx, int max_entries, char* names, size_t name_stride, float* ms,
+                       uint32_t* threads);
 
 /* ---- multi-GPU: each rank multiplies its shard and exports one partial point (opaque
  * little-endian blob: 48 words for G1, 96 for G2); any rank adds the gathered partials.

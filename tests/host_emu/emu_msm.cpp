@@ -37,13 +37,14 @@ static int emu_msm(const uint32_t* xy, const uint8_t* inf, const uint32_t* scala
   if (K) p.K = K;
   std::vector<uint32_t> hist(p.nb), offsets(p.nb + 1), segsum((p.nb + SCAN_SEG - 1) / SCAN_SEG + 1), err(1);
   std::vector<Entry> entries(p.max_entries + 1);
-  std::vector<XYZZ<F>> buckets(p.nb), partials(p.acc_threads), reduced((size_t)p.nwin * (p.B / p.K));
+  std::vector<XYZZ<F>> buckets(p.nb), partials(msm_partial_slots(p)), reduced((size_t)p.nwin * (p.B / p.K));
+  std::vector<uint32_t> pkeys(msm_partial_slots(p), 0x12345678u);
   // poison what the pipeline must overwrite before reading
   memset(buckets.data(), 0xAB, sizeof(XYZZ<F>) * buckets.size());
   memset(partials.data(), 0xCD, sizeof(XYZZ<F>) * partials.size());
   MsmBuffers<C> b;
   b.hist_cursor = hist.data(); b.offsets = offsets.data(); b.segsum = segsum.data(); b.entries = entries.data();
-  b.bucket_sums = buckets.data(); b.partials = partials.data(); b.reduced = reduced.data(); b.err = err.data();
+  b.bucket_sums = buckets.data(); b.partials = partials.data(); b.reduced = reduced.data(); b.err = err.data(); b.partial_keys = pkeys.data();
   XYZZ<F> xyzz;
   msm_launch<C>(ex, p, b, (const Affine<F>*)pts.data(), scalars, out_xyzz ? &xyzz : (XYZZ<F>*)nullptr,
                 out_xyzz ? (uint32_t*)nullptr : out_xy, out_xyzz ? (uint32_t*)nullptr : out_inf);

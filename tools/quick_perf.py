@@ -7,9 +7,6 @@ import torch
 import zk_toolkit_b200 as z
 
 ctx = z.Context(0)
-for v, name in ((0, "IMAD.WIDE indep"), (1, "IMAD.WIDE.X carry-chain"), (2, "IMAD 32")):
-    lp, ms = ctx.bench_imad(v, 8192)
-    print(f"probe {name}: {lp/1e12:.2f} T/s in {ms:.2f} ms", flush=True)
 
 R = z.R
 def rand_scalars(n, seed):
@@ -28,19 +25,20 @@ for logn in (16, 18, 20, 22):
         tgen = time.time() - t0
         sc = rand_scalars(n, 2)
         d_sc = torch.from_numpy(sc.view(np.int32)).cuda()
-        stream = torch.cuda.current_stream()
+        stream = torch.cuda.Stream()
+        torch.cuda.synchronize()
         ctx.set_stream(stream.cuda_stream)
         for cc in ((0,) if pre else (0, 13, 14, 15, 16, 17)):
             if logn != 20 and cc: continue
             ctx.set_window(cc)
             if pre and cc: continue
             for _ in range(2):
-                ctx.msm_enqueue(pts.set, d_sc.data_ptr(), n); ctx.msm_result(1)
+                ctx.msm_enqueue(pts, d_sc.data_ptr(), n); ctx.msm_result(1)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
             K = 5
             for _ in range(K):
-                ctx.msm_enqueue(pts.set, d_sc.data_ptr(), n)
+                ctx.msm_enqueue(pts, d_sc.data_ptr(), n)
             e1.record(stream)
             out, inf = ctx.msm_result(1)
             torch.cuda.synchronize()

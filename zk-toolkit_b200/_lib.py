@@ -32,7 +32,7 @@ SYMBOLS = [
     "zkmsm_g1_msm", "zkmsm_g2_msm", "zkmsm_g1_msm_device", "zkmsm_g2_msm_device",
     "zkmsm_g1_msm_oneshot", "zkmsm_g2_msm_oneshot",
     "zkmsm_g1_msm_enqueue", "zkmsm_g2_msm_enqueue", "zkmsm_g1_msm_result", "zkmsm_g2_msm_result",
-    "zkmsm_last_launch_count",
+    "zkmsm_last_launch_count", "zkmsm_profile", "zkmsm_profile_read",
     "zkmsm_g1_msm_partial", "zkmsm_g2_msm_partial", "zkmsm_g1_msm_partial_device",
     "zkmsm_g1_combine", "zkmsm_g2_combine", "zkmsm_g1_combine_device",
     "zkmsm_g1_mul_base", "zkmsm_g2_mul_base", "zkmsm_g1_points_from_scalars", "zkmsm_g2_points_from_scalars",
@@ -81,6 +81,8 @@ def load():
         "zkmsm_g1_msm_result": (ci, [vp, vp, ip]),
         "zkmsm_g2_msm_result": (ci, [vp, vp, ip]),
         "zkmsm_last_launch_count": (ci, [vp]),
+        "zkmsm_profile": (ci, [vp, ci]),
+        "zkmsm_profile_read": (ci, [vp, ci, vp, sz, vp, vp]),
         "zkmsm_g1_msm_partial": (ci, [vp, vp, vp, sz, vp]),
         "zkmsm_g2_msm_partial": (ci, [vp, vp, vp, sz, vp]),
         "zkmsm_g1_msm_partial_device": (ci, [vp, vp, vp, sz, vp]),

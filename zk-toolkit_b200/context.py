@@ -142,6 +142,21 @@ class Context:
     def last_launch_count(self):
         return self.lib.zkmsm_last_launch_count(self.h)
 
+    def profile(self, enable=True):
+        self._check(self.lib.zkmsm_profile(self.h, 1 if enable else 0))
+
+    def profile_read(self):
+        """[(kernel name, ms, logical threads)] of the last MSM, in launch order"""
+        cap, stride = 96, 32
+        names = ctypes.create_string_buffer(cap * stride)
+        ms = np.zeros(cap, dtype=np.float32)
+        thr = np.zeros(cap, dtype=np.uint32)
+        n = self.lib.zkmsm_profile_read(self.h, cap, names, stride, L.dptr(ms), L.dptr(thr))
+        if n < 0:
+            self._check(n)
+        raw = names.raw
+        return [(raw[i * stride:(i + 1) * stride].split(b"\0")[0].decode(), float(ms[i]), int(thr[i])) for i in range(n)]
+
     def msm_oneshot(self, group, xy, inf, scalars):
         xy = L.as_u32(xy, self._words(group)).reshape(-1, self._words(group))
         sc = L.as_u32(scalars, 8).reshape(-1, 8) if len(scalars) else np.zeros((0, 8), dtype=np.uint32)

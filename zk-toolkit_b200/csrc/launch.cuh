@@ -37,15 +37,34 @@ template <class Body> struct Launch : LaunchBase<Body, decltype(Body::run)> {};
 #define ZK_INSTANTIATE_KERNEL(...) template struct zk::LaunchBase<__VA_ARGS__, decltype(__VA_ARGS__::run)>
 
 // Exec policy for msm_launch (msm.cuh): stream-ordered CUDA launches
+// optional per-launch timing (zkmsm_profile): CUDA events on the launching stream around every kernel
+struct LaunchProfile {
+  static constexpr int MAX = 96;
+  int n = 0;
+  const char* names[MAX];
+  uint32_t threads[MAX];
+  cudaEvent_t beg[MAX], end[MAX];
+  bool have_events = false;
+};
+
 struct CudaExec {
   cudaStream_t st;
   int launches;
   cudaError_t err;
-  explicit CudaExec(cudaStream_t s) : st(s), launches(0), err(cudaSuccess) {}
+  LaunchProfile* prof;
+  explicit CudaExec(cudaStream_t s, LaunchProfile* p = nullptr) : st(s), launches(0), err(cudaSuccess), prof(p) {}
   template <class Body, class... Args>
   void launch(uint32_t nthreads, Args... args) {
     if (nthreads == 0 || err != cudaSuccess) return;
+    int slot = -1;
+    if (prof && prof->n < LaunchProfile::MAX) {
+      slot = prof->n++;
+      prof->names[slot] = Body::name();
+      prof->threads[slot] = nthreads;
+      cudaEventRecord(prof->beg[slot], st);
+    }
     cudaError_t e = Launch<Body>::go(st, nthreads, args...);
+    if (slot >= 0) cudaEventRecord(prof->end[slot], st);
     launches++;
     if (e != cudaSuccess) err = e;
   }

@@ -11,7 +11,7 @@
 //   3 Scatter       counting sort: (bucket, +-point index) pairs grouped by bucket
 //   4 Accumulate    fixed-size chunks of L sorted pairs per thread, XYZZ mixed adds; a bucket
 //                   that spans several chunks leaves one head sum + per-chunk partial sums
-//   5 BucketFixup   per bucket: head + partials -> bucket sum (empty bucket -> infinity)
+//   5 FixupLevel    16-ary tree over the per-chunk partial sums -> complete bucket sums
 //   6 BucketReduce  per K consecutive buckets: sum_j (j+1) * bucket_j by running sums
 //   7 PairSum       pairwise tree over the chunk results of each window -> window sums
 //   8 Finish        Horner over windows (c doublings each), to canonical affine
@@ -80,6 +80,7 @@ struct Digits {
 };
 
 struct RecodeCount {
+  static const char* name() { return "recode_count"; }
   static ZK_HD void run(uint32_t tid, MsmPlan p, const uint32_t* scalars, uint32_t* hist, uint32_t* err) {
     if (tid >= p.n) return;
     uint32_t s[SCALAR_LIMBS];
@@ -99,7 +100,7 @@ struct RecodeCount {
 // ---------------------------------------------------------------- exclusive scan (3 small kernels)
 static constexpr uint32_t SCAN_SEG = 256;
 
-struct ScanLocal {  // thread t: sum of hist[t*SEG .. (t+1)*SEG)
+struct ScanLocal {  static const char* name() { return "scan_local"; }  // thread t: sum of hist[t*SEG .. (t+1)*SEG)
   static ZK_HD void run(uint32_t tid, uint32_t nb, const uint32_t* hist, uint32_t* segsum) {
     uint32_t beg = tid * SCAN_SEG;
     if (beg >= nb) return;
@@ -108,7 +109,7 @@ struct ScanLocal {  // thread t: sum of hist[t*SEG .. (t+1)*SEG)
     segsum[tid] = s;
   }
 };
-struct ScanTop {  // one thread: exclusive scan of the segment sums; grand total -> offsets[nb]
+struct ScanTop {  static const char* name() { return "scan_top"; }  // one thread: exclusive scan of the segment sums; grand total -> offsets[nb]
   static ZK_HD void run(uint32_t tid, uint32_t nseg, uint32_t nb, uint32_t* segsum, uint32_t* offsets) {
     if (tid != 0) return;
     uint32_t run = 0;
@@ -116,7 +117,7 @@ struct ScanTop {  // one thread: exclusive scan of the segment sums; grand total
     offsets[nb] = run;
   }
 };
-struct ScanApply {  // offsets[] and the scatter cursors (cursor aliases hist)
+struct ScanApply {  static const char* name() { return "scan_apply"; }  // offsets[] and the scatter cursors (cursor aliases hist)
   static ZK_HD void run(uint32_t tid, uint32_t nb, uint32_t* hist_cursor, const uint32_t* segsum, uint32_t* offsets) {
     uint32_t beg = tid * SCAN_SEG;
     if (beg >= nb) return;
@@ -129,6 +130,7 @@ struct ScanApply {  // offsets[] and the scatter cursors (cursor aliases hist)
 struct alignas(8) Entry { uint32_t key, val; };  // val = point index | sign << 31
 
 struct Scatter {
+  static const char* name() { return "scatter"; }
   static ZK_HD void run(uint32_t tid, MsmPlan p, const uint32_t* scalars, uint32_t* cursor, Entry* entries) {
     if (tid >= p.n) return;
     uint32_t s[SCALAR_LIMBS];
@@ -150,16 +152,21 @@ struct Scatter {
 };
 
 // ---------------------------------------------------------------- bucket accumulation
+static constexpr uint32_t NO_KEY = 0xffffffffu;
+static constexpr uint32_t FIX_L = 16;  // partials per fix-up thread
+
 template <class C> struct Accumulate {
   typedef typename C::F F;
+  static const char* name() { return "accumulate"; }
   static ZK_HD void run(uint32_t tid, MsmPlan p, const uint32_t* offsets, const Entry* entries,
-                        const Affine<F>* points, XYZZ<F>* bucket_sums, XYZZ<F>* partials) {
+                        const Affine<F>* points, XYZZ<F>* bucket_sums, XYZZ<F>* partials, uint32_t* partial_keys) {
     uint32_t total = offsets[p.nb];
     uint64_t beg64 = (uint64_t)tid * p.L;
-    if (beg64 >= total) return;
+    if (beg64 >= total) { partial_keys[tid] = NO_KEY; return; }
     uint32_t beg = (uint32_t)beg64, end = beg + p.L < total ? beg + p.L : total;
     uint32_t key = entries[beg].key;
     bool head = beg == 0 || entries[beg - 1].key != key;   // segment starts its bucket?
+    partial_keys[tid] = head ? NO_KEY : key;
     XYZZ<F> acc;
     set_inf(acc);
     for (uint32_t pos = beg; pos < end; pos++) {
@@ -178,17 +185,42 @@ template <class C> struct Accumulate {
   }
 };
 
-template <class C> struct BucketFixup {
+// One level of the fix-up tree.  Input: `count` partial sums in bucket order, keys_in[t] = bucket the
+// partial continues (NO_KEY = none).  Thread u folds FIX_L consecutive partials: a run of equal keys
+// that STARTS inside the thread's range is added to its bucket sum (exactly one thread per bucket and
+// level does that); a run that continues from the previous range is passed on as one partial of the
+// next level.  Balanced for any scalar distribution: a bucket spanning m chunks costs log_16(m) levels.
+template <class C> struct FixupLevel {
   typedef typename C::F F;
-  static ZK_HD void run(uint32_t tid, MsmPlan p, const uint32_t* offsets, XYZZ<F>* bucket_sums, const XYZZ<F>* partials) {
-    if (tid >= p.nb) return;
-    uint32_t beg = offsets[tid], end = offsets[tid + 1];
-    if (beg == end) { XYZZ<F> z; set_inf(z); bucket_sums[tid] = z; return; }
-    uint32_t t0 = beg / p.L, t1 = (end - 1) / p.L;
-    if (t1 == t0) return;
-    XYZZ<F> acc = bucket_sums[tid];
-    for (uint32_t t = t0 + 1; t <= t1; t++) { XYZZ<F> q = partials[t]; xyzz_add(acc, q); }
-    bucket_sums[tid] = acc;
+  static const char* name() { return "fixup_level"; }
+  static ZK_HD void run(uint32_t tid, uint32_t count, const uint32_t* keys_in, const XYZZ<F>* parts_in,
+                        uint32_t* keys_out, XYZZ<F>* parts_out, XYZZ<F>* bucket_sums) {
+    uint32_t beg = tid * FIX_L;
+    if (beg >= count) return;
+    uint32_t end = beg + FIX_L < count ? beg + FIX_L : count;
+    uint32_t out_key = NO_KEY;
+    uint32_t key = NO_KEY;
+    bool head = true;
+    XYZZ<F> acc;
+    set_inf(acc);
+    for (uint32_t t = beg; t < end; t++) {
+      uint32_t k = keys_in[t];
+      if (k != key) {
+        if (key != NO_KEY) {
+          if (head) { XYZZ<F> b = bucket_sums[key]; xyzz_add(b, acc); bucket_sums[key] = b; }
+          else { parts_out[tid] = acc; out_key = key; }
+        }
+        set_inf(acc);
+        key = k;
+        head = !(t == beg && beg > 0 && keys_in[beg - 1] == k);
+      }
+      if (k != NO_KEY) { XYZZ<F> q = parts_in[t]; xyzz_add(acc, q); }
+    }
+    if (key != NO_KEY) {
+      if (head) { XYZZ<F> b = bucket_sums[key]; xyzz_add(b, acc); bucket_sums[key] = b; }
+      else { parts_out[tid] = acc; out_key = key; }
+    }
+    keys_out[tid] = out_key;
   }
 };
 
@@ -204,20 +236,20 @@ template <class F> ZK_HD void xyzz_mul_small(XYZZ<F>& p, uint32_t s) {
   }
 }
 
-// thread (win, k): out = sum_{i<K} (k K + i + 1) * bucket[win*B + k*K + i]
+// thread (win, k): out = sum_{i<K} (k K + i + 1) * bucket[win*B + k*K + i]; empty buckets were never written
 template <class C> struct BucketReduce {
   typedef typename C::F F;
-  static ZK_HD void run(uint32_t tid, MsmPlan p, const XYZZ<F>* bucket_sums, XYZZ<F>* out) {
+  static const char* name() { return "bucket_reduce"; }
+  static ZK_HD void run(uint32_t tid, MsmPlan p, const uint32_t* offsets, const XYZZ<F>* bucket_sums, XYZZ<F>* out) {
     uint32_t chunks = p.B / p.K;
     if (tid >= p.nwin * chunks) return;
     uint32_t win = tid / chunks, k = tid % chunks;
-    const XYZZ<F>* b = bucket_sums + (size_t)win * p.B + (size_t)k * p.K;
+    size_t base = (size_t)win * p.B + (size_t)k * p.K;
     XYZZ<F> run, acc;
     set_inf(run);
     set_inf(acc);
     for (int i = (int)p.K - 1; i >= 0; i--) {
-      XYZZ<F> q = b[i];
-      xyzz_add(run, q);
+      if (offsets[base + i] != offsets[base + i + 1]) { XYZZ<F> q = bucket_sums[base + i]; xyzz_add(run, q); }
       xyzz_add(acc, run);
     }
     xyzz_mul_small(run, k * p.K);
@@ -229,6 +261,7 @@ template <class C> struct BucketReduce {
 // level of the pairwise tree: arr is nwin rows of `m` points (row pitch `pitch`); row[i] += row[i + half]
 template <class C> struct PairSum {
   typedef typename C::F F;
+  static const char* name() { return "pair_sum"; }
   static ZK_HD void run(uint32_t tid, uint32_t nwin, uint32_t pitch, uint32_t m, uint32_t half, XYZZ<F>* arr) {
     if (tid >= nwin * half) return;
     uint32_t win = tid / half, i = tid % half;
@@ -259,6 +292,7 @@ template <> ZK_HD void load_canonical<Fp2>(Affine<Fp2>& a, const uint32_t* in) {
 // out_xyzz (Montgomery XYZZ, for multi-GPU partials) and out_affine (canonical limbs + flag) may be null.
 template <class C> struct Finish {
   typedef typename C::F F;
+  static const char* name() { return "finish"; }
   static ZK_HD void run(uint32_t tid, uint32_t nwin, uint32_t pitch, uint32_t c, const XYZZ<F>* arr,
                         XYZZ<F>* out_xyzz, uint32_t* out_affine, uint32_t* out_inf) {
     if (tid != 0) return;
@@ -281,6 +315,7 @@ template <class C> struct Finish {
 // sum of k XYZZ partial results (multi-GPU combine) -> canonical affine
 template <class C> struct CombinePartials {
   typedef typename C::F F;
+  static const char* name() { return "combine_partials"; }
   static ZK_HD void run(uint32_t tid, uint32_t k, const XYZZ<F>* parts, uint32_t* out_affine, uint32_t* out_inf) {
     if (tid != 0) return;
     XYZZ<F> acc;
@@ -297,6 +332,7 @@ template <class C> struct CombinePartials {
 // canonical affine limbs (+ optional infinity flags) -> Montgomery affine, slab 0
 template <class C> struct LoadPoints {
   typedef typename C::F F;
+  static const char* name() { return "load_points"; }
   static ZK_HD void run(uint32_t tid, uint32_t n, const uint32_t* canon, const uint8_t* inf, Affine<F>* out) {
     if (tid >= n) return;
     Affine<F> a;
@@ -309,6 +345,7 @@ template <class C> struct LoadPoints {
 // slab w = 2^c * slab (w-1), w = 1 .. W-1 (one thread per point walks all levels)
 template <class C> struct PrecomputeSlabs {
   typedef typename C::F F;
+  static const char* name() { return "precompute_slabs"; }
   static ZK_HD void run(uint32_t tid, uint32_t n, uint32_t stride, uint32_t c, uint32_t W, Affine<F>* pts) {
     if (tid >= n) return;
     Affine<F> a = pts[tid];
@@ -330,6 +367,7 @@ template <class C> struct PrecomputeSlabs {
 // table[j] = 2^j * base, j < 256, built by one thread then converted to affine in parallel
 template <class C> struct BaseTableChain {
   typedef typename C::F F;
+  static const char* name() { return "base_table_chain"; }
   static ZK_HD void run(uint32_t tid, const uint32_t* base_canon, XYZZ<F>* chain) {
     if (tid != 0) return;
     Affine<F> a;
@@ -341,6 +379,7 @@ template <class C> struct BaseTableChain {
 };
 template <class C> struct BaseTableAffine {
   typedef typename C::F F;
+  static const char* name() { return "base_table_affine"; }
   static ZK_HD void run(uint32_t tid, const XYZZ<F>* chain, Affine<F>* table) {
     if (tid >= 256) return;
     Affine<F> a;
@@ -351,6 +390,7 @@ template <class C> struct BaseTableAffine {
 // out[i] = scalars[i] * base as Montgomery affine ((0,0) for infinity); full 256-bit scalars
 template <class C> struct FixedBaseMul {
   typedef typename C::F F;
+  static const char* name() { return "fixed_base_mul"; }
   static ZK_HD void run(uint32_t tid, uint32_t n, const uint32_t* scalars, const Affine<F>* table, Affine<F>* out) {
     if (tid >= n) return;
     XYZZ<F> acc;
@@ -369,6 +409,7 @@ template <class C> struct FixedBaseMul {
 // Montgomery affine -> canonical limbs + infinity flags (inverse of LoadPoints)
 template <class C> struct StorePoints {
   typedef typename C::F F;
+  static const char* name() { return "store_points"; }
   static ZK_HD void run(uint32_t tid, uint32_t n, const Affine<F>* in, uint32_t* canon, uint8_t* inf) {
     if (tid >= n) return;
     Affine<F> a = in[tid];
@@ -411,6 +452,14 @@ inline MsmPlan msm_plan(uint32_t n, uint32_t c, bool precomp, uint32_t stride) {
   return p;
 }
 
+// slots needed for the partial sums of all fix-up levels
+inline size_t msm_partial_slots(const MsmPlan& p) {
+  size_t total = 0;
+  uint32_t count = p.acc_threads;
+  for (;;) { total += count; if (count <= 1) break; count = (count + FIX_L - 1) / FIX_L; }
+  return total + 1;
+}
+
 // device buffers one MSM needs (sizes in elements), all owned by the caller
 template <class C> struct MsmBuffers {
   typedef typename C::F F;
@@ -419,7 +468,8 @@ template <class C> struct MsmBuffers {
   uint32_t* segsum;        // ceil(nb / SCAN_SEG)
   Entry* entries;          // max_entries
   XYZZ<F>* bucket_sums;    // nb
-  XYZZ<F>* partials;       // acc_threads
+  XYZZ<F>* partials;       // msm_partial_slots(): level 0 (one per accumulate thread), then the fix-up levels
+  uint32_t* partial_keys;  // same count
   XYZZ<F>* reduced;        // nwin * (B / K)
   uint32_t* err;           // 1
 };
@@ -438,11 +488,23 @@ void msm_launch(Exec& ex, const MsmPlan& p, const MsmBuffers<C>& b, const Affine
   ex.template launch<ScanApply>(nseg, p.nb, b.hist_cursor, (const uint32_t*)b.segsum, b.offsets);
   ex.template launch<Scatter>(p.n, p, d_scalars, b.hist_cursor, b.entries);
   ex.template launch<Accumulate<C>>(p.acc_threads, p, (const uint32_t*)b.offsets, (const Entry*)b.entries, points,
-                                    b.bucket_sums, b.partials);
-  ex.template launch<BucketFixup<C>>(p.nb, p, (const uint32_t*)b.offsets, b.bucket_sums,
-                                     (const XYZZ<typename C::F>*)b.partials);
+                                    b.bucket_sums, b.partials, b.partial_keys);
+  {  // fix-up tree over the per-chunk partial sums: level l reads region l, writes region l+1
+    uint32_t count = p.acc_threads;
+    XYZZ<typename C::F>* pin = b.partials;
+    uint32_t* kin = b.partial_keys;
+    while (count > 1) {
+      uint32_t next = (count + FIX_L - 1) / FIX_L;
+      ex.template launch<FixupLevel<C>>(next, count, (const uint32_t*)kin, (const XYZZ<typename C::F>*)pin, kin + count,
+                                        pin + count, b.bucket_sums);
+      pin += count;
+      kin += count;
+      count = next;
+    }
+  }
   uint32_t chunks = p.B / p.K;
-  ex.template launch<BucketReduce<C>>(p.nwin * chunks, p, (const XYZZ<typename C::F>*)b.bucket_sums, b.reduced);
+  ex.template launch<BucketReduce<C>>(p.nwin * chunks, p, (const uint32_t*)b.offsets,
+                                      (const XYZZ<typename C::F>*)b.bucket_sums, b.reduced);
   uint32_t m = chunks;
   while (m > 1) {
     uint32_t half = (m + 1) / 2;

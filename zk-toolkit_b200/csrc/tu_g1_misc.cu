@@ -3,7 +3,7 @@
 #define ZK_FMUL_NOINLINE
 #include "launch.cuh"
 #include "msm.cuh"
-ZK_INSTANTIATE_KERNEL(zk::BucketFixup<zk::G1>);
+ZK_INSTANTIATE_KERNEL(zk::FixupLevel<zk::G1>);
 ZK_INSTANTIATE_KERNEL(zk::BucketReduce<zk::G1>);
 ZK_INSTANTIATE_KERNEL(zk::PairSum<zk::G1>);
 ZK_INSTANTIATE_KERNEL(zk::Finish<zk::G1>);

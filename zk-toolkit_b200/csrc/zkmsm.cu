@@ -17,7 +17,7 @@ using namespace zk;
 // ------------------------------------------------------------------------------------------------
 
 // ------------------------------------------------------------------------------------------------
-enum { WS_HIST, WS_OFFSETS, WS_SEGSUM, WS_ENTRIES, WS_BUCKETS, WS_PARTIALS, WS_REDUCED, WS_SCALARS, WS_MISC, WS_COUNT };
+enum { WS_HIST, WS_OFFSETS, WS_SEGSUM, WS_ENTRIES, WS_BUCKETS, WS_PARTIALS, WS_PKEYS, WS_REDUCED, WS_SCALARS, WS_MISC, WS_COUNT };
 
 struct alignas(16) ResultBlock {      // device + pinned host mirror
   uint32_t xyzz[96];      // first: XYZZ<F> needs 16-byte alignment
@@ -38,6 +38,7 @@ struct zkmsm_ctx {
   int last_launches;
   int pending;          // 0 none, 1 kernels enqueued, 2 trivially infinity (n == 0)
   int pending_words;    // 24 or 48
+  LaunchProfile* prof;  // non-null while profiling is enabled
 };
 
 struct zkmsm_points {
@@ -118,6 +119,7 @@ extern "C" int zkmsm_destroy(zkmsm_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   for (int i = 0; i < WS_COUNT; i++)
     if (ctx->ws[i]) cudaFree(ctx->ws[i]);
+  if (ctx->prof) zkmsm_profile(ctx, 0);
   cudaFree(ctx->d_res);
   cudaFreeHost(ctx->h_res);
   cudaStreamDestroy(ctx->own_stream);
@@ -148,6 +150,38 @@ extern "C" int zkmsm_host_alloc(size_t bytes, void** out) {
 extern "C" int zkmsm_host_free(void* p) { return cudaFreeHost(p) == cudaSuccess ? ZKMSM_OK : ZKMSM_ERR_CUDA; }
 
 extern "C" int zkmsm_last_launch_count(const zkmsm_ctx* ctx) { return ctx ? ctx->last_launches : 0; }
+
+extern "C" int zkmsm_profile(zkmsm_ctx* ctx, int enable) {
+  if (!ctx) return ZKMSM_ERR_INVALID_ARG;
+  CU(ctx, cudaSetDevice(ctx->device));
+  if (enable && !ctx->prof) {
+    ctx->prof = new (std::nothrow) LaunchProfile();
+    if (!ctx->prof) return fail(ctx, ZKMSM_ERR_NOMEM, "host allocation");
+    for (int i = 0; i < LaunchProfile::MAX; i++) { CU(ctx, cudaEventCreate(&ctx->prof->beg[i])); CU(ctx, cudaEventCreate(&ctx->prof->end[i])); }
+  } else if (!enable && ctx->prof) {
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < LaunchProfile::MAX; i++) { cudaEventDestroy(ctx->prof->beg[i]); cudaEventDestroy(ctx->prof->end[i]); }
+    delete ctx->prof;
+    ctx->prof = nullptr;
+  }
+  return ZKMSM_OK;
+}
+
+extern "C" int zkmsm_profile_read(zkmsm_ctx* ctx, int max_entries, char* names, size_t name_stride, float* ms,
+                                  uint32_t* threads) {
+  if (!ctx || !ctx->prof) return fail(ctx, ZKMSM_ERR_INVALID_ARG, "profiling is not enabled");
+  CU(ctx, cudaSetDevice(ctx->device));
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  int n = ctx->prof->n < max_entries ? ctx->prof->n : max_entries;
+  for (int i = 0; i < n; i++) {
+    float t = 0;
+    CU(ctx, cudaEventElapsedTime(&t, ctx->prof->beg[i], ctx->prof->end[i]));
+    if (ms) ms[i] = t;
+    if (threads) threads[i] = ctx->prof->threads[i];
+    if (names && name_stride) { strncpy(names + i * name_stride, ctx->prof->names[i], name_stride - 1); names[i * name_stride + name_stride - 1] = 0; }
+  }
+  return n;
+}
 
 // ------------------------------------------------------------------------------------------------
 // point sets
@@ -280,7 +314,8 @@ static int msm_enqueue_impl(zkmsm_ctx* ctx, const zkmsm_points* ps, const uint32
   if ((rc = ws_reserve(ctx, WS_HIST, sizeof(uint32_t) * p.nb)) || (rc = ws_reserve(ctx, WS_OFFSETS, sizeof(uint32_t) * (p.nb + 1))) ||
       (rc = ws_reserve(ctx, WS_SEGSUM, sizeof(uint32_t) * nseg)) || (rc = ws_reserve(ctx, WS_ENTRIES, sizeof(Entry) * (size_t)p.max_entries)) ||
       (rc = ws_reserve(ctx, WS_BUCKETS, sizeof(XYZZ<F>) * (size_t)p.nb)) ||
-      (rc = ws_reserve(ctx, WS_PARTIALS, sizeof(XYZZ<F>) * (size_t)p.acc_threads)) ||
+      (rc = ws_reserve(ctx, WS_PARTIALS, sizeof(XYZZ<F>) * msm_partial_slots(p))) ||
+      (rc = ws_reserve(ctx, WS_PKEYS, sizeof(uint32_t) * msm_partial_slots(p))) ||
       (rc = ws_reserve(ctx, WS_REDUCED, sizeof(XYZZ<F>) * (size_t)p.nwin * (p.B / p.K))))
     return rc;
   MsmBuffers<C> b;
@@ -290,9 +325,11 @@ static int msm_enqueue_impl(zkmsm_ctx* ctx, const zkmsm_points* ps, const uint32
   b.entries = (Entry*)ctx->ws[WS_ENTRIES];
   b.bucket_sums = (XYZZ<F>*)ctx->ws[WS_BUCKETS];
   b.partials = (XYZZ<F>*)ctx->ws[WS_PARTIALS];
+  b.partial_keys = (uint32_t*)ctx->ws[WS_PKEYS];
   b.reduced = (XYZZ<F>*)ctx->ws[WS_REDUCED];
   b.err = &ctx->d_res->err;
-  CudaExec ex(ctx->stream);
+  if (ctx->prof) ctx->prof->n = 0;
+  CudaExec ex(ctx->stream, ctx->prof);
   XYZZ<F>* d_xyzz = d_partial_out ? (XYZZ<F>*)d_partial_out : (XYZZ<F>*)ctx->d_res->xyzz;
   msm_launch<C>(ex, p, b, (const Affine<F>*)ps->d_pts, d_scalars, want_affine ? (XYZZ<F>*)nullptr : d_xyzz,
                 want_affine ? ctx->d_res->affine : (uint32_t*)nullptr, want_affine ? &ctx->d_res->inf : (uint32_t*)nullptr);
