@@ -144,8 +144,9 @@ int zkmsm_g2_points_from_scalars(zkmsm_ctx* ctx, const uint32_t base_xy[48], con
                                  unsigned flags, zkmsm_points** out);
 
 /* ---- diagnostics: integer-multiply throughput of this device (roofline denominator).
- * variant 0: independent IMAD.WIDE.U32 chains; 1: carry-chained IMAD.WIDE.U32.X (mad.lo.cc/
- * madc.hi.cc pairs); 2: 32-bit IMAD.  Returns limb products per second. */
+ * variant 0: independent mad.wide.u32; 1: carry-chained IMAD.WIDE.U32.X (mad.lo.cc/madc.hi.cc
+ * pairs); 2: 32-bit IMAD (half a limb product each); 3: as 1 with data-dependent multipliers (the
+ * Montgomery inner loop's shape).  Returns multiply-accumulates per second. */
 int zkmsm_bench_imad(zkmsm_ctx* ctx, int variant, int iters, double* out_lp_per_s, double* out_ms);
 
 #ifdef __cplusplus

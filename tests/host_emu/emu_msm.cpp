@@ -18,6 +18,12 @@ struct HostExec {
     launches++;
   }
   void zero(void* p, size_t bytes) { memset(p, 0, bytes); }
+  void exclusive_scan(uint32_t nb, uint32_t* hist_cursor, uint32_t* offsets, uint32_t* segsum) {
+    uint32_t nseg = (nb + SCAN_SEG - 1) / SCAN_SEG;
+    launch<ScanLocal>(nseg, nb, (const uint32_t*)hist_cursor, segsum);
+    launch<ScanTop>(1u, nseg, nb, segsum, offsets);
+    launch<ScanApply>(nseg, nb, hist_cursor, (const uint32_t*)segsum, offsets);
+  }
 };
 
 template <class C>
@@ -75,6 +81,17 @@ int emu_g1_msm_sharded(const uint32_t* xy, const uint32_t* scalars, uint32_t n, 
   }
   HostExec ex;
   ex.launch<CombinePartials<G1>>(1u, k, (const XYZZ<Fp>*)parts.data(), out_xy, out_inf);
+  return 0;
+}
+// one rank's share: partial point as the opaque 48-word blob of the C ABI, and the combine step
+int emu_g1_msm_partial(const uint32_t* xy, const uint32_t* scalars, uint32_t n, uint32_t* out_partial) {
+  if (n == 0) { memset(out_partial, 0, sizeof(XYZZ<Fp>)); return 0; }
+  uint32_t dummy[24], dinf;
+  return emu_msm<G1>(xy, nullptr, scalars, n, n, 0, 0, 0, 0, dummy, &dinf, out_partial);
+}
+int emu_g1_combine(const uint32_t* partials, uint32_t k, uint32_t* out_xy, uint32_t* out_inf) {
+  HostExec ex;
+  ex.launch<CombinePartials<G1>>(1u, k, (const XYZZ<Fp>*)partials, out_xy, out_inf);
   return 0;
 }
 // `base * k_i` for a vector of raw 256-bit scalars (FixedBaseMul path)

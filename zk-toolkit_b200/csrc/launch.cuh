@@ -37,6 +37,9 @@ template <class Body> struct Launch : LaunchBase<Body, decltype(Body::run)> {};
 #define ZK_INSTANTIATE_KERNEL(...) template struct zk::LaunchBase<__VA_ARGS__, decltype(__VA_ARGS__::run)>
 
 // Exec policy for msm_launch (msm.cuh): stream-ordered CUDA launches
+// block-cooperative exclusive scan (tu_sort.cu): offsets[0..n] = scan(hist), hist <- offsets (cursors)
+cudaError_t zk_exclusive_scan(cudaStream_t st, uint32_t n, uint32_t* hist_cursor, uint32_t* offsets, uint32_t* blocksums);
+
 // optional per-launch timing (zkmsm_profile): CUDA events on the launching stream around every kernel
 struct LaunchProfile {
   static constexpr int MAX = 96;
@@ -66,6 +69,20 @@ struct CudaExec {
     cudaError_t e = Launch<Body>::go(st, nthreads, args...);
     if (slot >= 0) cudaEventRecord(prof->end[slot], st);
     launches++;
+    if (e != cudaSuccess) err = e;
+  }
+  void exclusive_scan(uint32_t n, uint32_t* hist_cursor, uint32_t* offsets, uint32_t* blocksums) {
+    if (err != cudaSuccess) return;
+    int slot = -1;
+    if (prof && prof->n < LaunchProfile::MAX) {
+      slot = prof->n++;
+      prof->names[slot] = "exclusive_scan";
+      prof->threads[slot] = n;
+      cudaEventRecord(prof->beg[slot], st);
+    }
+    cudaError_t e = zk_exclusive_scan(st, n, hist_cursor, offsets, blocksums);
+    if (slot >= 0) cudaEventRecord(prof->end[slot], st);
+    launches += 3;
     if (e != cudaSuccess) err = e;
   }
   void zero(void* p, size_t bytes) {

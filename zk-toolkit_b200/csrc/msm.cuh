@@ -97,8 +97,10 @@ struct RecodeCount {
   }
 };
 
-// ---------------------------------------------------------------- exclusive scan (3 small kernels)
-static constexpr uint32_t SCAN_SEG = 256;
+// ---------------------------------------------------------------- exclusive scan
+// Reference formulation as three bodies (used by the CPU emulation of the pipeline); the CUDA build
+// runs the block-cooperative kernels of tu_sort.cu instead (CudaExec::exclusive_scan), same result.
+static constexpr uint32_t SCAN_SEG = 1024;  // elements per scan block; segsum holds nb / SCAN_SEG + 1 sums
 
 struct ScanLocal {  static const char* name() { return "scan_local"; }  // thread t: sum of hist[t*SEG .. (t+1)*SEG)
   static ZK_HD void run(uint32_t tid, uint32_t nb, const uint32_t* hist, uint32_t* segsum) {
@@ -479,13 +481,11 @@ template <class C> struct MsmBuffers {
 template <class C, class Exec>
 void msm_launch(Exec& ex, const MsmPlan& p, const MsmBuffers<C>& b, const Affine<typename C::F>* points,
                 const uint32_t* d_scalars, XYZZ<typename C::F>* out_xyzz, uint32_t* out_affine, uint32_t* out_inf) {
-  uint32_t nseg = (p.nb + SCAN_SEG - 1) / SCAN_SEG;
   ex.zero(b.hist_cursor, sizeof(uint32_t) * p.nb);
   ex.zero(b.err, sizeof(uint32_t));
   ex.template launch<RecodeCount>(p.n, p, d_scalars, b.hist_cursor, b.err);
-  ex.template launch<ScanLocal>(nseg, p.nb, (const uint32_t*)b.hist_cursor, b.segsum);
-  ex.template launch<ScanTop>(1u, nseg, p.nb, b.segsum, b.offsets);
-  ex.template launch<ScanApply>(nseg, p.nb, b.hist_cursor, (const uint32_t*)b.segsum, b.offsets);
+  // offsets[0..nb] = exclusive scan of the histogram; the histogram array becomes the scatter cursors
+  ex.exclusive_scan(p.nb, b.hist_cursor, b.offsets, b.segsum);
   ex.template launch<Scatter>(p.n, p, d_scalars, b.hist_cursor, b.entries);
   ex.template launch<Accumulate<C>>(p.acc_threads, p, (const uint32_t*)b.offsets, (const Entry*)b.entries, points,
                                     b.bucket_sums, b.partials, b.partial_keys);

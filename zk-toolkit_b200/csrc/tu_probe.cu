@@ -40,6 +40,24 @@ __global__ void __launch_bounds__(256) imad_probe(uint32_t* sink, uint32_t seed,
 #pragma unroll
     for (int k = 0; k < 12; k++) s ^= e[k] ^ o[k];
     if (s == 0x12345678u) sink[0] = s;
+  } else if (VARIANT == 3) {   // as 1, but every row's multiplier is the other accumulator's low limb (as the
+                               // Montgomery m_i is), so nothing is loop-invariant and nothing can be hoisted
+    uint32_t e[12], o[12], xs[6];
+#pragma unroll
+    for (int k = 0; k < 12; k++) { e[k] = x + k; o[k] = y + k; }
+#pragma unroll
+    for (int k = 0; k < 6; k++) xs[k] = x * (k + 3) + 1;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+      for (int r = 0; r < 2; r++) {
+        detail::row_mad<12>(o, detail::Arr{xs}, e[0]);
+        detail::row_mad<12>(e, detail::Arr{xs}, o[0]);
+      }
+    }
+    uint32_t s = 0;
+#pragma unroll
+    for (int k = 0; k < 12; k++) s ^= e[k] ^ o[k];
+    if (s == 0x12345678u) sink[0] = s;
   } else {                     // 16 independent 32-bit IMAD
     uint32_t a[16];
 #pragma unroll
@@ -62,6 +80,7 @@ __global__ void __launch_bounds__(256) imad_probe(uint32_t* sink, uint32_t seed,
 extern "C" int zkmsm_probe_launch(int variant, int grid, int block, cudaStream_t st, uint32_t* sink, int iters) {
   if (variant == 0) imad_probe<0><<<grid, block, 0, st>>>(sink, 7u, iters);
   else if (variant == 1) imad_probe<1><<<grid, block, 0, st>>>(sink, 7u, iters);
+  else if (variant == 3) imad_probe<3><<<grid, block, 0, st>>>(sink, 7u, iters);
   else imad_probe<2><<<grid, block, 0, st>>>(sink, 7u, iters);
   return (int)cudaGetLastError();
 }

@@ -1,10 +1,96 @@
-// recode / histogram / scan / scatter kernels (no field arithmetic)
+// recode / histogram / scatter kernels and the block-cooperative exclusive scan (no field arithmetic)
 #define ZK_DEFINE_LAUNCH
 #define ZK_FMUL_NOINLINE
 #include "launch.cuh"
 #include "msm.cuh"
 ZK_INSTANTIATE_KERNEL(zk::RecodeCount);
-ZK_INSTANTIATE_KERNEL(zk::ScanLocal);
-ZK_INSTANTIATE_KERNEL(zk::ScanTop);
-ZK_INSTANTIATE_KERNEL(zk::ScanApply);
 ZK_INSTANTIATE_KERNEL(zk::Scatter);
+
+namespace zk {
+
+// 256 threads x 4 consecutive elements (one 128-bit load) = SCAN_SEG elements per block
+static constexpr int SCAN_THREADS = 256;
+static_assert(SCAN_THREADS * 4 == SCAN_SEG, "scan tile");
+
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* total) {
+  __shared__ uint32_t warp_sums[SCAN_THREADS / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t inc = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= d) inc += t;
+  }
+  if (lane == 31) warp_sums[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t w = lane < SCAN_THREADS / 32 ? warp_sums[lane] : 0, winc = w;
+#pragma unroll
+    for (int d = 1; d < SCAN_THREADS / 32; d <<= 1) {
+      uint32_t t = __shfl_up_sync(0xffffffffu, winc, d);
+      if (lane >= d) winc += t;
+    }
+    if (lane < SCAN_THREADS / 32) warp_sums[lane] = winc - w;  // exclusive warp bases
+    if (lane == SCAN_THREADS / 32 - 1) *total = winc;
+  }
+  __syncthreads();
+  return inc - v + warp_sums[warp];
+}
+
+__device__ __forceinline__ uint4 load4(const uint32_t* p, uint32_t i, uint32_t n) {
+  if (i + 3 < n) return *reinterpret_cast<const uint4*>(p + i);
+  uint4 v = make_uint4(0, 0, 0, 0);
+  if (i < n) v.x = p[i];
+  if (i + 1 < n) v.y = p[i + 1];
+  if (i + 2 < n) v.z = p[i + 2];
+  return v;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_block_sums(uint32_t n, const uint32_t* hist, uint32_t* blocksums) {
+  __shared__ uint32_t total;
+  uint32_t i = (blockIdx.x * SCAN_THREADS + threadIdx.x) * 4;
+  uint4 v = load4(hist, i, n);
+  block_exclusive_scan(v.x + v.y + v.z + v.w, &total);
+  if (threadIdx.x == 0) blocksums[blockIdx.x] = total;
+}
+
+// one block: exclusive scan of up to 8 * SCAN_THREADS block sums in place; grand total -> *grand
+__global__ void __launch_bounds__(SCAN_THREADS) scan_top_level(uint32_t nblocks, uint32_t* blocksums, uint32_t* grand) {
+  __shared__ uint32_t total;
+  uint32_t run = 0;
+  for (uint32_t base = 0; base < nblocks; base += SCAN_THREADS) {   // tiles in order, carried base
+    uint32_t i = base + threadIdx.x;
+    uint32_t v = i < nblocks ? blocksums[i] : 0;
+    uint32_t ex = block_exclusive_scan(v, &total);
+    if (i < nblocks) blocksums[i] = run + ex;
+    run += total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *grand = run;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_apply(uint32_t n, uint32_t* hist_cursor, const uint32_t* blocksums, uint32_t* offsets) {
+  __shared__ uint32_t total;
+  uint32_t i = (blockIdx.x * SCAN_THREADS + threadIdx.x) * 4;
+  uint4 v = load4(hist_cursor, i, n);
+  uint32_t ex = block_exclusive_scan(v.x + v.y + v.z + v.w, &total) + blocksums[blockIdx.x];
+  uint4 o = make_uint4(ex, ex + v.x, ex + v.x + v.y, ex + v.x + v.y + v.z);
+  if (i + 3 < n) {
+    *reinterpret_cast<uint4*>(offsets + i) = o;
+    *reinterpret_cast<uint4*>(hist_cursor + i) = o;
+  } else {
+    if (i < n) { offsets[i] = o.x; hist_cursor[i] = o.x; }
+    if (i + 1 < n) { offsets[i + 1] = o.y; hist_cursor[i + 1] = o.y; }
+    if (i + 2 < n) { offsets[i + 2] = o.z; hist_cursor[i + 2] = o.z; }
+  }
+}
+
+cudaError_t zk_exclusive_scan(cudaStream_t st, uint32_t n, uint32_t* hist_cursor, uint32_t* offsets, uint32_t* blocksums) {
+  uint32_t nblocks = (n + SCAN_SEG - 1) / SCAN_SEG;
+  scan_block_sums<<<nblocks, SCAN_THREADS, 0, st>>>(n, hist_cursor, blocksums);
+  scan_top_level<<<1, SCAN_THREADS, 0, st>>>(nblocks, blocksums, offsets + n);
+  scan_apply<<<nblocks, SCAN_THREADS, 0, st>>>(n, hist_cursor, blocksums, offsets);
+  return cudaGetLastError();
+}
+
+}  // namespace zk

@@ -310,7 +310,7 @@ static int msm_enqueue_impl(zkmsm_ctx* ctx, const zkmsm_points* ps, const uint32
   unsigned c = ps->precomp ? ps->c : (ctx->window_override ? ctx->window_override : msm_pick_c((uint32_t)n, false));
   MsmPlan p = msm_plan((uint32_t)n, c, ps->precomp, (uint32_t)ps->n);
   int rc;
-  uint32_t nseg = (p.nb + SCAN_SEG - 1) / SCAN_SEG;
+  uint32_t nseg = (p.nb + SCAN_SEG - 1) / SCAN_SEG + 1;
   if ((rc = ws_reserve(ctx, WS_HIST, sizeof(uint32_t) * p.nb)) || (rc = ws_reserve(ctx, WS_OFFSETS, sizeof(uint32_t) * (p.nb + 1))) ||
       (rc = ws_reserve(ctx, WS_SEGSUM, sizeof(uint32_t) * nseg)) || (rc = ws_reserve(ctx, WS_ENTRIES, sizeof(Entry) * (size_t)p.max_entries)) ||
       (rc = ws_reserve(ctx, WS_BUCKETS, sizeof(XYZZ<F>) * (size_t)p.nb)) ||
@@ -567,14 +567,14 @@ extern "C" int zkmsm_g2_mul_base(zkmsm_ctx* ctx, const uint32_t* base, const uin
 extern "C" int zkmsm_probe_launch(int variant, int grid, int block, cudaStream_t st, uint32_t* sink, int iters);
 
 extern "C" int zkmsm_bench_imad(zkmsm_ctx* ctx, int variant, int iters, double* out_lp_per_s, double* out_ms) {
-  if (!ctx || !out_lp_per_s || iters <= 0 || variant < 0 || variant > 2) return fail(ctx, ZKMSM_ERR_INVALID_ARG, "bad argument");
+  if (!ctx || !out_lp_per_s || iters <= 0 || variant < 0 || variant > 3) return fail(ctx, ZKMSM_ERR_INVALID_ARG, "bad argument");
   CU(ctx, cudaSetDevice(ctx->device));
   int sms = 0;
   CU(ctx, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
   int rc = ws_reserve(ctx, WS_MISC, 64);
   if (rc) return rc;
   dim3 grid(sms * 8), block(256);
-  const double per_iter[3] = {32.0, 24.0, 32.0};
+  const double per_iter[4] = {32.0, 24.0, 32.0, 24.0};
   cudaEvent_t e0, e1;
   CU(ctx, cudaEventCreate(&e0));
   CU(ctx, cudaEventCreate(&e1));
