@@ -21,6 +21,7 @@ int emu_field_op(int field, int op, const uint32_t* a, const uint32_t* b, uint32
       case 4: finv(z, x); break;
       case 5: fto_mont(z, a); break;
       case 6: ffrom_mont(z.v, x); break;
+      case 7: finv_fermat(z, x); break;
       default: return -1;
     }
     memcpy(r, z.v, 48);
@@ -35,6 +36,7 @@ int emu_field_op(int field, int op, const uint32_t* a, const uint32_t* b, uint32
       case 4: finv(z, x); break;
       case 5: fto_mont(z, a); break;
       case 6: ffrom_mont(z.v, x); break;
+      case 7: finv_fermat(z, x); break;
       default: return -1;
     }
     memcpy(r, z.v, 32);

@@ -60,9 +60,13 @@ def test_mont_field_ops(lib, field):
         assert field_op(lib, field, 1, a, b) == (a - b) % p
         # Montgomery product: mont(a,b) = a*b/R
         assert field_op(lib, field, 2, a, b) == a * b * pow(Rm, -1, p) % p
-    for a in vals[1:12]:
+    for a in vals[1:40]:
         am = a * Rm % p
-        assert field_op(lib, field, 4, am) == pow(a, -1, p) * Rm % p
+        assert field_op(lib, field, 4, am) == pow(a, -1, p) * Rm % p      # binary extended Euclid
+    for a in vals[1:8]:
+        am = a * Rm % p
+        assert field_op(lib, field, 7, am) == pow(a, -1, p) * Rm % p      # Fermat cross-check
+    assert field_op(lib, field, 4, 0) == 0
 
 
 def test_fp2_ops(lib):

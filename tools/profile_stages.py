@@ -20,14 +20,14 @@ def main():
     ctx.set_stream(stream.cuda_stream)
     for logn in logns:
         n = 1 << logn
-        for pre in (False, True):
-            pts = ctx.points_from_scalars(1, z.G1Point.g().limbs(), rand_scalars(n, 1), precompute=pre)
-            d_sc = torch.from_numpy(rand_scalars(n, 2).view(np.int32)).cuda()
-            torch.cuda.synchronize()
-            for c in cs:
-                if pre and c:
-                    continue
+        modes = [m == "1" for m in os.environ.get("MODES", "0,1").split(",")]
+        for pre in modes:
+          for c in cs:
+            if True:
                 ctx.set_window(c)
+                pts = ctx.points_from_scalars(1, z.G1Point.g().limbs(), rand_scalars(n, 1), precompute=pre)
+                d_sc = torch.from_numpy(rand_scalars(n, 2).view(np.int32)).cuda()
+                torch.cuda.synchronize()
                 ctx.profile(False)
                 for _ in range(3):
                     ctx.msm_enqueue(pts, d_sc.data_ptr(), n); ctx.msm_result(1)
@@ -46,12 +46,12 @@ def main():
                     a = agg.setdefault(name, [0.0, 0, 0])
                     a[0] += ms; a[1] += 1; a[2] = max(a[2], thr)
                 ssum = sum(v[0] for v in agg.values())
-                print(f"== n=2^{logn} precomp={pre} c={c}: {total:.3f} ms/MSM ({n/total/1e3:.1f} Mpts/s), sum of kernels {ssum:.3f} ms, {len(rows)} launches")
+                print(f"== n=2^{logn} precomp={pre} c={c} L={os.environ.get('ZKMSM_L','-')} K={os.environ.get('ZKMSM_K','-')}: {total:.3f} ms/MSM ({n/total/1e3:.1f} Mpts/s), sum of kernels {ssum:.3f} ms, {len(rows)} launches")
                 for name, (ms, cnt, thr) in agg.items():
                     print(f"   {name:18s} {ms:8.3f} ms  {100*ms/ssum:5.1f}%  x{cnt}  max_threads={thr}")
                 sys.stdout.flush()
-            ctx.set_window(0)
-            ctx.profile(False)
-            pts.free()
+                ctx.set_window(0)
+                ctx.profile(False)
+                pts.free()
 
 main()

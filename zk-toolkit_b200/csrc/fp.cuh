@@ -28,6 +28,7 @@ struct FqCfg {
   ZK_HD static uint32_t one(int i) { return FQ_ONE[i]; }
   ZK_HD static uint32_t r2(int i) { return FQ_R2[i]; }
   ZK_HD static uint32_t pm2(int i) { return FQ_PM2[i]; }
+  ZK_HD static uint32_t r3(int i) { return FQ_R3[i]; }
 };
 
 struct FrCfg {
@@ -37,6 +38,7 @@ struct FrCfg {
   ZK_HD static uint32_t one(int i) { return FR_ONE[i]; }
   ZK_HD static uint32_t r2(int i) { return FR_R2[i]; }
   ZK_HD static uint32_t pm2(int i) { return FR_PM2[i]; }
+  ZK_HD static uint32_t r3(int i) { return FR_R3[i]; }
 };
 
 template <class Cfg>
@@ -237,9 +239,8 @@ template <class C> ZK_HD void ffrom_mont(uint32_t* canon, const Mont<C>& a) {
   for (int i = 0; i < C::N; i++) canon[i] = r.v[i];
 }
 
-// a^(p-2) by left-to-right square-and-multiply (replaces the extended-Euclid inverse of
-// prime_field_elem.rs:379-432; same value since p is prime).  inv(0) = 0.
-template <class C> ZK_HD void finv(Mont<C>& r, const Mont<C>& a) {
+// a^(p-2) by left-to-right square-and-multiply (Fermat).  Kept as the simple cross-check of finv.
+template <class C> ZK_HD void finv_fermat(Mont<C>& r, const Mont<C>& a) {
   Mont<C> acc;
   fset_one(acc);
   for (int i = C::N - 1; i >= 0; i--) {
@@ -250,6 +251,73 @@ template <class C> ZK_HD void finv(Mont<C>& r, const Mont<C>& a) {
     }
   }
   r = acc;
+}
+
+namespace detail {
+template <int n> ZK_HD bool limbs_is_one(const uint32_t* a) {
+  uint32_t o = a[0] ^ 1u;
+#pragma unroll
+  for (int i = 1; i < n; i++) o |= a[i];
+  return o == 0;
+}
+// a >>= 1 (a has n limbs plus the extra top bit `hi`)
+template <int n> ZK_HD void limbs_shr1(uint32_t* a, uint32_t hi) {
+#pragma unroll
+  for (int i = 0; i < n - 1; i++) a[i] = (a[i] >> 1) | (a[i + 1] << 31);
+  a[n - 1] = (a[n - 1] >> 1) | (hi << 31);
+}
+// x = x / 2 mod p  (x < p): x even -> x >> 1, else (x + p) >> 1
+template <class C> ZK_HD void halve_mod(uint32_t* x) {
+  constexpr int n = C::N;
+  uint32_t odd = 0u - (x[0] & 1u);
+  uint32_t t[n];
+  t[0] = ptx::add_cc(x[0], C::p(0) & odd);
+#pragma unroll
+  for (int i = 1; i < n; i++) t[i] = ptx::addc_cc(x[i], C::p(i) & odd);
+  uint32_t hi = ptx::addc(0, 0);
+#pragma unroll
+  for (int i = 0; i < n; i++) x[i] = t[i];
+  limbs_shr1<n>(x, hi);
+}
+// a -= b (a >= b), plain integers
+template <int n> ZK_HD void limbs_sub(uint32_t* a, const uint32_t* b) {
+  a[0] = ptx::sub_cc(a[0], b[0]);
+#pragma unroll
+  for (int i = 1; i < n - 1; i++) a[i] = ptx::subc_cc(a[i], b[i]);
+  a[n - 1] = ptx::subc(a[n - 1], b[n - 1]);
+}
+template <int n> ZK_HD bool limbs_ge(const uint32_t* a, const uint32_t* b) {
+  uint32_t t = ptx::sub_cc(a[0], b[0]);
+#pragma unroll
+  for (int i = 1; i < n; i++) t = ptx::subc_cc(a[i], b[i]);
+  (void)t;
+  return ptx::subc(0, 0) == 0;  // no borrow
+}
+}  // namespace detail
+
+// Modular inverse by the binary extended Euclid (shift / subtract only: ~760 short carry-chain
+// steps instead of ~570 Montgomery multiplications, which matters because exactly ONE thread runs
+// it at the end of an MSM).  Replaces the extended-Euclid inverse of prime_field_elem.rs:379-432;
+// same value since p is prime.  Montgomery in, Montgomery out; inv(0) = 0.
+template <class C> ZK_HD void finv(Mont<C>& r, const Mont<C>& a) {
+  constexpr int n = C::N;
+  if (fis_zero(a)) { fset_zero(r); return; }
+  uint32_t u[n], v[n];
+  Mont<C> x1, x2;
+#pragma unroll
+  for (int i = 0; i < n; i++) { u[i] = a.v[i]; v[i] = C::p(i); x1.v[i] = 0; x2.v[i] = 0; }
+  x1.v[0] = 1;
+  while (!detail::limbs_is_one<n>(u) && !detail::limbs_is_one<n>(v)) {
+    while (!(u[0] & 1)) { detail::limbs_shr1<n>(u, 0); detail::halve_mod<C>(x1.v); }
+    while (!(v[0] & 1)) { detail::limbs_shr1<n>(v, 0); detail::halve_mod<C>(x2.v); }
+    if (detail::limbs_ge<n>(u, v)) { detail::limbs_sub<n>(u, v); fsub(x1, x1, x2); }
+    else { detail::limbs_sub<n>(v, u); fsub(x2, x2, x1); }
+  }
+  // plain inverse of the Montgomery representative aR is a^-1 R^-1; times R^3 (Montgomery) = a^-1 R
+  Mont<C> r3, t = detail::limbs_is_one<n>(u) ? x1 : x2;
+#pragma unroll
+  for (int i = 0; i < n; i++) r3.v[i] = C::r3(i);
+  fmul(r, t, r3);
 }
 
 }  // namespace zk

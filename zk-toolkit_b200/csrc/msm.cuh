@@ -26,6 +26,7 @@
 // The bodies are plain functions of (tid, args) so that tests/host_emu can run the identical
 // pipeline on the CPU (test infrastructure only); the product launches them as CUDA kernels.
 #pragma once
+#include <stdlib.h>
 #include "ec.cuh"
 
 namespace zk {
@@ -155,7 +156,8 @@ struct Scatter {
 
 // ---------------------------------------------------------------- bucket accumulation
 static constexpr uint32_t NO_KEY = 0xffffffffu;
-static constexpr uint32_t FIX_L = 16;  // partials per fix-up thread
+// partials folded per fix-up thread: 4 on the first (widest) level for parallelism, 16 above it
+inline uint32_t fix_fan(uint32_t level) { return level == 0 ? 4u : 16u; }
 
 template <class C> struct Accumulate {
   typedef typename C::F F;
@@ -188,38 +190,40 @@ template <class C> struct Accumulate {
 };
 
 // One level of the fix-up tree.  Input: `count` partial sums in bucket order, keys_in[t] = bucket the
-// partial continues (NO_KEY = none).  Thread u folds FIX_L consecutive partials: a run of equal keys
+// partial continues (NO_KEY = none).  Thread u folds `fan` consecutive partials: a run of equal keys
 // that STARTS inside the thread's range is added to its bucket sum (exactly one thread per bucket and
 // level does that); a run that continues from the previous range is passed on as one partial of the
 // next level.  Balanced for any scalar distribution: a bucket spanning m chunks costs log_16(m) levels.
 template <class C> struct FixupLevel {
   typedef typename C::F F;
   static const char* name() { return "fixup_level"; }
-  static ZK_HD void run(uint32_t tid, uint32_t count, const uint32_t* keys_in, const XYZZ<F>* parts_in,
+  static ZK_HD void run(uint32_t tid, uint32_t count, uint32_t fan, const uint32_t* keys_in, const XYZZ<F>* parts_in,
                         uint32_t* keys_out, XYZZ<F>* parts_out, XYZZ<F>* bucket_sums) {
-    uint32_t beg = tid * FIX_L;
+    uint32_t beg = tid * fan;
     if (beg >= count) return;
-    uint32_t end = beg + FIX_L < count ? beg + FIX_L : count;
+    uint32_t end = beg + fan < count ? beg + fan : count;
     uint32_t out_key = NO_KEY;
     uint32_t key = NO_KEY;
     bool head = true;
     XYZZ<F> acc;
     set_inf(acc);
+    // One add site per element keeps the warp converged: a run that starts here begins from the
+    // bucket's current sum and is stored back when the run ends (no add at the flush).
     for (uint32_t t = beg; t < end; t++) {
       uint32_t k = keys_in[t];
       if (k != key) {
         if (key != NO_KEY) {
-          if (head) { XYZZ<F> b = bucket_sums[key]; xyzz_add(b, acc); bucket_sums[key] = b; }
+          if (head) bucket_sums[key] = acc;
           else { parts_out[tid] = acc; out_key = key; }
         }
-        set_inf(acc);
         key = k;
         head = !(t == beg && beg > 0 && keys_in[beg - 1] == k);
+        if (k != NO_KEY && head) acc = bucket_sums[k]; else set_inf(acc);
       }
       if (k != NO_KEY) { XYZZ<F> q = parts_in[t]; xyzz_add(acc, q); }
     }
     if (key != NO_KEY) {
-      if (head) { XYZZ<F> b = bucket_sums[key]; xyzz_add(b, acc); bucket_sums[key] = b; }
+      if (head) bucket_sums[key] = acc;
       else { parts_out[tid] = acc; out_key = key; }
     }
     keys_out[tid] = out_key;
@@ -448,7 +452,9 @@ inline MsmPlan msm_plan(uint32_t n, uint32_t c, bool precomp, uint32_t stride) {
   p.stride = stride;
   p.max_entries = n * p.W;
   p.L = p.max_entries >= (1u << 23) ? 32 : (p.max_entries >= (1u << 21) ? 16 : 8);
-  p.K = p.B >= 4096 ? 16 : (p.B >= 16 ? 8 : p.B);
+  p.K = p.B >= 8 ? 8 : p.B;
+  if (const char* e = getenv("ZKMSM_L")) { uint32_t v = (uint32_t)atoi(e); if (v >= 1 && v <= 4096) p.L = v; }   // tuning overrides
+  if (const char* e = getenv("ZKMSM_K")) { uint32_t v = (uint32_t)atoi(e); if (v >= 1 && v <= p.B && (v & (v - 1)) == 0) p.K = v; }
   p.acc_threads = (p.max_entries + p.L - 1) / p.L;
   if (p.acc_threads == 0) p.acc_threads = 1;
   return p;
@@ -457,8 +463,8 @@ inline MsmPlan msm_plan(uint32_t n, uint32_t c, bool precomp, uint32_t stride) {
 // slots needed for the partial sums of all fix-up levels
 inline size_t msm_partial_slots(const MsmPlan& p) {
   size_t total = 0;
-  uint32_t count = p.acc_threads;
-  for (;;) { total += count; if (count <= 1) break; count = (count + FIX_L - 1) / FIX_L; }
+  uint32_t count = p.acc_threads, level = 0;
+  for (;;) { total += count; if (count <= 1) break; uint32_t fan = fix_fan(level++); count = (count + fan - 1) / fan; }
   return total + 1;
 }
 
@@ -490,13 +496,13 @@ void msm_launch(Exec& ex, const MsmPlan& p, const MsmBuffers<C>& b, const Affine
   ex.template launch<Accumulate<C>>(p.acc_threads, p, (const uint32_t*)b.offsets, (const Entry*)b.entries, points,
                                     b.bucket_sums, b.partials, b.partial_keys);
   {  // fix-up tree over the per-chunk partial sums: level l reads region l, writes region l+1
-    uint32_t count = p.acc_threads;
+    uint32_t count = p.acc_threads, level = 0;
     XYZZ<typename C::F>* pin = b.partials;
     uint32_t* kin = b.partial_keys;
     while (count > 1) {
-      uint32_t next = (count + FIX_L - 1) / FIX_L;
-      ex.template launch<FixupLevel<C>>(next, count, (const uint32_t*)kin, (const XYZZ<typename C::F>*)pin, kin + count,
-                                        pin + count, b.bucket_sums);
+      uint32_t fan = fix_fan(level++), next = (count + fan - 1) / fan;
+      ex.template launch<FixupLevel<C>>(next, count, fan, (const uint32_t*)kin, (const XYZZ<typename C::F>*)pin,
+                                        kin + count, pin + count, b.bucket_sums);
       pin += count;
       kin += count;
       count = next;
