@@ -1,0 +1,114 @@
+"""Groth16 proof generation on the GPU: the five MSMs of `Prover::prove`
+(src/zk/w_trusted_setup/groth16/zktoolkit_based/prover.rs:96-147).
+
+The reference evaluates, per wire i, `ui[i].eval_with_g1_hidings(xi) * a_i` and sums the results
+(prover.rs:108-117): (m+1) nested MSMs.  Because the group is commutative that equals ONE MSM with the
+aggregated coefficients  sum_i a_i * u_{i,j}  (the canonical affine result is
+identical).  The blinding terms are folded into the same MSMs by appending the single CRS points to
+the resident sets:
+
+    A    = alpha   + sum_j u_j [x^j]_1 + r delta        = MSM(xi_1 ++ [alpha_1, delta_1], u ++ [1, r])
+    B    = beta_2  + sum_j v_j [x^j]_2 + s delta_2      = MSM(xi_2 ++ [beta_2,  delta_2], v ++ [1, s])
+    B_g1 = beta_1  + sum_j v_j [x^j]_1 + s delta_1      = MSM(xi_1 ++ [beta_1,  delta_1], v ++ [1, s])
+    C    = sum_{i>l} a_i uvw_wit_i + sum_j h_j [x^j t/delta]_1 - (r s) delta_1   (one MSM)
+           + s A + r B_g1                                                          (one 2-term MSM)
+
+All scalar work here is exact integer arithmetic mod r on the host (the reference's Fr aggregation,
+qap.rs:99-109, is the next row of the scope table); every group operation runs in libzkmsm.so.
+"""
+from dataclasses import dataclass
+
+import numpy as np
+
+from .api import G1Point, G1Points, G2Point, G2Points, R, default_context, scalars_to_array
+
+
+@dataclass
+class Proof:  # proof.rs:7-11
+    A: G1Point
+    B: G2Point
+    C: G1Point
+
+
+class DeviceCRS:
+    """CRS vectors of crs.rs:17-43 resident on one GPU, with the single points appended (see above)."""
+
+    def __init__(self, g1_alpha, g1_beta, g1_delta, g1_xi, g1_uvw_wit, g1_xt_by_delta, g2_beta, g2_delta, g2_xi,
+                 precompute=True, ctx=None):
+        self.ctx = ctx or default_context()
+        self.n = len(g1_xi)
+        self.n_wit = len(g1_uvw_wit)
+        self.n_xt = len(g1_xt_by_delta)
+        self.g1_delta = g1_delta
+        mk1 = lambda pts: G1Points(pts, precompute=precompute, ctx=self.ctx)
+        self.set_A = mk1(list(g1_xi) + [g1_alpha, g1_delta])
+        self.set_Bg1 = mk1(list(g1_xi) + [g1_beta, g1_delta])
+        self.set_B = G2Points(list(g2_xi) + [g2_beta, g2_delta], precompute=precompute, ctx=self.ctx)
+        self.set_C = mk1(list(g1_uvw_wit) + list(g1_xt_by_delta) + [g1_delta])
+
+    @classmethod
+    def from_arrays(cls, arrs, precompute=True, ctx=None):
+        """arrs: dict of canonical limb arrays (for large synthetic instances built on the device):
+        g1_xi (n,24), g1_uvw_wit, g1_xt_by_delta, g2_xi (n,48), and single points g1_alpha, g1_beta,
+        g1_delta (24,), g2_beta, g2_delta (48,)."""
+        self = cls.__new__(cls)
+        self.ctx = ctx or default_context()
+        self.n, self.n_wit, self.n_xt = len(arrs["g1_xi"]), len(arrs["g1_uvw_wit"]), len(arrs["g1_xt_by_delta"])
+        self.g1_delta = G1Point.from_limbs(arrs["g1_delta"], False)
+        cat = lambda *a: np.concatenate([np.asarray(x, dtype=np.uint32).reshape(-1, np.asarray(a[0]).shape[-1]) for x in a])
+        self.set_A = G1Points.from_arrays(cat(arrs["g1_xi"], arrs["g1_alpha"], arrs["g1_delta"]), precompute=precompute, ctx=self.ctx)
+        self.set_Bg1 = G1Points.from_arrays(cat(arrs["g1_xi"], arrs["g1_beta"], arrs["g1_delta"]), precompute=precompute, ctx=self.ctx)
+        self.set_B = G2Points.from_arrays(cat(arrs["g2_xi"], arrs["g2_beta"], arrs["g2_delta"]), precompute=precompute, ctx=self.ctx)
+        self.set_C = G1Points.from_arrays(cat(arrs["g1_uvw_wit"], arrs["g1_xt_by_delta"], arrs["g1_delta"]), precompute=precompute, ctx=self.ctx)
+        return self
+
+
+def aggregate(polys, wires):
+    """sum_i a_i * poly_i as a coefficient list mod r (Prover's per-wire loop, prover.rs:108-117, made one vector)."""
+    n = max(len(p) for p in polys)
+    out = [0] * n
+    for p, a in zip(polys, wires):
+        a = int(a) % R
+        if a == 0:
+            continue
+        for j, c in enumerate(p):
+            out[j] = (out[j] + a * int(c)) % R
+    return out
+
+
+def _pad(v, n):
+    v = [int(x) % R for x in v]
+    if len(v) > n:
+        if any(v[n:]):
+            raise IndexError("index out of bounds: more coefficients than powers")  # polynomial.rs:278
+        v = v[:n]
+    return v + [0] * (n - len(v))
+
+
+class Prover:
+    """prover.rs:35-46 restricted to what `prove` reads: aggregated u, v coefficient vectors, h, witness wires."""
+
+    def __init__(self, u_agg, v_agg, h, witness_wires):
+        self.u, self.v, self.h, self.wit = u_agg, v_agg, h, witness_wires
+
+    @classmethod
+    def from_per_wire(cls, ui, vi, h, wires, l):
+        """ui, vi: per-wire coefficient lists (prover.ui / prover.vi), wires a_0..a_m, l = last statement wire"""
+        return cls(aggregate(ui, wires), aggregate(vi, wires), list(h), list(wires[l + 1:]))
+
+    def prove(self, crs: DeviceCRS, r: int, s: int) -> Proof:
+        ctx = crs.ctx
+        r, s = int(r) % R, int(s) % R
+        n = crs.n
+        su = scalars_to_array(_pad(self.u, n) + [1, r])
+        sv = scalars_to_array(_pad(self.v, n) + [1, s])
+        A = G1Point.from_limbs(*ctx.msm(crs.set_A.set, su))                       # prover.rs:118
+        B = G2Point.from_limbs(*ctx.msm(crs.set_B.set, sv))                       # :119
+        B_g1 = G1Point.from_limbs(*ctx.msm(crs.set_Bg1.set, sv))                  # :120
+        if len(self.wit) != crs.n_wit:
+            raise IndexError("witness length does not match crs.g1.uvw_wit")
+        sc = scalars_to_array(_pad(self.wit, crs.n_wit) + _pad(self.h, crs.n_xt) + [(-(r * s)) % R])
+        C_main = G1Point.from_limbs(*ctx.msm(crs.set_C.set, sc))                  # :128-133 and -(delta r) s
+        xy, inf = G1Point.pack([A, B_g1])
+        C_blind = G1Point.from_limbs(*ctx.msm_oneshot(1, xy, inf if inf.any() else None, scalars_to_array([s, r])))  # :137-138
+        return Proof(A, B, C_main + C_blind)
