@@ -12,6 +12,8 @@ def rand_scalars(n, seed):
     a[:, 7] &= 0x3FFFFFFF
     return a
 
+GROUP = int(os.environ.get("GROUP", "1"))
+
 def main():
     logns = [int(x) for x in sys.argv[1].split(",")] if len(sys.argv) > 1 else [20]
     cs = [int(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else [0]
@@ -25,21 +27,21 @@ def main():
           for c in cs:
             if True:
                 ctx.set_window(c)
-                pts = ctx.points_from_scalars(1, z.G1Point.g().limbs(), rand_scalars(n, 1), precompute=pre)
+                pts = ctx.points_from_scalars(GROUP, (z.G1Point if GROUP == 1 else z.G2Point).g().limbs(), rand_scalars(n, 1), precompute=pre)
                 d_sc = torch.from_numpy(rand_scalars(n, 2).view(np.int32)).cuda()
                 torch.cuda.synchronize()
                 ctx.profile(False)
                 for _ in range(3):
-                    ctx.msm_enqueue(pts, d_sc.data_ptr(), n); ctx.msm_result(1)
+                    ctx.msm_enqueue(pts, d_sc.data_ptr(), n); ctx.msm_result(GROUP)
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record(stream)
                 for _ in range(5):
                     ctx.msm_enqueue(pts, d_sc.data_ptr(), n)
                 e1.record(stream)
-                ctx.msm_result(1)
+                ctx.msm_result(GROUP)
                 total = e0.elapsed_time(e1) / 5
                 ctx.profile(True)
-                ctx.msm_enqueue(pts, d_sc.data_ptr(), n); ctx.msm_result(1)
+                ctx.msm_enqueue(pts, d_sc.data_ptr(), n); ctx.msm_result(GROUP)
                 rows = ctx.profile_read()
                 agg = collections.OrderedDict()
                 for name, ms, thr in rows:

@@ -48,13 +48,11 @@ def _int(a):
 
 def scalars_to_array(scalars):
     """ints -> (n, 8) uint32.  Field elements are < r; anything >= 2^255 is rejected by the device."""
-    out = np.zeros((len(scalars), 8), dtype=np.uint32)
-    for i, s in enumerate(scalars):
-        s = int(s)
-        if s < 0 or s >> 256:
-            raise ValueError("scalar out of range")
-        out[i] = _limbs(s, 8)
-    return out
+    try:
+        raw = b"".join(int(s).to_bytes(32, "little") for s in scalars)
+    except OverflowError:
+        raise ValueError("scalar out of range")
+    return np.frombuffer(raw, dtype=np.uint32).reshape(-1, 8).copy() if raw else np.zeros((0, 8), dtype=np.uint32)
 
 
 class _Point:

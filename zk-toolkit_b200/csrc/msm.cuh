@@ -156,8 +156,8 @@ struct Scatter {
 
 // ---------------------------------------------------------------- bucket accumulation
 static constexpr uint32_t NO_KEY = 0xffffffffu;
-// partials folded per fix-up thread: 4 on the first (widest) level for parallelism, 16 above it
-inline uint32_t fix_fan(uint32_t level) { return level == 0 ? 4u : 16u; }
+// partials folded per fix-up thread (4-ary tree: short serial chains; upper levels are usually empty)
+inline uint32_t fix_fan(uint32_t level) { (void)level; return 4u; }
 
 template <class C> struct Accumulate {
   typedef typename C::F F;
@@ -427,14 +427,19 @@ template <class C> struct StorePoints {
 // ---------------------------------------------------------------- planning
 inline uint32_t msm_windows(uint32_t c) { return 255 / c + 1; }
 
-// cost model in mixed-add units: n*W accumulate + ~5 add-equivalents per bucket (fix-up, two
-// running-sum adds at 1.4x a mixed add each), used only to pick c
+// Window choice.  Cost model in mixed-add units, calibrated on B200 at n = 2^20 (profiles/): expected
+// sorted pairs (a full window contributes n, a top window of tb bits n (1 - 2^-tb), a carry-only top
+// window n / 2) plus a per-bucket charge for fix-up + reduction (6 with one shared bucket set, 11 per
+// window otherwise), plus a penalty when a narrow top window funnels its pairs into a few giant buckets.
 inline uint32_t msm_pick_c(uint32_t n, bool precomp) {
   uint32_t best = 8;
   double best_cost = 1e300;
   for (uint32_t c = 3; c <= 22; c++) {
-    double W = msm_windows(c), B = (double)(1u << (c - 1));
-    double cost = W * n + 5.0 * B * (precomp ? 1.0 : W);
+    uint32_t full = 255 / c, tb = 255 - full * c;
+    double W = full + 1, B = (double)(1u << (c - 1));
+    double entries = (double)n * (full + (tb == 0 ? 0.5 : 1.0 - 1.0 / (double)(1u << (tb > 30 ? 30 : tb))));
+    double cost = entries + (precomp ? 6.0 * B : 11.0 * B * W);
+    if (tb > 0 && 2 * tb < c) cost += (double)n;
     if (cost < best_cost) { best_cost = cost; best = c; }
   }
   return best;

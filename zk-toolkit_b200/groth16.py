@@ -90,6 +90,13 @@ class Prover:
 
     def __init__(self, u_agg, v_agg, h, witness_wires):
         self.u, self.v, self.h, self.wit = u_agg, v_agg, h, witness_wires
+        self._limbs = {}   # scalar vectors marshalled once to the ABI layout (padding depends on the CRS)
+
+    def _arr(self, name, vec, n):
+        key = (name, n)
+        if key not in self._limbs:
+            self._limbs[key] = scalars_to_array(_pad(vec, n))
+        return self._limbs[key]
 
     @classmethod
     def from_per_wire(cls, ui, vi, h, wires, l):
@@ -100,14 +107,15 @@ class Prover:
         ctx = crs.ctx
         r, s = int(r) % R, int(s) % R
         n = crs.n
-        su = scalars_to_array(_pad(self.u, n) + [1, r])
-        sv = scalars_to_array(_pad(self.v, n) + [1, s])
+        su = np.concatenate([self._arr("u", self.u, n), scalars_to_array([1, r])])
+        sv = np.concatenate([self._arr("v", self.v, n), scalars_to_array([1, s])])
         A = G1Point.from_limbs(*ctx.msm(crs.set_A.set, su))                       # prover.rs:118
         B = G2Point.from_limbs(*ctx.msm(crs.set_B.set, sv))                       # :119
         B_g1 = G1Point.from_limbs(*ctx.msm(crs.set_Bg1.set, sv))                  # :120
         if len(self.wit) != crs.n_wit:
             raise IndexError("witness length does not match crs.g1.uvw_wit")
-        sc = scalars_to_array(_pad(self.wit, crs.n_wit) + _pad(self.h, crs.n_xt) + [(-(r * s)) % R])
+        sc = np.concatenate([self._arr("wit", self.wit, crs.n_wit), self._arr("h", self.h, crs.n_xt),
+                             scalars_to_array([(-(r * s)) % R])])
         C_main = G1Point.from_limbs(*ctx.msm(crs.set_C.set, sc))                  # :128-133 and -(delta r) s
         xy, inf = G1Point.pack([A, B_g1])
         C_blind = G1Point.from_limbs(*ctx.msm_oneshot(1, xy, inf if inf.any() else None, scalars_to_array([s, r])))  # :137-138
