@@ -165,7 +165,8 @@ def main():
             dlog_arr[i] = 0
             dlog_arr[i, 0] = 1
     sc_arr, scalars = synth_scalars(n_total, args.seed + 2, lo, hi)
-    pts = ctx.points_from_scalars(1, z.G1Point.g().limbs(), dlog_arr, precompute=not args.no_precompute)
+    pts = ctx.points_from_scalars(1, z.G1Point.g().limbs(), dlog_arr, precompute=not args.no_precompute,
+                                  in_subgroup=True)   # multiples of g have order r; scalars are < r
     expected_k = sum(k * s for k, s in zip(dlogs, scalars)) % R     # this rank's share of sum s_i k_i
     log(f"[rank {rank}] shard [{lo},{hi}) set up in {time.time() - t_setup:.1f}s")
 

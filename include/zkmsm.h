@@ -39,13 +39,17 @@ extern "C" {
 #define ZKMSM_OK 0
 #define ZKMSM_ERR_INVALID_ARG (-1)
 #define ZKMSM_ERR_CUDA (-2)
-#define ZKMSM_ERR_SCALAR_RANGE (-3)   /* a scalar had bit 255 set */
+#define ZKMSM_ERR_SCALAR_RANGE (-3)   /* a scalar had bit 255 set, or was >= r for a ZKMSM_SUBGROUP set */
 #define ZKMSM_ERR_NO_DEVICE (-4)
 #define ZKMSM_ERR_TOO_FEW_POINTS (-5) /* n > points loaded; the reference panics, polynomial.rs:278 */
 #define ZKMSM_ERR_NOMEM (-6)
 
 /* zkmsm_*_load_points flags */
 #define ZKMSM_PRECOMPUTE 1u /* also store 2^(c w) P for every window w (CRS-style static sets) */
+#define ZKMSM_SUBGROUP 2u   /* caller asserts every point has order r (true for any CRS vector: multiples of the
+                             * generator).  Scalars must then be < r; s > (r-1)/2 is evaluated as (r-s)(-P), which
+                             * saves the carry window.  Without the flag scalars are raw integers < 2^255 and nothing
+                             * is assumed about the points (curves/macros.rs:10-21). */
 
 typedef struct zkmsm_ctx zkmsm_ctx;       /* one CUDA device + stream + workspace */
 typedef struct zkmsm_points zkmsm_points; /* device-resident point set (G1 or G2) */

@@ -32,13 +32,15 @@ static int emu_msm(const uint32_t* xy, const uint8_t* inf, const uint32_t* scala
                    uint32_t* out_xyzz) {
   typedef typename C::F F;
   HostExec ex;
-  if (c == 0) c = msm_pick_c(precomp ? npts : n, precomp != 0);
-  uint32_t W = msm_windows(c);
+  bool half = (precomp & 2) != 0;
+  precomp &= 1;
+  if (c == 0) c = msm_pick_c(precomp ? npts : n, precomp != 0, half);
+  uint32_t W = msm_windows(c, half);
   std::vector<Affine<F>> pts((size_t)npts * (precomp ? W : 1) + 1);
   ex.launch<LoadPoints<C>>(npts, npts, xy, inf, pts.data());
   if (precomp) ex.launch<PrecomputeSlabs<C>>(npts, npts, npts, c, W, pts.data());
   if (n == 0) { *out_inf = 1; memset(out_xy, 0, 4 * C::AFF_LIMBS); return 0; }
-  MsmPlan p = msm_plan(n, c, precomp != 0, npts);
+  MsmPlan p = msm_plan(n, c, precomp != 0, npts, half);
   if (L) { p.L = L; p.acc_threads = (p.max_entries + L - 1) / L; }
   if (K) p.K = K;
   std::vector<uint32_t> hist(p.nb), offsets(p.nb + 1), segsum((p.nb + SCAN_SEG - 1) / SCAN_SEG + 1), err(1);

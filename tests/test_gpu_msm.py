@@ -136,6 +136,13 @@ def test_msm_edge_cases(z, ctx, small_g1):
     with pytest.raises(z.ZkmsmError) as e:                                     # bit 255 set: rejected
         run([1 << 255, 1], z.G1Points(P[:2]))
     assert e.value.code == -3
+    half = (O.R - 1) // 2                                                      # subgroup sets: s -> r - s, P -> -P
+    s = [half, half + 1, O.R - 1, 1, 0, half - 1, O.R - 2, 2, 3, 4, 5, 6]
+    for pre_ in (False, True):
+        assert run(s, z.G1Points(P, precompute=pre_, in_subgroup=True)) == exp(s)
+    with pytest.raises(z.ZkmsmError) as e:                                     # ... and s >= r is rejected there
+        run([O.R, 1], z.G1Points(P[:2], in_subgroup=True))
+    assert e.value.code == -3
     with pytest.raises(z.ZkmsmError) as e:                                     # more scalars than points
         ctx.msm(z.G1Points(P[:2]).set, z.scalars_to_array([1, 2, 3]))
     assert e.value.code == -5

@@ -65,7 +65,9 @@ def test_emu_g1_small_vs_oracle_msm(lib, g1_set):
         assert got == O.msm(pts[:n], sc)          # the reference's serial loop
 
 
-@pytest.mark.parametrize("c,precomp,L,K", [(0, 0, 0, 0), (4, 0, 3, 2), (7, 0, 5, 8), (5, 1, 4, 4), (8, 1, 0, 0), (13, 0, 0, 0)])
+# precomp: bit 0 = precomputed slabs, bit 1 = subgroup point set (scalars folded to (r-1)/2)
+@pytest.mark.parametrize("c,precomp,L,K", [(0, 0, 0, 0), (4, 0, 3, 2), (7, 0, 5, 8), (5, 1, 4, 4), (8, 1, 0, 0), (13, 0, 0, 0),
+                                           (0, 2, 0, 0), (6, 3, 3, 2), (9, 3, 0, 0), (5, 2, 2, 4)])
 def test_emu_g1_window_variants(lib, g1_set, c, precomp, L, K):
     dlogs, pts = g1_set
     rnd = random.Random(c * 10 + precomp)
@@ -112,6 +114,13 @@ def test_emu_g1_edge_cases(lib, g1_set):
     assert emu_g1(lib, P[:2], sc) == (0, O.msm(P[:2], sc))
     # r * P = AtInfinity
     assert emu_g1(lib, P[:1], [O.R]) == (0, O.INF)
+    # subgroup point sets: scalars around (r-1)/2 and r-1 are folded to r - s with the point negated
+    half = (O.R - 1) // 2
+    sc = [half, half + 1, O.R - 1, 1, 0, half - 1, O.R - 2, 2, 3, 4, 5, 6]
+    for mode, cc in ((2, 0), (3, 6), (2, 5)):
+        assert emu_g1(lib, P, sc, precomp=mode, c=cc) == (0, exp(sc))
+    rc, _ = emu_g1(lib, P[:2], [O.R, 1], precomp=2)          # s >= r is rejected for such sets
+    assert rc == -3
 
 
 def test_emu_g1_sharded_partials_match_single(lib, g1_set):

@@ -14,6 +14,7 @@ ERR_NAMES = {
     -4: "ZKMSM_ERR_NO_DEVICE", -5: "ZKMSM_ERR_TOO_FEW_POINTS", -6: "ZKMSM_ERR_NOMEM",
 }
 PRECOMPUTE = 1
+SUBGROUP = 2
 G1_WORDS, G2_WORDS = 24, 48
 G1_PARTIAL_WORDS, G2_PARTIAL_WORDS = 48, 96
 

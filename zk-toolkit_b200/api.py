@@ -183,25 +183,31 @@ class _Points:
     """Device-resident slice of points (a CRS vector)."""
     POINT = None
 
-    def __init__(self, points=None, precompute=False, ctx=None, _set=None):
+    def __init__(self, points=None, precompute=False, ctx=None, _set=None, in_subgroup=False):
+        """in_subgroup=True asserts that every point has order r (any CRS vector does: its points are multiples
+        of the generator); scalars must then be field elements (< r) and the device may evaluate s P as
+        (r - s)(-P).  Leave it False for arbitrary curve points / raw integer scalars (macros.rs:10-21)."""
         self.ctx = ctx or default_context()
         if _set is not None:
             self.set = _set
         else:
             xy, inf = self.POINT.pack(points)
-            self.set = self.ctx.load_points(self.POINT.GROUP, xy, inf if inf.any() else None, precompute=precompute)
+            self.set = self.ctx.load_points(self.POINT.GROUP, xy, inf if inf.any() else None, precompute=precompute,
+                                            in_subgroup=in_subgroup)
 
     @classmethod
-    def from_arrays(cls, xy, inf=None, precompute=False, ctx=None):
+    def from_arrays(cls, xy, inf=None, precompute=False, ctx=None, in_subgroup=False):
         ctx = ctx or default_context()
-        return cls(ctx=ctx, _set=ctx.load_points(cls.POINT.GROUP, xy, inf, precompute=precompute))
+        return cls(ctx=ctx, _set=ctx.load_points(cls.POINT.GROUP, xy, inf, precompute=precompute, in_subgroup=in_subgroup))
 
     @classmethod
-    def generator_multiples(cls, scalars, precompute=False, ctx=None):
-        """[k * g for k in scalars] computed on the device (CRS::new's calc_n_pows, crs.rs:88-104)."""
+    def generator_multiples(cls, scalars, precompute=False, ctx=None, in_subgroup=True):
+        """[k * g for k in scalars] computed on the device (CRS::new's calc_n_pows, crs.rs:88-104).
+        Multiples of the generator have order r, so in_subgroup defaults to True here."""
         ctx = ctx or default_context()
         sc = scalars if isinstance(scalars, np.ndarray) else scalars_to_array(scalars)
-        return cls(ctx=ctx, _set=ctx.points_from_scalars(cls.POINT.GROUP, cls.POINT.g().limbs(), sc, precompute=precompute))
+        return cls(ctx=ctx, _set=ctx.points_from_scalars(cls.POINT.GROUP, cls.POINT.g().limbs(), sc, precompute=precompute,
+                                                         in_subgroup=in_subgroup))
 
     def __len__(self):
         return len(self.set)

@@ -73,7 +73,11 @@ class Context:
     def _words(self, group):
         return L.G1_WORDS if group == 1 else L.G2_WORDS
 
-    def load_points(self, group, xy, inf=None, precompute=False):
+    @staticmethod
+    def _flags(precompute, in_subgroup):
+        return (L.PRECOMPUTE if precompute else 0) | (L.SUBGROUP if in_subgroup else 0)
+
+    def load_points(self, group, xy, inf=None, precompute=False, in_subgroup=False):
         xy = L.as_u32(xy, self._words(group)).reshape(-1, self._words(group))
         n = xy.shape[0]
         if inf is not None:
@@ -81,15 +85,15 @@ class Context:
             assert inf.shape == (n,)
         fn = self.lib.zkmsm_g1_load_points if group == 1 else self.lib.zkmsm_g2_load_points
         h = ctypes.c_void_p()
-        self._check(fn(self.h, L.dptr(xy), L.dptr(inf), n, L.PRECOMPUTE if precompute else 0, ctypes.byref(h)))
+        self._check(fn(self.h, L.dptr(xy), L.dptr(inf), n, self._flags(precompute, in_subgroup), ctypes.byref(h)))
         return PointSet(self, h, group, n, precompute)
 
-    def points_from_scalars(self, group, base_xy, scalars, precompute=False):
+    def points_from_scalars(self, group, base_xy, scalars, precompute=False, in_subgroup=False):
         base = L.as_u32(base_xy, self._words(group)).reshape(-1)
         sc = L.as_u32(scalars, 8).reshape(-1, 8)
         fn = self.lib.zkmsm_g1_points_from_scalars if group == 1 else self.lib.zkmsm_g2_points_from_scalars
         h = ctypes.c_void_p()
-        self._check(fn(self.h, L.dptr(base), L.dptr(sc), sc.shape[0], L.PRECOMPUTE if precompute else 0, ctypes.byref(h)))
+        self._check(fn(self.h, L.dptr(base), L.dptr(sc), sc.shape[0], self._flags(precompute, in_subgroup), ctypes.byref(h)))
         return PointSet(self, h, group, sc.shape[0], precompute)
 
     def mul_base(self, group, base_xy, scalars):

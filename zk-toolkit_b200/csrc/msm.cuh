@@ -43,7 +43,7 @@ struct G1 { typedef Fp F; static constexpr int AFF_LIMBS = 24; };
 struct G2 { typedef Fp2 F; static constexpr int AFF_LIMBS = 48; };
 
 static constexpr int SCALAR_LIMBS = 8;
-static constexpr uint32_t ERR_SCALAR_RANGE = 1u;  // a scalar had bit 255 set
+static constexpr uint32_t ERR_SCALAR_RANGE = 1u;  // a scalar had bit 255 set (or was >= r for a subgroup point set)
 
 struct MsmPlan {
   uint32_t n;          // terms
@@ -58,6 +58,8 @@ struct MsmPlan {
   uint32_t K;          // buckets per reduce thread (power of two, divides B)
   uint32_t max_entries;   // n * W
   uint32_t acc_threads;   // ceil(max_entries / L)
+  uint32_t half;          // 1: point set is in the prime-order subgroup; scalars s > (r-1)/2 become r - s with
+                          //    the point negated, so 254 bits are recoded and no carry-only top window exists
 };
 
 // ---------------------------------------------------------------- signed-digit recoding
@@ -80,14 +82,42 @@ struct Digits {
   }
 };
 
+// Loads scalar `tid`.  Returns false (scalar rejected) when it is out of range.  With p.half the scalar must
+// be < r; if it exceeds (r-1)/2 it is replaced by r - s and *negate is set: (r - s)(-P) = sP because the
+// points of such a set have order r.
+ZK_HD bool load_scalar(const MsmPlan& p, const uint32_t* scalars, uint32_t tid, uint32_t* s, bool* negate) {
+#pragma unroll
+  for (int i = 0; i < SCALAR_LIMBS; i++) s[i] = scalars[(size_t)tid * SCALAR_LIMBS + i];
+  *negate = false;
+  if (!p.half) return (s[SCALAR_LIMBS - 1] >> 31) == 0;
+  uint32_t d[SCALAR_LIMBS];
+  d[0] = ptx::sub_cc(FR_P[0], s[0]);                      // d = r - s
+#pragma unroll
+  for (int i = 1; i < SCALAR_LIMBS; i++) d[i] = ptx::subc_cc(FR_P[i], s[i]);
+  uint32_t borrow = ptx::subc(0, 0);
+  bool is_zero = true;
+#pragma unroll
+  for (int i = 0; i < SCALAR_LIMBS; i++) is_zero = is_zero && d[i] == 0;
+  if (borrow || is_zero) return false;                    // s >= r
+  uint32_t t = ptx::sub_cc(FR_HALF[0], s[0]);             // (r-1)/2 - s < 0  <=>  s in the upper half
+#pragma unroll
+  for (int i = 1; i < SCALAR_LIMBS; i++) t = ptx::subc_cc(FR_HALF[i], s[i]);
+  (void)t;
+  if (ptx::subc(0, 0)) {
+    *negate = true;
+#pragma unroll
+    for (int i = 0; i < SCALAR_LIMBS; i++) s[i] = d[i];
+  }
+  return true;
+}
+
 struct RecodeCount {
   static const char* name() { return "recode_count"; }
   static ZK_HD void run(uint32_t tid, MsmPlan p, const uint32_t* scalars, uint32_t* hist, uint32_t* err) {
     if (tid >= p.n) return;
     uint32_t s[SCALAR_LIMBS];
-#pragma unroll
-    for (int i = 0; i < SCALAR_LIMBS; i++) s[i] = scalars[(size_t)tid * SCALAR_LIMBS + i];
-    if (s[SCALAR_LIMBS - 1] >> 31) { zk_atomic_or(err, ERR_SCALAR_RANGE); return; }
+    bool negate;
+    if (!load_scalar(p, scalars, tid, s, &negate)) { zk_atomic_or(err, ERR_SCALAR_RANGE); return; }
     Digits dg(s, p.c);
     for (uint32_t w = 0; w < p.W; w++) {
       int32_t d = dg.next(w);
@@ -137,14 +167,14 @@ struct Scatter {
   static ZK_HD void run(uint32_t tid, MsmPlan p, const uint32_t* scalars, uint32_t* cursor, Entry* entries) {
     if (tid >= p.n) return;
     uint32_t s[SCALAR_LIMBS];
-#pragma unroll
-    for (int i = 0; i < SCALAR_LIMBS; i++) s[i] = scalars[(size_t)tid * SCALAR_LIMBS + i];
-    if (s[SCALAR_LIMBS - 1] >> 31) return;
+    bool negate;
+    if (!load_scalar(p, scalars, tid, s, &negate)) return;
     Digits dg(s, p.c);
     for (uint32_t w = 0; w < p.W; w++) {
       int32_t d = dg.next(w);
       if (d == 0) continue;
       uint32_t neg = d < 0, mag = (uint32_t)(neg ? -d : d) - 1;
+      neg ^= negate ? 1u : 0u;
       uint32_t key = (p.precomp ? 0 : w * p.B) + mag;
       uint32_t idx = p.precomp ? w * p.stride + tid : tid;
       uint32_t pos = zk_atomic_add(&cursor[key], 1u);
@@ -425,31 +455,33 @@ template <class C> struct StorePoints {
 };
 
 // ---------------------------------------------------------------- planning
-inline uint32_t msm_windows(uint32_t c) { return 255 / c + 1; }
+// windows needed for 255-bit scalars (254-bit after the half-range fold): the last one absorbs the recoding carry
+inline uint32_t msm_windows(uint32_t c, bool half = false) { return (half ? 254u : 255u) / c + 1; }
 
 // Window choice.  Cost model in mixed-add units, calibrated on B200 at n = 2^20 (profiles/): expected
 // sorted pairs (a full window contributes n, a top window of tb bits n (1 - 2^-tb), a carry-only top
 // window n / 2) plus a per-bucket charge for fix-up + reduction (6 with one shared bucket set, 11 per
 // window otherwise), plus a penalty when a narrow top window funnels its pairs into a few giant buckets.
-inline uint32_t msm_pick_c(uint32_t n, bool precomp) {
+inline uint32_t msm_pick_c(uint32_t n, bool precomp, bool half = false) {
   uint32_t best = 8;
   double best_cost = 1e300;
   for (uint32_t c = 3; c <= 22; c++) {
-    uint32_t full = 255 / c, tb = 255 - full * c;
+    uint32_t bits = half ? 254u : 255u, full = bits / c, tb = bits - full * c;
     double W = full + 1, B = (double)(1u << (c - 1));
     double entries = (double)n * (full + (tb == 0 ? 0.5 : 1.0 - 1.0 / (double)(1u << (tb > 30 ? 30 : tb))));
     double cost = entries + (precomp ? 6.0 * B : 11.0 * B * W);
-    if (tb > 0 && 2 * tb < c) cost += (double)n;
+    if (2 * tb < c) cost += 0.5 * (double)n;   // carry-only or narrow top window: a few giant buckets
     if (cost < best_cost) { best_cost = cost; best = c; }
   }
   return best;
 }
 
-inline MsmPlan msm_plan(uint32_t n, uint32_t c, bool precomp, uint32_t stride) {
+inline MsmPlan msm_plan(uint32_t n, uint32_t c, bool precomp, uint32_t stride, bool half = false) {
   MsmPlan p;
   p.n = n;
   p.c = c;
-  p.W = msm_windows(c);
+  p.half = half ? 1 : 0;
+  p.W = msm_windows(c, half);
   p.B = 1u << (c - 1);
   p.precomp = precomp ? 1 : 0;
   p.nwin = precomp ? 1 : p.W;
@@ -457,7 +489,9 @@ inline MsmPlan msm_plan(uint32_t n, uint32_t c, bool precomp, uint32_t stride) {
   p.stride = stride;
   p.max_entries = n * p.W;
   p.L = p.max_entries >= (1u << 23) ? 32 : (p.max_entries >= (1u << 21) ? 16 : 8);
-  p.K = p.B >= 8 ? 8 : p.B;
+  p.K = 2;                                   // ~16k reduce threads: short chains while the chip stays busy
+  while (p.K < 64 && p.B / p.K > 16384) p.K *= 2;
+  if (p.K > p.B) p.K = p.B;
   if (const char* e = getenv("ZKMSM_L")) { uint32_t v = (uint32_t)atoi(e); if (v >= 1 && v <= 4096) p.L = v; }   // tuning overrides
   if (const char* e = getenv("ZKMSM_K")) { uint32_t v = (uint32_t)atoi(e); if (v >= 1 && v <= p.B && (v & (v - 1)) == 0) p.K = v; }
   p.acc_threads = (p.max_entries + p.L - 1) / p.L;

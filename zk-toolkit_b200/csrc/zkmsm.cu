@@ -47,6 +47,7 @@ struct zkmsm_points {
   size_t n;             // points per slab
   unsigned c, W;        // window layout of the slabs (precomputed sets)
   bool precomp;
+  bool half;            // ZKMSM_SUBGROUP: points have order r, scalars are folded to (r-1)/2
   void* d_pts;          // Affine<F>[W * n] (precomp) or Affine<F>[n]
 };
 
@@ -208,8 +209,9 @@ static int alloc_point_set(zkmsm_ctx* ctx, size_t n, unsigned flags, int curve, 
   ps->device = ctx->device;
   ps->n = n;
   ps->precomp = (flags & ZKMSM_PRECOMPUTE) != 0 && n > 0;
-  ps->c = ps->precomp ? (ctx->window_override ? ctx->window_override : msm_pick_c((uint32_t)n, true)) : 0;
-  ps->W = ps->precomp ? msm_windows(ps->c) : 1;
+  ps->half = (flags & ZKMSM_SUBGROUP) != 0;
+  ps->c = ps->precomp ? (ctx->window_override ? ctx->window_override : msm_pick_c((uint32_t)n, true, ps->half)) : 0;
+  ps->W = ps->precomp ? msm_windows(ps->c, ps->half) : 1;
   size_t slabs = ps->precomp ? ps->W : 1;
   if ((uint64_t)slabs * n >= (1ull << 31)) { delete ps; return fail(ctx, ZKMSM_ERR_INVALID_ARG, "point set too large"); }
   size_t bytes = sizeof(Affine<F>) * slabs * (n ? n : 1);
@@ -307,8 +309,8 @@ static int msm_enqueue_impl(zkmsm_ctx* ctx, const zkmsm_points* ps, const uint32
     if (d_partial_out) CU(ctx, cudaMemsetAsync(d_partial_out, 0, sizeof(XYZZ<F>), ctx->stream));
     return ZKMSM_OK;
   }
-  unsigned c = ps->precomp ? ps->c : (ctx->window_override ? ctx->window_override : msm_pick_c((uint32_t)n, false));
-  MsmPlan p = msm_plan((uint32_t)n, c, ps->precomp, (uint32_t)ps->n);
+  unsigned c = ps->precomp ? ps->c : (ctx->window_override ? ctx->window_override : msm_pick_c((uint32_t)n, false, ps->half));
+  MsmPlan p = msm_plan((uint32_t)n, c, ps->precomp, (uint32_t)ps->n, ps->half);
   int rc;
   uint32_t nseg = (p.nb + SCAN_SEG - 1) / SCAN_SEG + 1;
   if ((rc = ws_reserve(ctx, WS_HIST, sizeof(uint32_t) * p.nb)) || (rc = ws_reserve(ctx, WS_OFFSETS, sizeof(uint32_t) * (p.nb + 1))) ||
@@ -352,7 +354,7 @@ static int msm_collect(zkmsm_ctx* ctx) {
   CU(ctx, cudaMemcpyAsync(ctx->h_res, ctx->d_res, sizeof(ResultBlock), cudaMemcpyDeviceToHost, ctx->stream));
   CU(ctx, cudaStreamSynchronize(ctx->stream));
   ctx->pending = 0;
-  if (ctx->h_res->err & ERR_SCALAR_RANGE) return fail(ctx, ZKMSM_ERR_SCALAR_RANGE, "a scalar has bit 255 set");
+  if (ctx->h_res->err & ERR_SCALAR_RANGE) return fail(ctx, ZKMSM_ERR_SCALAR_RANGE, "a scalar is out of range (bit 255 set, or >= r for a ZKMSM_SUBGROUP point set)");
   return ZKMSM_OK;
 }
 

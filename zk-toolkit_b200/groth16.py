@@ -40,10 +40,10 @@ class DeviceCRS:
         self.n_wit = len(g1_uvw_wit)
         self.n_xt = len(g1_xt_by_delta)
         self.g1_delta = g1_delta
-        mk1 = lambda pts: G1Points(pts, precompute=precompute, ctx=self.ctx)
+        mk1 = lambda pts: G1Points(pts, precompute=precompute, ctx=self.ctx, in_subgroup=True)  # CRS points have order r
         self.set_A = mk1(list(g1_xi) + [g1_alpha, g1_delta])
         self.set_Bg1 = mk1(list(g1_xi) + [g1_beta, g1_delta])
-        self.set_B = G2Points(list(g2_xi) + [g2_beta, g2_delta], precompute=precompute, ctx=self.ctx)
+        self.set_B = G2Points(list(g2_xi) + [g2_beta, g2_delta], precompute=precompute, ctx=self.ctx, in_subgroup=True)
         self.set_C = mk1(list(g1_uvw_wit) + list(g1_xt_by_delta) + [g1_delta])
 
     @classmethod
@@ -56,10 +56,10 @@ class DeviceCRS:
         self.n, self.n_wit, self.n_xt = len(arrs["g1_xi"]), len(arrs["g1_uvw_wit"]), len(arrs["g1_xt_by_delta"])
         self.g1_delta = G1Point.from_limbs(arrs["g1_delta"], False)
         cat = lambda *a: np.concatenate([np.asarray(x, dtype=np.uint32).reshape(-1, np.asarray(a[0]).shape[-1]) for x in a])
-        self.set_A = G1Points.from_arrays(cat(arrs["g1_xi"], arrs["g1_alpha"], arrs["g1_delta"]), precompute=precompute, ctx=self.ctx)
-        self.set_Bg1 = G1Points.from_arrays(cat(arrs["g1_xi"], arrs["g1_beta"], arrs["g1_delta"]), precompute=precompute, ctx=self.ctx)
-        self.set_B = G2Points.from_arrays(cat(arrs["g2_xi"], arrs["g2_beta"], arrs["g2_delta"]), precompute=precompute, ctx=self.ctx)
-        self.set_C = G1Points.from_arrays(cat(arrs["g1_uvw_wit"], arrs["g1_xt_by_delta"], arrs["g1_delta"]), precompute=precompute, ctx=self.ctx)
+        self.set_A = G1Points.from_arrays(cat(arrs["g1_xi"], arrs["g1_alpha"], arrs["g1_delta"]), precompute=precompute, ctx=self.ctx, in_subgroup=True)
+        self.set_Bg1 = G1Points.from_arrays(cat(arrs["g1_xi"], arrs["g1_beta"], arrs["g1_delta"]), precompute=precompute, ctx=self.ctx, in_subgroup=True)
+        self.set_B = G2Points.from_arrays(cat(arrs["g2_xi"], arrs["g2_beta"], arrs["g2_delta"]), precompute=precompute, ctx=self.ctx, in_subgroup=True)
+        self.set_C = G1Points.from_arrays(cat(arrs["g1_uvw_wit"], arrs["g1_xt_by_delta"], arrs["g1_delta"]), precompute=precompute, ctx=self.ctx, in_subgroup=True)
         return self
 
 
