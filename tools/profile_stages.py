@@ -27,7 +27,7 @@ def main():
           for c in cs:
             if True:
                 ctx.set_window(c)
-                pts = ctx.points_from_scalars(GROUP, (z.G1Point if GROUP == 1 else z.G2Point).g().limbs(), rand_scalars(n, 1), precompute=pre)
+                pts = ctx.points_from_scalars(GROUP, (z.G1Point if GROUP == 1 else z.G2Point).g().limbs(), rand_scalars(n, 1), precompute=pre, in_subgroup=os.environ.get("HALF", "1") == "1")
                 d_sc = torch.from_numpy(rand_scalars(n, 2).view(np.int32)).cuda()
                 torch.cuda.synchronize()
                 ctx.profile(False)
@@ -48,7 +48,7 @@ def main():
                     a = agg.setdefault(name, [0.0, 0, 0])
                     a[0] += ms; a[1] += 1; a[2] = max(a[2], thr)
                 ssum = sum(v[0] for v in agg.values())
-                print(f"== n=2^{logn} precomp={pre} c={c} L={os.environ.get('ZKMSM_L','-')} K={os.environ.get('ZKMSM_K','-')}: {total:.3f} ms/MSM ({n/total/1e3:.1f} Mpts/s), sum of kernels {ssum:.3f} ms, {len(rows)} launches")
+                print(f"== n=2^{logn} precomp={pre} half={os.environ.get('HALF', '1')} c={c} L={os.environ.get('ZKMSM_L','-')} K={os.environ.get('ZKMSM_K','-')}: {total:.3f} ms/MSM ({n/total/1e3:.1f} Mpts/s), sum of kernels {ssum:.3f} ms, {len(rows)} launches")
                 for name, (ms, cnt, thr) in agg.items():
                     print(f"   {name:18s} {ms:8.3f} ms  {100*ms/ssum:5.1f}%  x{cnt}  max_threads={thr}")
                 sys.stdout.flush()

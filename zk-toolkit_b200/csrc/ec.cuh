@@ -122,6 +122,46 @@ template <class F> ZK_HD void xyzz_add(XYZZ<F>& acc, const XYZZ<F>& q) {
   fmul(t, acc.zzz, q.zzz);  fmul(acc.zzz, t, ppp);
 }
 
+// ---- latency-oriented variants (independent field products issued as lockstep pairs, fmul2).  Used by the
+// kernels after the accumulation, which run a handful of warps and are bound by the length of one
+// thread's dependency chain, not by multiplier throughput.  Same formulas, same results.
+template <class F> ZK_HD void xyzz_dbl_ilp(XYZZ<F>& p) {
+  if (is_inf(p)) return;
+  F u, v, w, s, m, t, t2;
+  fdbl(u, p.y);
+  fmul2(v, u, u, t, p.x, p.x);            // V = U^2 | X^2
+  fdbl(m, t); fadd(m, m, t);              // M = 3 X^2
+  fmul2(w, u, v, s, p.x, v);              // W = U V | S = X V
+  fsqr(t, m);
+  fsub(t, t, s); fsub(p.x, t, s);         // X3 = M^2 - 2S
+  fsub(t, s, p.x);
+  fmul2(t, m, t, u, w, p.y);              // M (S - X3) | W Y
+  fsub(p.y, t, u);
+  fmul2(p.zz, v, p.zz, p.zzz, w, p.zzz);
+  (void)t2;
+}
+
+template <class F> ZK_HD void xyzz_add_ilp(XYZZ<F>& acc, const XYZZ<F>& q) {
+  if (is_inf(q)) return;
+  if (is_inf(acc)) { acc = q; return; }
+  F u1, s1, p, r, t, t2, pp, ppp, qq;
+  fmul2(u1, acc.x, q.zz, t, q.x, acc.zz);      fsub(p, t, u1);     // P = U2 - U1
+  fmul2(s1, acc.y, q.zzz, t, q.y, acc.zzz);    fsub(r, t, s1);     // R = S2 - S1
+  if (fis_zero(p)) {
+    if (fis_zero(r)) xyzz_dbl_ilp(acc);
+    else set_inf(acc);
+    return;
+  }
+  fmul2(pp, p, p, t, r, r);                    // PP | R^2
+  fmul2(ppp, p, pp, qq, u1, pp);               // PPP | Q
+  fsub(t, t, ppp); fsub(t, t, qq); fsub(acc.x, t, qq);
+  fsub(t, qq, acc.x);
+  fmul2(t, r, t, qq, s1, ppp);                 // R (Q - X3) | S1 PPP
+  fsub(acc.y, t, qq);
+  fmul2(t, acc.zz, q.zz, t2, acc.zzz, q.zzz);
+  fmul2(acc.zz, t, pp, acc.zzz, t2, ppp);
+}
+
 // canonical affine form; one inversion: t = 1/ZZZ, 1/ZZ = (ZZ t)^2
 template <class F> ZK_HD void xyzz_to_affine(Affine<F>& r, const XYZZ<F>& p) {
   if (is_inf(p)) { set_inf(r); return; }

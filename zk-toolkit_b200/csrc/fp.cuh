@@ -221,6 +221,33 @@ template <class C> ZK_FMUL_ATTR void fmul(Mont<C>& r, const Mont<C>& a, const Mo
 
 template <class C> ZK_HD void fsqr(Mont<C>& r, const Mont<C>& a) { fmul(r, a, a); }
 
+// Two independent products advanced in lockstep (row by row), for the latency-bound kernels that run
+// one warp per scheduler: the two carry chains overlap, so a pair costs little more than one product
+// in wall time.  Always inlined.  r1/r2 may alias the inputs.
+template <class C> ZK_HD void fmul2(Mont<C>& r1, const Mont<C>& a1, const Mont<C>& b1,
+                                    Mont<C>& r2, const Mont<C>& a2, const Mont<C>& b2) {
+  constexpr int n = C::N;
+  uint32_t e1[n], o1[n], e2[n], o2[n];
+#pragma unroll
+  for (int i = 0; i < n; i += 2) {
+    detail::mont_step<C>(e1, o1, a1.v, b1.v[i], i == 0);
+    detail::mont_step<C>(e2, o2, a2.v, b2.v[i], i == 0);
+    detail::mont_step<C>(o1, e1, a1.v, b1.v[i + 1], false);
+    detail::mont_step<C>(o2, e2, a2.v, b2.v[i + 1], false);
+  }
+  uint32_t t1[n], t2[n];
+  t1[0] = ptx::add_cc(e1[0], o1[1]);
+#pragma unroll
+  for (int i = 1; i < n - 1; i++) t1[i] = ptx::addc_cc(e1[i], o1[i + 1]);
+  t1[n - 1] = ptx::addc(e1[n - 1], 0);
+  t2[0] = ptx::add_cc(e2[0], o2[1]);
+#pragma unroll
+  for (int i = 1; i < n - 1; i++) t2[i] = ptx::addc_cc(e2[i], o2[i + 1]);
+  t2[n - 1] = ptx::addc(e2[n - 1], 0);
+  freduce_once(r1, t1);
+  freduce_once(r2, t2);
+}
+
 // ---------------------------------------------------------------- conversions, inverse
 // canonical limbs (< p) -> Montgomery form
 template <class C> ZK_HD void fto_mont(Mont<C>& r, const uint32_t* canon) {

@@ -33,6 +33,15 @@ ZK_HD void fmul(Fp2& r, const Fp2& a, const Fp2& b) {
   fsub(r.c0, t0, t1);
 }
 
+// pair of independent Fq2 products (no lockstep variant: the Fq2 product already has 3 independent Fq products)
+ZK_HD void fmul2(Fp2& r1, const Fp2& a1, const Fp2& b1, Fp2& r2, const Fp2& a2, const Fp2& b2) {
+  Fp2 t1, t2;
+  fmul(t1, a1, b1);
+  fmul(t2, a2, b2);
+  r1 = t1;
+  r2 = t2;
+}
+
 ZK_HD void fsqr(Fp2& r, const Fp2& a) {
   Fp s, d, m;
   fadd(s, a.c0, a.c1);

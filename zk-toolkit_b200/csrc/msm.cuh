@@ -34,7 +34,15 @@ namespace zk {
 #if defined(__CUDA_ARCH__)
 ZK_D uint32_t zk_atomic_add(uint32_t* p, uint32_t v) { return atomicAdd(p, v); }
 ZK_D void zk_atomic_or(uint32_t* p, uint32_t v) { atomicOr(p, v); }
+// pull the cache lines of [p, p + bytes) towards the SM ahead of use (no registers held)
+ZK_D void zk_prefetch(const void* p, uint32_t bytes) {
+  const char* c = (const char*)p;
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(c));
+  if ((((uintptr_t)c) & 127u) + bytes > 128u) asm volatile("prefetch.global.L1 [%0];" ::"l"(c + bytes - 1));
+  if (bytes > 128u) asm volatile("prefetch.global.L1 [%0];" ::"l"(c + 128));
+}
 #else
+inline void zk_prefetch(const void*, uint32_t) {}
 inline uint32_t zk_atomic_add(uint32_t* p, uint32_t v) { uint32_t o = *p; *p = o + v; return o; }
 inline void zk_atomic_or(uint32_t* p, uint32_t v) { *p |= v; }
 #endif
@@ -203,8 +211,10 @@ template <class C> struct Accumulate {
     partial_keys[tid] = head ? NO_KEY : key;
     XYZZ<F> acc;
     set_inf(acc);
+    Entry e = entries[beg];
     for (uint32_t pos = beg; pos < end; pos++) {
-      Entry e = entries[pos];
+      Entry en = pos + 1 < end ? entries[pos + 1] : e;
+      zk_prefetch(&points[en.val & 0x7fffffffu], sizeof(Affine<F>));   // next point rides under this mixed add
       if (e.key != key) {
         if (head) bucket_sums[key] = acc; else partials[tid] = acc;
         set_inf(acc);
@@ -214,6 +224,7 @@ template <class C> struct Accumulate {
       Affine<F> q = points[e.val & 0x7fffffffu];
       affine_cneg(q, (e.val >> 31) != 0);
       xyzz_madd(acc, q);
+      e = en;
     }
     if (head) bucket_sums[key] = acc; else partials[tid] = acc;
   }
@@ -250,7 +261,7 @@ template <class C> struct FixupLevel {
         head = !(t == beg && beg > 0 && keys_in[beg - 1] == k);
         if (k != NO_KEY && head) acc = bucket_sums[k]; else set_inf(acc);
       }
-      if (k != NO_KEY) { XYZZ<F> q = parts_in[t]; xyzz_add(acc, q); }
+      if (k != NO_KEY) { XYZZ<F> q = parts_in[t]; xyzz_add_ilp(acc, q); }
     }
     if (key != NO_KEY) {
       if (head) bucket_sums[key] = acc;
@@ -267,8 +278,8 @@ template <class F> ZK_HD void xyzz_mul_small(XYZZ<F>& p, uint32_t s) {
   int top = 31;
   while (!((s >> top) & 1)) top--;
   for (int b = top - 1; b >= 0; b--) {
-    xyzz_dbl(p);
-    if ((s >> b) & 1) xyzz_add(p, base);
+    xyzz_dbl_ilp(p);
+    if ((s >> b) & 1) xyzz_add_ilp(p, base);
   }
 }
 
@@ -285,11 +296,11 @@ template <class C> struct BucketReduce {
     set_inf(run);
     set_inf(acc);
     for (int i = (int)p.K - 1; i >= 0; i--) {
-      if (offsets[base + i] != offsets[base + i + 1]) { XYZZ<F> q = bucket_sums[base + i]; xyzz_add(run, q); }
-      xyzz_add(acc, run);
+      if (offsets[base + i] != offsets[base + i + 1]) { XYZZ<F> q = bucket_sums[base + i]; xyzz_add_ilp(run, q); }
+      xyzz_add_ilp(acc, run);
     }
     xyzz_mul_small(run, k * p.K);
-    xyzz_add(acc, run);
+    xyzz_add_ilp(acc, run);
     out[tid] = acc;
   }
 };
@@ -304,7 +315,7 @@ template <class C> struct PairSum {
     if (i + half >= m) return;
     XYZZ<F>* row = arr + (size_t)win * pitch;
     XYZZ<F> a = row[i], b = row[i + half];
-    xyzz_add(a, b);
+    xyzz_add_ilp(a, b);
     row[i] = a;
   }
 };
@@ -334,9 +345,9 @@ template <class C> struct Finish {
     if (tid != 0) return;
     XYZZ<F> acc = arr[(size_t)(nwin - 1) * pitch];
     for (int w = (int)nwin - 2; w >= 0; w--) {
-      for (uint32_t i = 0; i < c; i++) xyzz_dbl(acc);
+      for (uint32_t i = 0; i < c; i++) xyzz_dbl_ilp(acc);
       XYZZ<F> q = arr[(size_t)w * pitch];
-      xyzz_add(acc, q);
+      xyzz_add_ilp(acc, q);
     }
     if (out_xyzz) *out_xyzz = acc;
     if (out_affine) {
@@ -356,7 +367,7 @@ template <class C> struct CombinePartials {
     if (tid != 0) return;
     XYZZ<F> acc;
     set_inf(acc);
-    for (uint32_t i = 0; i < k; i++) { XYZZ<F> q = parts[i]; xyzz_add(acc, q); }
+    for (uint32_t i = 0; i < k; i++) { XYZZ<F> q = parts[i]; xyzz_add_ilp(acc, q); }
     Affine<F> a;
     xyzz_to_affine(a, acc);
     store_canonical<F>(out_affine, a);
@@ -460,8 +471,9 @@ inline uint32_t msm_windows(uint32_t c, bool half = false) { return (half ? 254u
 
 // Window choice.  Cost model in mixed-add units, calibrated on B200 at n = 2^20 (profiles/): expected
 // sorted pairs (a full window contributes n, a top window of tb bits n (1 - 2^-tb), a carry-only top
-// window n / 2) plus a per-bucket charge for fix-up + reduction (6 with one shared bucket set, 11 per
-// window otherwise), plus a penalty when a narrow top window funnels its pairs into a few giant buckets.
+// window n / 2) plus a per-bucket charge for fix-up + reduction (11 per bucket, times W without a shared
+// window: ~4 ns per bucket vs 0.37 ns per mixed add), plus a penalty when a narrow top window funnels its
+// pairs into a few giant buckets.
 inline uint32_t msm_pick_c(uint32_t n, bool precomp, bool half = false) {
   uint32_t best = 8;
   double best_cost = 1e300;
@@ -469,7 +481,7 @@ inline uint32_t msm_pick_c(uint32_t n, bool precomp, bool half = false) {
     uint32_t bits = half ? 254u : 255u, full = bits / c, tb = bits - full * c;
     double W = full + 1, B = (double)(1u << (c - 1));
     double entries = (double)n * (full + (tb == 0 ? 0.5 : 1.0 - 1.0 / (double)(1u << (tb > 30 ? 30 : tb))));
-    double cost = entries + (precomp ? 6.0 * B : 11.0 * B * W);
+    double cost = entries + 11.0 * B * (precomp ? 1.0 : W);
     if (2 * tb < c) cost += 0.5 * (double)n;   // carry-only or narrow top window: a few giant buckets
     if (cost < best_cost) { best_cost = cost; best = c; }
   }
