@@ -6,7 +6,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libzkmsm.so")
+LIB_PATH = os.environ.get("ZKMSM_LIB") or os.path.join(_HERE, "libzkmsm.so")   # override: A/B builds of the library
 
 OK = 0
 ERR_NAMES = {

@@ -49,6 +49,9 @@ class Context:
         self.device = device
 
     def close(self):
+        for p in getattr(self, "_pinned", []):
+            self.lib.zkmsm_host_free(p)
+        self._pinned = []
         if getattr(self, "h", None):
             self.lib.zkmsm_destroy(self.h)
             self.h = None
@@ -62,6 +65,19 @@ class Context:
     def _check(self, rc):
         if rc != L.OK:
             raise L.ZkmsmError(rc, self.lib.zkmsm_last_error(self.h).decode())
+
+    def pinned_array(self, shape, dtype=np.uint32):
+        """numpy array in page-locked host memory (zkmsm_host_alloc): H2D copies of it run at full PCIe rate
+        and asynchronously.  Freed with the context."""
+        nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = ctypes.c_void_p()
+        rc = self.lib.zkmsm_host_alloc(max(nbytes, 16), ctypes.byref(p))
+        if rc != L.OK:
+            raise L.ZkmsmError(rc, "zkmsm_host_alloc")
+        self._pinned = getattr(self, "_pinned", [])
+        self._pinned.append(p)
+        buf = (ctypes.c_uint8 * max(nbytes, 16)).from_address(p.value)
+        return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
 
     def set_stream(self, cuda_stream_ptr):
         self._check(self.lib.zkmsm_set_stream(self.h, ctypes.c_void_p(cuda_stream_ptr or 0)))

@@ -14,8 +14,12 @@ namespace zk {
 
 static constexpr uint32_t kBlock = 128;
 
+#ifndef ZK_MIN_BLOCKS
+#define ZK_MIN_BLOCKS 1   // a translation unit may ask ptxas to fit this many 128-thread blocks per SM
+#endif
+
 template <class Body, class... A>
-__global__ void __launch_bounds__(kBlock) body_kernel(uint32_t nthreads, A... a) {
+__global__ void __launch_bounds__(kBlock, ZK_MIN_BLOCKS) body_kernel(uint32_t nthreads, A... a) {
   uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
   if (tid < nthreads) Body::run(tid, a...);
 }

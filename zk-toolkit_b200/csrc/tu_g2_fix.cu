@@ -1,0 +1,5 @@
+// G2 fix-up tree (field arithmetic inlined)
+#define ZK_DEFINE_LAUNCH
+#include "launch.cuh"
+#include "msm.cuh"
+ZK_INSTANTIATE_KERNEL(zk::FixupLevel<zk::G2>);

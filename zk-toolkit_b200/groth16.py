@@ -92,10 +92,18 @@ class Prover:
         self.u, self.v, self.h, self.wit = u_agg, v_agg, h, witness_wires
         self._limbs = {}   # scalar vectors marshalled once to the ABI layout (padding depends on the CRS)
 
-    def _arr(self, name, vec, n):
-        key = (name, n)
+    def _arr(self, ctx, name, parts, extra):
+        """scalar vector = concatenation of padded `parts` [(vec, n), ...] plus `extra` trailing slots that change
+        per proof; kept in pinned host memory so that only the trailing rows are rewritten for each proof"""
+        key = (name, tuple(n for _, n in parts), extra)
         if key not in self._limbs:
-            self._limbs[key] = scalars_to_array(_pad(vec, n))
+            total = sum(n for _, n in parts) + extra
+            arr = ctx.pinned_array((total, 8))
+            pos = 0
+            for vec, n in parts:
+                arr[pos:pos + n] = scalars_to_array(_pad(vec, n))
+                pos += n
+            self._limbs[key] = arr
         return self._limbs[key]
 
     @classmethod
@@ -107,15 +115,17 @@ class Prover:
         ctx = crs.ctx
         r, s = int(r) % R, int(s) % R
         n = crs.n
-        su = np.concatenate([self._arr("u", self.u, n), scalars_to_array([1, r])])
-        sv = np.concatenate([self._arr("v", self.v, n), scalars_to_array([1, s])])
+        su = self._arr(ctx, "u", [(self.u, n)], 2)
+        su[n:] = scalars_to_array([1, r])
+        sv = self._arr(ctx, "v", [(self.v, n)], 2)
+        sv[n:] = scalars_to_array([1, s])
         A = G1Point.from_limbs(*ctx.msm(crs.set_A.set, su))                       # prover.rs:118
         B = G2Point.from_limbs(*ctx.msm(crs.set_B.set, sv))                       # :119
         B_g1 = G1Point.from_limbs(*ctx.msm(crs.set_Bg1.set, sv))                  # :120
         if len(self.wit) != crs.n_wit:
             raise IndexError("witness length does not match crs.g1.uvw_wit")
-        sc = np.concatenate([self._arr("wit", self.wit, crs.n_wit), self._arr("h", self.h, crs.n_xt),
-                             scalars_to_array([(-(r * s)) % R])])
+        sc = self._arr(ctx, "c", [(self.wit, crs.n_wit), (self.h, crs.n_xt)], 1)
+        sc[crs.n_wit + crs.n_xt:] = scalars_to_array([(-(r * s)) % R])
         C_main = G1Point.from_limbs(*ctx.msm(crs.set_C.set, sc))                  # :128-133 and -(delta r) s
         xy, inf = G1Point.pack([A, B_g1])
         C_blind = G1Point.from_limbs(*ctx.msm_oneshot(1, xy, inf if inf.any() else None, scalars_to_array([s, r])))  # :137-138
