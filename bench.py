@@ -305,6 +305,15 @@ def main():
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
+    # DRAM bytes per launch of the dominant kernel: taken from the committed ncu --set full capture of the
+    # same command (profiles/*_accumulate_traffic.json, written by tools/summarize_profiles.py), never guessed
+    traffic = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "accumulate_traffic.json")))
+        if tr.get("n") == n_total and tr.get("n_gpus", 1) == world:
+            traffic = tr
+    except Exception:
+        pass
     roofline = {
         "bound": "int32 multiplier (IMAD.WIDE on the fma pipe); not hbm, not tensor",
         "kernel": "Accumulate<G1> (XYZZ mixed adds into buckets)",
@@ -318,11 +327,19 @@ def main():
         "kernel_ms": round(acc_avg_ms, 4),
         "kernel_share_of_step": round(acc_avg_ms / (sum(step_ms) / len(step_ms)), 4),
         "step_frac": round(n_total * LP_PER_G1_POINT / (ms_per_step * 1e-3) / lp_peak, 4) if lp_peak else None,
-        "traffic": None,
+        "traffic": traffic,
+        "actual_lp_per_point": None,
         "hbm": {"achieved_GBps": round(n_total * BYTES_PER_G1_POINT / (ms_per_step * 1e-3) / 1e9, 2),
                 "peak_GBps": peaks.get("hbm_gbs"), "note": "algorithmic 128 B/point; the path is multiplier-bound"},
         "stages_ms_last_step": stage_profile,
     }
+
+    info = pts.info()
+    if info["precomputed"]:
+        # what the kernel really multiplies: windows used x 10 modmul x 300 LP (fewer windows than the canonical 16
+        # with precomputed tables): multiplier-pipe utilisation ~ frac * actual / canonical
+        roofline["actual_lp_per_point"] = info["windows"] * 3000
+        roofline["window_bits"] = info["c"]
 
     # ---- CPU baseline beside it (rank 0, N = 1 only): the reference algorithm on a bounded sample
     cpu_baseline = None

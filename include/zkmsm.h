@@ -80,6 +80,9 @@ int zkmsm_g2_load_points(zkmsm_ctx* ctx, const uint32_t* xy, const uint8_t* inf_
                          unsigned flags, zkmsm_points** out);
 int zkmsm_points_free(zkmsm_ctx* ctx, zkmsm_points* pts);
 size_t zkmsm_points_len(const zkmsm_points* pts);
+/* Layout of a set: window width c and number of slabs (0 / 0 for a plain set, whose c is chosen per call),
+ * and the two load flags.  Any out-pointer may be NULL. */
+int zkmsm_points_info(const zkmsm_points* pts, unsigned* c, unsigned* windows, int* precomputed, int* subgroup);
 /* Copy a point set back as canonical affine limbs (+ flags, nullable). */
 int zkmsm_points_read(zkmsm_ctx* ctx, const zkmsm_points* pts, size_t first, size_t n, uint32_t* xy,
                       uint8_t* inf_flags);

@@ -29,7 +29,7 @@ class ZkmsmError(RuntimeError):
 SYMBOLS = [
     "zkmsm_version", "zkmsm_create", "zkmsm_destroy", "zkmsm_set_stream", "zkmsm_last_error", "zkmsm_set_window",
     "zkmsm_host_alloc", "zkmsm_host_free",
-    "zkmsm_g1_load_points", "zkmsm_g2_load_points", "zkmsm_points_free", "zkmsm_points_len", "zkmsm_points_read",
+    "zkmsm_g1_load_points", "zkmsm_g2_load_points", "zkmsm_points_free", "zkmsm_points_len", "zkmsm_points_info", "zkmsm_points_read",
     "zkmsm_g1_msm", "zkmsm_g2_msm", "zkmsm_g1_msm_device", "zkmsm_g2_msm_device",
     "zkmsm_g1_msm_oneshot", "zkmsm_g2_msm_oneshot",
     "zkmsm_g1_msm_enqueue", "zkmsm_g2_msm_enqueue", "zkmsm_g1_msm_result", "zkmsm_g2_msm_result",
@@ -70,6 +70,7 @@ def load():
         "zkmsm_g2_load_points": (ci, [vp, vp, vp, sz, cu, vpp]),
         "zkmsm_points_free": (ci, [vp, vp]),
         "zkmsm_points_len": (sz, [vp]),
+        "zkmsm_points_info": (ci, [vp, ctypes.POINTER(cu), ctypes.POINTER(cu), ip, ip]),
         "zkmsm_points_read": (ci, [vp, vp, sz, sz, vp, vp]),
         "zkmsm_g1_msm": (ci, [vp, vp, vp, sz, vp, ip]),
         "zkmsm_g2_msm": (ci, [vp, vp, vp, sz, vp, ip]),

@@ -15,6 +15,12 @@ class PointSet:
     def __len__(self):
         return self.n
 
+    def info(self):
+        c, w, pre, sub = ctypes.c_uint(0), ctypes.c_uint(0), ctypes.c_int(0), ctypes.c_int(0)
+        self.ctx._check(self.ctx.lib.zkmsm_points_info(self.handle, ctypes.byref(c), ctypes.byref(w), ctypes.byref(pre),
+                                                       ctypes.byref(sub)))
+        return {"c": c.value, "windows": w.value, "precomputed": bool(pre.value), "subgroup": bool(sub.value)}
+
     def read(self, first=0, n=None):
         """canonical affine limbs and infinity flags of points [first, first+n)"""
         n = self.n - first if n is None else n

@@ -265,6 +265,15 @@ extern "C" int zkmsm_points_free(zkmsm_ctx* ctx, zkmsm_points* ps) {
 
 extern "C" size_t zkmsm_points_len(const zkmsm_points* ps) { return ps ? ps->n : 0; }
 
+extern "C" int zkmsm_points_info(const zkmsm_points* ps, unsigned* c, unsigned* windows, int* precomputed, int* subgroup) {
+  if (!ps) return ZKMSM_ERR_INVALID_ARG;
+  if (c) *c = ps->c;
+  if (windows) *windows = ps->precomp ? ps->W : 0;
+  if (precomputed) *precomputed = ps->precomp ? 1 : 0;
+  if (subgroup) *subgroup = ps->half ? 1 : 0;
+  return ZKMSM_OK;
+}
+
 template <class C>
 static int points_read_impl(zkmsm_ctx* ctx, const zkmsm_points* ps, size_t first, size_t n, uint32_t* xy, uint8_t* inf) {
   typedef typename C::F F;
