@@ -112,6 +112,11 @@ int zkmsm_g1_msm_enqueue(zkmsm_ctx* ctx, const zkmsm_points* pts, const uint32_t
 int zkmsm_g2_msm_enqueue(zkmsm_ctx* ctx, const zkmsm_points* pts, const uint32_t* scalars_device, size_t n);
 int zkmsm_g1_msm_result(zkmsm_ctx* ctx, uint32_t out_xy[24], int* out_is_inf);
 int zkmsm_g2_msm_result(zkmsm_ctx* ctx, uint32_t out_xy[48], int* out_is_inf);
+/* Host-scalar variant of enqueue: copies the scalars (asynchronously when they live in pinned memory, see
+ * zkmsm_host_alloc) and enqueues; zkmsm_g{1,2}_msm_result collects.  Several contexts on one device give
+ * concurrent MSMs (the five of a Groth16 proof, prover.rs:108-133, are independent). */
+int zkmsm_g1_msm_begin(zkmsm_ctx* ctx, const zkmsm_points* pts, const uint32_t* scalars, size_t n);
+int zkmsm_g2_msm_begin(zkmsm_ctx* ctx, const zkmsm_points* pts, const uint32_t* scalars, size_t n);
 /* Number of kernels the last enqueue launched. */
 int zkmsm_last_launch_count(const zkmsm_ctx* ctx);
 /* Per-kernel timing of the MSMs that follow: CUDA events on the launching stream around every

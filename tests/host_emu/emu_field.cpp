@@ -22,6 +22,8 @@ int emu_field_op(int field, int op, const uint32_t* a, const uint32_t* b, uint32
       case 5: fto_mont(z, a); break;
       case 6: ffrom_mont(z.v, x); break;
       case 7: finv_fermat(z, x); break;
+      case 8: fsqr(z, x); break;
+      case 9: fmul2(z, x, y, y, y, x); fadd(z, z, y); break;   // x*y + y*x through the lockstep pair
       default: return -1;
     }
     memcpy(r, z.v, 48);
@@ -37,6 +39,8 @@ int emu_field_op(int field, int op, const uint32_t* a, const uint32_t* b, uint32
       case 5: fto_mont(z, a); break;
       case 6: ffrom_mont(z.v, x); break;
       case 7: finv_fermat(z, x); break;
+      case 8: fsqr(z, x); break;
+      case 9: fmul2(z, x, y, y, y, x); fadd(z, z, y); break;
       default: return -1;
     }
     memcpy(r, z.v, 32);

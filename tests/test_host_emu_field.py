@@ -60,6 +60,13 @@ def test_mont_field_ops(lib, field):
         assert field_op(lib, field, 1, a, b) == (a - b) % p
         # Montgomery product: mont(a,b) = a*b/R
         assert field_op(lib, field, 2, a, b) == a * b * pow(Rm, -1, p) % p
+    rinv = pow(Rm, -1, p)
+    allones = [((1 << (32 * n)) - 1) % p, ((1 << (32 * n - 1)) - 1) % p, (0xFFFFFFFF << (32 * (n - 1))) % p]
+    for a in vals + allones:
+        assert field_op(lib, field, 8, a) == a * a * rinv % p            # dedicated squaring == mont(a, a)
+    for _ in range(50):
+        a, b = rnd.choice(vals + allones), rnd.choice(vals)
+        assert field_op(lib, field, 9, a, b) == 2 * a * b * rinv % p     # lockstep pair
     for a in vals[1:40]:
         am = a * Rm % p
         assert field_op(lib, field, 4, am) == pow(a, -1, p) * Rm % p      # binary extended Euclid

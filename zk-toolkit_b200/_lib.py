@@ -32,7 +32,7 @@ SYMBOLS = [
     "zkmsm_g1_load_points", "zkmsm_g2_load_points", "zkmsm_points_free", "zkmsm_points_len", "zkmsm_points_info", "zkmsm_points_read",
     "zkmsm_g1_msm", "zkmsm_g2_msm", "zkmsm_g1_msm_device", "zkmsm_g2_msm_device",
     "zkmsm_g1_msm_oneshot", "zkmsm_g2_msm_oneshot",
-    "zkmsm_g1_msm_enqueue", "zkmsm_g2_msm_enqueue", "zkmsm_g1_msm_result", "zkmsm_g2_msm_result",
+    "zkmsm_g1_msm_enqueue", "zkmsm_g2_msm_enqueue", "zkmsm_g1_msm_begin", "zkmsm_g2_msm_begin", "zkmsm_g1_msm_result", "zkmsm_g2_msm_result",
     "zkmsm_last_launch_count", "zkmsm_profile", "zkmsm_profile_read",
     "zkmsm_g1_msm_partial", "zkmsm_g2_msm_partial", "zkmsm_g1_msm_partial_device",
     "zkmsm_g1_combine", "zkmsm_g2_combine", "zkmsm_g1_combine_device",
@@ -78,6 +78,8 @@ def load():
         "zkmsm_g2_msm_device": (ci, [vp, vp, vp, sz, vp, ip]),
         "zkmsm_g1_msm_oneshot": (ci, [vp, vp, vp, vp, sz, vp, ip]),
         "zkmsm_g2_msm_oneshot": (ci, [vp, vp, vp, vp, sz, vp, ip]),
+        "zkmsm_g1_msm_begin": (ci, [vp, vp, vp, sz]),
+        "zkmsm_g2_msm_begin": (ci, [vp, vp, vp, sz]),
         "zkmsm_g1_msm_enqueue": (ci, [vp, vp, vp, sz]),
         "zkmsm_g2_msm_enqueue": (ci, [vp, vp, vp, sz]),
         "zkmsm_g1_msm_result": (ci, [vp, vp, ip]),

@@ -154,6 +154,14 @@ class Context:
         self._check(fn(self.h, pts.handle, ctypes.c_void_p(scalars_dev_ptr), n, L.dptr(out), ctypes.byref(inf)))
         return out, bool(inf.value)
 
+    def msm_begin(self, pts: PointSet, scalars, n=None):
+        """start an MSM with host scalars (keep the array alive until msm_result); returns immediately"""
+        sc = L.as_u32(scalars, 8).reshape(-1, 8)
+        n = sc.shape[0] if n is None else n
+        fn = self.lib.zkmsm_g1_msm_begin if pts.group == 1 else self.lib.zkmsm_g2_msm_begin
+        self._check(fn(self.h, pts.handle, L.dptr(sc), n))
+        self._inflight = sc
+
     def msm_enqueue(self, pts: PointSet, scalars_dev_ptr, n):
         fn = self.lib.zkmsm_g1_msm_enqueue if pts.group == 1 else self.lib.zkmsm_g2_msm_enqueue
         self._check(fn(self.h, pts.handle, ctypes.c_void_p(scalars_dev_ptr), n))

@@ -219,7 +219,112 @@ template <class C> ZK_FMUL_ATTR void fmul(Mont<C>& r, const Mont<C>& a, const Mo
   freduce_once(r, t);
 }
 
-template <class C> ZK_HD void fsqr(Mont<C>& r, const Mont<C>& a) { fmul(r, a, a); }
+namespace detail {
+
+// t[0..2n) = a^2 as a plain integer.  Off-diagonal products a_i a_j (i < j) are summed once into two
+// accumulators (64-bit digits at even resp. odd limb positions), doubled, and the squares a_i^2 are added:
+// n(n+1)/2 = 78 limb products for n = 12 instead of 144.  Rows are taken in increasing i, so the carry out
+// of a row's chain always lands in a limb no earlier row has used for a product (it holds 0, or a carry).
+template <int n> ZK_HD void square_wide(uint32_t* t, const uint32_t* a) {
+  uint32_t e[2 * n], o[2 * n];
+#pragma unroll
+  for (int k = 0; k < 2 * n; k++) { e[k] = 0; o[k] = 0; }
+#pragma unroll
+  for (int i = 0; i < n - 1; i++) {
+    // positions i + j with j = i+1, i+3, ..: parity of (2i + 1) -> odd accumulator
+    {
+      int p = 2 * i + 1;
+      o[p] = ptx::mad_lo_cc(a[i], a[i + 1], o[p]);
+      o[p + 1] = ptx::madc_hi_cc(a[i], a[i + 1], o[p + 1]);
+#pragma unroll
+      for (int j = i + 3; j < n; j += 2) {
+        p = i + j;
+        o[p] = ptx::madc_lo_cc(a[i], a[j], o[p]);
+        o[p + 1] = ptx::madc_hi_cc(a[i], a[j], o[p + 1]);
+      }
+      o[p + 2] = ptx::addc(o[p + 2], 0);
+    }
+    if (i + 2 < n) {  // j = i+2, i+4, ..: even accumulator
+      int p = 2 * i + 2;
+      e[p] = ptx::mad_lo_cc(a[i], a[i + 2], e[p]);
+      e[p + 1] = ptx::madc_hi_cc(a[i], a[i + 2], e[p + 1]);
+#pragma unroll
+      for (int j = i + 4; j < n; j += 2) {
+        p = i + j;
+        e[p] = ptx::madc_lo_cc(a[i], a[j], e[p]);
+        e[p + 1] = ptx::madc_hi_cc(a[i], a[j], e[p + 1]);
+      }
+      e[p + 2] = ptx::addc(e[p + 2], 0);
+    }
+  }
+  // s = e + o (limb 0 and limb 2n-1 of the off-diagonal sum are zero), then t = 2 s
+  uint32_t s[2 * n];
+  s[0] = 0;
+  s[1] = ptx::add_cc(e[1], o[1]);
+#pragma unroll
+  for (int k = 2; k < 2 * n - 1; k++) s[k] = ptx::addc_cc(e[k], o[k]);
+  s[2 * n - 1] = ptx::addc(e[2 * n - 1], o[2 * n - 1]);
+#pragma unroll
+  for (int k = 2 * n - 1; k > 0; k--) s[k] = (s[k] << 1) | (s[k - 1] >> 31);
+  // + diagonal: one carry chain over all 2n limbs
+  t[0] = ptx::mad_lo_cc(a[0], a[0], s[0]);
+  t[1] = ptx::madc_hi_cc(a[0], a[0], s[1]);
+#pragma unroll
+  for (int i = 1; i < n; i++) {
+    t[2 * i] = ptx::madc_lo_cc(a[i], a[i], s[2 * i]);
+    t[2 * i + 1] = ptx::madc_hi_cc(a[i], a[i], s[2 * i + 1]);
+  }
+}
+
+// r = t / R mod p for a 2n-limb t < p * R (Montgomery reduction), result fully reduced.
+// Same sliding even/odd window as fmul: each step cancels the low limb with m p and shifts; instead of a
+// row a * b_i, the next limb of t enters at the top of the window.
+template <class C> ZK_HD void mont_reduce_wide(Mont<C>& r, const uint32_t* t) {
+  constexpr int n = C::N;
+  uint32_t ev[n], od[n];
+#pragma unroll
+  for (int k = 0; k < n; k++) { ev[k] = t[k]; od[k] = 0; }
+  uint32_t* E = ev;
+  uint32_t* O = od;
+#pragma unroll
+  for (int i = 0; i < n; i++) {
+    if (i > 0) {
+      // shift: the old odd accumulator becomes even, the old even one (>> 64) becomes odd
+      uint32_t* tmp = E; E = O; O = tmp;
+      E[0] = ptx::add_cc(E[0], O[1]);
+#pragma unroll
+      for (int k = 0; k < n - 2; k++) O[k] = ptx::addc_cc(O[k + 2], 0);
+      // incoming limb t[n + i - 1] sits at window limb n - 1 = odd digit (n-1, n): O[n-2], O[n-1]
+      O[n - 2] = ptx::addc_cc(t[n + i - 1], 0);
+      O[n - 1] = ptx::addc(0, 0);
+    }
+    uint32_t m = E[0] * C::INV;
+    row_mad<n>(O, ModOdd<C>(), m);
+    row_mad<n>(E, ModEven<C>(), m);
+    O[n - 1] = ptx::addc(O[n - 1], 0);
+  }
+  // value = (E + O 2^32) / 2^32 + t[2n-1] 2^(32(n-1)), with E[0] == 0
+  uint32_t u[n];
+  u[0] = ptx::add_cc(O[0], E[1]);
+#pragma unroll
+  for (int k = 1; k < n - 1; k++) u[k] = ptx::addc_cc(O[k], E[k + 1]);
+  u[n - 1] = ptx::addc(O[n - 1], 0);
+  u[n - 1] += t[2 * n - 1];
+  freduce_once(r, u);
+}
+
+}  // namespace detail
+
+// Dedicated squaring: 78 + 144 limb products + 12 for the m_i, instead of 288 + 12 (22 % fewer multiplier slots).
+template <class C> ZK_HD void fsqr(Mont<C>& r, const Mont<C>& a) {
+#if defined(ZK_FMUL_NOINLINE) && defined(__CUDACC__)
+  fmul(r, a, a);   // call-based translation units keep the single shared multiplication routine
+#else
+  uint32_t t[2 * C::N];
+  detail::square_wide<C::N>(t, a.v);
+  detail::mont_reduce_wide<C>(r, t);
+#endif
+}
 
 // Two independent products advanced in lockstep (row by row), for the latency-bound kernels that run
 // one warp per scheduler: the two carry chains overlap, so a pair costs little more than one product

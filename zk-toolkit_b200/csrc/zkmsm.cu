@@ -404,6 +404,23 @@ static int msm_host_impl(zkmsm_ctx* ctx, const zkmsm_points* ps, const uint32_t*
   return msm_result_impl(ctx, C::AFF_LIMBS, out_xy, out_is_inf);
 }
 
+// asynchronous first half of msm_host_impl: copy the scalars (truly asynchronous from pinned memory) and enqueue
+template <class C>
+static int msm_begin_impl(zkmsm_ctx* ctx, const zkmsm_points* ps, const uint32_t* scalars, size_t n, int curve) {
+  if (!ctx || !ps) return fail(ctx, ZKMSM_ERR_INVALID_ARG, "null argument");
+  if (n > ps->n) return fail(ctx, ZKMSM_ERR_TOO_FEW_POINTS, "%zu scalars but only %zu points", n, ps->n);
+  const uint32_t* d_s;
+  int rc = upload_scalars(ctx, scalars, n, &d_s);
+  if (rc) return rc;
+  return msm_enqueue_impl<C>(ctx, ps, d_s, n, curve, true, nullptr);
+}
+extern "C" int zkmsm_g1_msm_begin(zkmsm_ctx* ctx, const zkmsm_points* ps, const uint32_t* s, size_t n) {
+  return msm_begin_impl<G1>(ctx, ps, s, n, 1);
+}
+extern "C" int zkmsm_g2_msm_begin(zkmsm_ctx* ctx, const zkmsm_points* ps, const uint32_t* s, size_t n) {
+  return msm_begin_impl<G2>(ctx, ps, s, n, 2);
+}
+
 extern "C" int zkmsm_g1_msm(zkmsm_ctx* ctx, const zkmsm_points* ps, const uint32_t* s, size_t n, uint32_t* out, int* inf) {
   return msm_host_impl<G1>(ctx, ps, s, n, 1, out, inf);
 }

@@ -46,6 +46,16 @@ class DeviceCRS:
         self.set_B = G2Points(list(g2_xi) + [g2_beta, g2_delta], precompute=precompute, ctx=self.ctx, in_subgroup=True)
         self.set_C = mk1(list(g1_uvw_wit) + list(g1_xt_by_delta) + [g1_delta])
 
+    def contexts(self, k):
+        """k contexts on this CRS's device (the first is the CRS's own), created on first use"""
+        from .context import Context
+        pool = getattr(self, "_pool", None)
+        if pool is None:
+            pool = self._pool = [self.ctx]
+        while len(pool) < k:
+            pool.append(Context(self.ctx.device))
+        return pool[:k]
+
     @classmethod
     def from_arrays(cls, arrs, precompute=True, ctx=None):
         """arrs: dict of canonical limb arrays (for large synthetic instances built on the device):
@@ -119,14 +129,21 @@ class Prover:
         su[n:] = scalars_to_array([1, r])
         sv = self._arr(ctx, "v", [(self.v, n)], 2)
         sv[n:] = scalars_to_array([1, s])
-        A = G1Point.from_limbs(*ctx.msm(crs.set_A.set, su))                       # prover.rs:118
-        B = G2Point.from_limbs(*ctx.msm(crs.set_B.set, sv))                       # :119
-        B_g1 = G1Point.from_limbs(*ctx.msm(crs.set_Bg1.set, sv))                  # :120
         if len(self.wit) != crs.n_wit:
             raise IndexError("witness length does not match crs.g1.uvw_wit")
         sc = self._arr(ctx, "c", [(self.wit, crs.n_wit), (self.h, crs.n_xt)], 1)
         sc[crs.n_wit + crs.n_xt:] = scalars_to_array([(-(r * s)) % R])
-        C_main = G1Point.from_limbs(*ctx.msm(crs.set_C.set, sc))                  # :128-133 and -(delta r) s
+        # the four large MSMs are independent: one context (stream + workspace) each, all in flight at once, so
+        # the latency-bound reduction tail of one overlaps the accumulation of the others
+        cA, cB, cBg1, cC = crs.contexts(4)
+        cB.msm_begin(crs.set_B.set, sv)                                           # prover.rs:119 (G2, the longest)
+        cA.msm_begin(crs.set_A.set, su)                                           # :118
+        cBg1.msm_begin(crs.set_Bg1.set, sv)                                       # :120
+        cC.msm_begin(crs.set_C.set, sc)                                           # :128-133 and -(delta r) s
+        A = G1Point.from_limbs(*cA.msm_result(1))
+        B_g1 = G1Point.from_limbs(*cBg1.msm_result(1))
         xy, inf = G1Point.pack([A, B_g1])
-        C_blind = G1Point.from_limbs(*ctx.msm_oneshot(1, xy, inf if inf.any() else None, scalars_to_array([s, r])))  # :137-138
+        C_blind = G1Point.from_limbs(*cA.msm_oneshot(1, xy, inf if inf.any() else None, scalars_to_array([s, r])))  # :137-138
+        C_main = G1Point.from_limbs(*cC.msm_result(1))
+        B = G2Point.from_limbs(*cB.msm_result(2))
         return Proof(A, B, C_main + C_blind)
