@@ -317,7 +317,7 @@ template <class C> ZK_HD void mont_reduce_wide(Mont<C>& r, const uint32_t* t) {
 
 // Dedicated squaring: 78 + 144 limb products + 12 for the m_i, instead of 288 + 12 (22 % fewer multiplier slots).
 template <class C> ZK_HD void fsqr(Mont<C>& r, const Mont<C>& a) {
-#if defined(ZK_FMUL_NOINLINE) && defined(__CUDACC__)
+#if (defined(ZK_FMUL_NOINLINE) && defined(__CUDACC__)) || defined(ZK_NO_FSQR)
   fmul(r, a, a);   // call-based translation units keep the single shared multiplication routine
 #else
   uint32_t t[2 * C::N];

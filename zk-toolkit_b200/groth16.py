@@ -142,8 +142,9 @@ class Prover:
         cC.msm_begin(crs.set_C.set, sc)                                           # :128-133 and -(delta r) s
         A = G1Point.from_limbs(*cA.msm_result(1))
         B_g1 = G1Point.from_limbs(*cBg1.msm_result(1))
-        xy, inf = G1Point.pack([A, B_g1])
-        C_blind = G1Point.from_limbs(*cA.msm_oneshot(1, xy, inf if inf.any() else None, scalars_to_array([s, r])))  # :137-138
         C_main = G1Point.from_limbs(*cC.msm_result(1))
         B = G2Point.from_limbs(*cB.msm_result(2))
+        # s A + r B_g1 needs A and B_g1; it is a 2-term MSM, run once the device is idle again
+        xy, inf = G1Point.pack([A, B_g1])
+        C_blind = G1Point.from_limbs(*cA.msm_oneshot(1, xy, inf if inf.any() else None, scalars_to_array([s, r])))  # :137-138
         return Proof(A, B, C_main + C_blind)
