@@ -212,6 +212,24 @@ template <class C> struct Accumulate {
     XYZZ<F> acc;
     set_inf(acc);
     Entry e = entries[beg];
+#if defined(ZK_ACC_DOUBLE_BUFFER)
+    // software pipeline: the next point is loaded into registers before the current mixed add starts
+    Affine<F> qn = points[e.val & 0x7fffffffu];
+    for (uint32_t pos = beg; pos < end; pos++) {
+      Entry en = pos + 1 < end ? entries[pos + 1] : e;
+      Affine<F> q = qn;
+      qn = points[en.val & 0x7fffffffu];
+      if (e.key != key) {
+        if (head) bucket_sums[key] = acc; else partials[tid] = acc;
+        set_inf(acc);
+        key = e.key;
+        head = true;
+      }
+      affine_cneg(q, (e.val >> 31) != 0);
+      xyzz_madd(acc, q);
+      e = en;
+    }
+#else
     for (uint32_t pos = beg; pos < end; pos++) {
       Entry en = pos + 1 < end ? entries[pos + 1] : e;
       zk_prefetch(&points[en.val & 0x7fffffffu], sizeof(Affine<F>));   // next point rides under this mixed add
@@ -226,6 +244,7 @@ template <class C> struct Accumulate {
       xyzz_madd(acc, q);
       e = en;
     }
+#endif
     if (head) bucket_sums[key] = acc; else partials[tid] = acc;
   }
 };
