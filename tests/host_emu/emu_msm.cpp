@@ -18,6 +18,13 @@ struct HostExec {
     launches++;
   }
   void zero(void* p, size_t bytes) { memset(p, 0, bytes); }
+  template <class C> void bucket_reduce(const MsmPlan& p, const uint32_t* offsets, const XYZZ<typename C::F>* buckets,
+                                        XYZZ<typename C::F>* out) {
+    launch<BucketReduce<C>>(p.nwin * (p.B / p.K), p, offsets, buckets, out);
+  }
+  template <class C> void pair_sum(uint32_t nwin, uint32_t pitch, uint32_t m, uint32_t half, XYZZ<typename C::F>* arr) {
+    launch<PairSum<C>>(nwin * half, nwin, pitch, m, half, arr);
+  }
   void exclusive_scan(uint32_t nb, uint32_t* hist_cursor, uint32_t* offsets, uint32_t* segsum) {
     uint32_t nseg = (nb + SCAN_SEG - 1) / SCAN_SEG;
     launch<ScanLocal>(nseg, nb, (const uint32_t*)hist_cursor, segsum);

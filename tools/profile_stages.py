@@ -51,6 +51,8 @@ def main():
                 print(f"== n=2^{logn} precomp={pre} half={os.environ.get('HALF', '1')} c={c} L={os.environ.get('ZKMSM_L','-')} K={os.environ.get('ZKMSM_K','-')}: {total:.3f} ms/MSM ({n/total/1e3:.1f} Mpts/s), sum of kernels {ssum:.3f} ms, {len(rows)} launches")
                 for name, (ms, cnt, thr) in agg.items():
                     print(f"   {name:18s} {ms:8.3f} ms  {100*ms/ssum:5.1f}%  x{cnt}  max_threads={thr}")
+                if os.environ.get("DETAIL"):
+                    print("   per launch:", " ".join(f"{nm[:6]}:{ms*1e3:.0f}us/{thr}" for nm, ms, thr in rows))
                 sys.stdout.flush()
                 ctx.set_window(0)
                 ctx.profile(False)

@@ -3,7 +3,7 @@
 #include <cstdio>
 #include <cstdint>
 #include <cuda_runtime.h>
-#include "../zk-toolkit_b200/csrc/fp.cuh"
+#include "../zk-toolkit_b200/csrc/ec.cuh"
 using namespace zk;
 
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %d\n", cudaGetErrorString(e), __LINE__); return 1; } } while (0)
@@ -167,6 +167,31 @@ __global__ void k_fmul28c(F28* io, int iters, uint32_t inv28) {
   io[i] = x;
 }
 
+// ---- G: latency of one point operation on a lone warp (what bounds the reduction tail)
+template <int MODE> __global__ void k_pointop(XYZZ<Fp>* io, int iters) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  XYZZ<Fp> a = io[2 * i], b = io[2 * i + 1];
+  for (int it = 0; it < iters; it++) {
+    if (MODE == 0) xyzz_add(a, b);
+    else if (MODE == 1) xyzz_add_ilp(a, b);
+    else if (MODE == 2) xyzz_dbl(a);
+    else xyzz_dbl_ilp(a);
+  }
+  io[2 * i] = a;
+}
+__global__ void k_fmul_lat(Fp* io, int iters) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  Fp x = io[i], y = io[i ^ 1];
+  for (int it = 0; it < iters; it++) fmul(x, x, y);
+  io[i] = x;
+}
+__global__ void k_fmul2_lat(Fp* io, int iters) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  Fp x = io[i], y = io[i ^ 1], z = io[i ^ 2];
+  for (int it = 0; it < iters; it++) fmul2(x, x, y, z, z, y);
+  io[i] = x; io[i ^ 2] = z;
+}
+
 template <class K, class... A> float timeit(int grid, int block, K k, A... a) {
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   k<<<grid, block>>>(a...);  // warm
@@ -208,6 +233,18 @@ int main() {
     float ms3 = timeit(grid, block, k_fmul28c, io28, it2, inv28);
     double n = (double)grid * block * it2;
     printf("modmul @%4d thr/SM: 12x32 carry-chain %7.2f G/s | 14x28 carry-free %7.2f G/s | 14x28 const-q %7.2f G/s\n", tps, n / ms / 1e6, n / ms2 / 1e6, n / ms3 / 1e6);
+  }
+  {
+    XYZZ<Fp>* pio; CK(cudaMalloc(&pio, sizeof(XYZZ<Fp>) * 2 * sms * 128)); CK(cudaMemset(pio, 0x11, sizeof(XYZZ<Fp>) * 2 * sms * 128));
+    int it3 = 200;
+    for (int warps : {1, 4}) {   // warps per SM (1 = a lone warp on one scheduler, 4 = one per scheduler)
+      int block = warps * 32, grid = sms;
+      float m0 = timeit(grid, block, k_pointop<0>, pio, it3), m1 = timeit(grid, block, k_pointop<1>, pio, it3);
+      float m2 = timeit(grid, block, k_pointop<2>, pio, it3), m3 = timeit(grid, block, k_pointop<3>, pio, it3);
+      float f1 = timeit(grid, block, k_fmul_lat, io, 2000), f2 = timeit(grid, block, k_fmul2_lat, io, 2000);
+      printf("latency @%d warp(s)/SM: fmul %.3f us | fmul2 pair %.3f us | xyzz_add %.2f us, _ilp %.2f us | xyzz_dbl %.2f us, _ilp %.2f us\n",
+             warps, f1 * 1e3 / 2000, f2 * 1e3 / 2000, m0 * 1e3 / it3, m1 * 1e3 / it3, m2 * 1e3 / it3, m3 * 1e3 / it3);
+    }
   }
   CK(cudaDeviceSynchronize());
   return 0;

@@ -1,0 +1,262 @@
+// Block-cooperative point operations for the latency-bound tail of the MSM (bucket reduction, window tree).
+//
+// Measured on B200 (tools/ubench.cu, profiles/r1_ubench_latency.log): one warp issues an IMAD.WIDE every
+// ~6 cycles whatever its instruction-level parallelism, so a lone warp needs 0.95 us per modular
+// multiplication, 13.2 us per XYZZ addition and 8.4 us per doubling, and the ~45 dependent point operations of
+// the reduction cost > 0.5 ms while most of the chip idles.  Here a block of 4 warps (one per scheduler of an
+// SM) works on 32 chains at once (lane = chain): the independent field products of one point operation are
+// spread over the 4 warps and meet in shared memory, so an addition is 4 multiplication rounds (instead of 14
+// sequential products) and a doubling 3 (instead of 9).
+//
+// Shared-memory slot layout: slot s, limb j, lane l at word (s * NL + j) * 32 + l  (conflict-free).
+// Same formulas and exceptional cases as ec.cuh (xyzz_add / xyzz_dbl); results are bit-identical.
+#pragma once
+#include "msm.cuh"
+
+namespace zk {
+namespace coop {
+
+static constexpr int kWarps = 4;
+static constexpr int kThreads = kWarps * 32;
+
+template <class F> struct Slots {
+  static constexpr int NL = sizeof(F) / 4;
+  uint32_t* base;
+  __device__ __forceinline__ F load(int slot, int lane) const {
+    F r;
+    const uint32_t* p = base + slot * NL * 32 + lane;
+    uint32_t* w = reinterpret_cast<uint32_t*>(&r);
+#pragma unroll
+    for (int j = 0; j < NL; j++) w[j] = p[j * 32];
+    return r;
+  }
+  __device__ __forceinline__ void store(int slot, int lane, const F& v) const {
+    uint32_t* p = base + slot * NL * 32 + lane;
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(&v);
+#pragma unroll
+    for (int j = 0; j < NL; j++) p[j * 32] = w[j];
+  }
+  __device__ __forceinline__ void mul(int dst, int a, int b, int lane) const {
+    F x = load(a, lane), y = load(b, lane), r;
+    fmul(r, x, y);
+    store(dst, lane, r);
+  }
+};
+
+// point = 4 consecutive slots X, Y, ZZ, ZZZ
+enum { PX = 0, PY = 1, PZZ = 2, PZZZ = 3 };
+// temporaries used by add / dbl (relative to the temp base)
+enum { T_U1 = 0, T_U2, T_S1, T_S2, T_P, T_R, T_PP, T_RR, T_ZZ12, T_ZZZ12, T_PPP, T_Q, T_TT, T_VV,
+       T_RX, T_RY, T_RZZ, T_RZZZ, T_DX, T_DY, T_DZZ, T_DZZZ, T_COUNT };
+// flag bytes per lane (in shared memory after the slots)
+struct Flags { uint8_t zero_p[32], zero_r[32]; };
+
+// A = 2 A in place.  Infinity (ZZ = 0) and Y = 0 come out as ZZ = 0 without special handling.
+// (uses temporaries U1, U2, P, R, PP, RR, PPP, Q, TT, VV only -- never the R* / D* result slots of point_add)
+template <class F> __device__ __noinline__ void point_dbl(Slots<F> S, int A, int T) {
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  // round 1: V = (2Y)^2 | XX = X^2
+  if (w == 0) {
+    F y = S.load(A + PY, l), u, v;
+    fdbl(u, y);
+    fmul(v, u, u);
+    S.store(T + T_U1, l, u);    // U
+    S.store(T + T_PP, l, v);    // V
+  } else if (w == 1) {
+    S.mul(T + T_RR, A + PX, A + PX, l);   // XX
+  }
+  __syncthreads();
+  // round 2: W = U V | S = X V | M = 3 XX, MM = M^2 | ZZ' = V ZZ
+  if (w == 0) S.mul(T + T_PPP, T + T_U1, T + T_PP, l);        // W
+  else if (w == 1) S.mul(T + T_Q, A + PX, T + T_PP, l);       // S
+  else if (w == 2) {
+    F xx = S.load(T + T_RR, l), m, mm;
+    fdbl(m, xx);
+    fadd(m, m, xx);
+    fmul(mm, m, m);
+    S.store(T + T_P, l, m);     // M
+    S.store(T + T_R, l, mm);    // MM
+  } else S.mul(A + PZZ, T + T_PP, A + PZZ, l);
+  __syncthreads();
+  // round 3: X3 = MM - 2S, TT = M (S - X3) | WY = W Y | ZZZ' = W ZZZ
+  if (w == 0) {
+    F mm = S.load(T + T_R, l), s = S.load(T + T_Q, l), m = S.load(T + T_P, l), x3, t;
+    fsub(x3, mm, s);
+    fsub(x3, x3, s);
+    fsub(t, s, x3);
+    fmul(t, m, t);
+    S.store(T + T_U2, l, x3);
+    S.store(T + T_TT, l, t);
+  } else if (w == 1) S.mul(T + T_VV, T + T_PPP, A + PY, l);
+  else if (w == 2) S.mul(A + PZZZ, T + T_PPP, A + PZZZ, l);
+  __syncthreads();
+  // round 4: Y3 = TT - WY
+  if (w == 0) {
+    F t = S.load(T + T_TT, l), wy = S.load(T + T_VV, l), y3;
+    fsub(y3, t, wy);
+    S.store(A + PY, l, y3);
+    S.store(A + PX, l, S.load(T + T_U2, l));
+  }
+  __syncthreads();
+}
+
+// A += Q (both XYZZ, complete).  q_masked: this lane's Q counts as infinity (used for the bit-serial scalar mul).
+template <class F> __device__ __noinline__ void point_add(Slots<F> S, Flags* fl, int A, int Q, int T, bool q_masked) {
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  const bool inf_a = fis_zero(S.load(A + PZZ, l));
+  const bool inf_q = q_masked || fis_zero(S.load(Q + PZZ, l));
+  // round 1: U1 = X1 ZZ2 | U2 = X2 ZZ1 | S1 = Y1 ZZZ2 | S2 = Y2 ZZZ1
+  if (w == 0) S.mul(T + T_U1, A + PX, Q + PZZ, l);
+  else if (w == 1) S.mul(T + T_U2, Q + PX, A + PZZ, l);
+  else if (w == 2) S.mul(T + T_S1, A + PY, Q + PZZZ, l);
+  else S.mul(T + T_S2, Q + PY, A + PZZZ, l);
+  __syncthreads();
+  // round 2: P = U2 - U1, PP = P^2 | R = S2 - S1, RR = R^2 | ZZ1 ZZ2 | ZZZ1 ZZZ2
+  if (w == 0) {
+    F u1 = S.load(T + T_U1, l), u2 = S.load(T + T_U2, l), p, pp;
+    fsub(p, u2, u1);
+    fmul(pp, p, p);
+    S.store(T + T_P, l, p);
+    S.store(T + T_PP, l, pp);
+    fl->zero_p[l] = fis_zero(p);
+  } else if (w == 1) {
+    F s1 = S.load(T + T_S1, l), s2 = S.load(T + T_S2, l), r, rr;
+    fsub(r, s2, s1);
+    fmul(rr, r, r);
+    S.store(T + T_R, l, r);
+    S.store(T + T_RR, l, rr);
+    fl->zero_r[l] = fis_zero(r);
+  } else if (w == 2) S.mul(T + T_ZZ12, A + PZZ, Q + PZZ, l);
+  else S.mul(T + T_ZZZ12, A + PZZZ, Q + PZZZ, l);
+  __syncthreads();
+  // round 3: PPP = P PP | Q = U1 PP | ZZ3 = ZZ12 PP
+  if (w == 0) S.mul(T + T_PPP, T + T_P, T + T_PP, l);
+  else if (w == 1) S.mul(T + T_Q, T + T_U1, T + T_PP, l);
+  else if (w == 2) S.mul(T + T_RZZ, T + T_ZZ12, T + T_PP, l);
+  __syncthreads();
+  // round 4: X3 = RR - PPP - 2Q, TT = R (Q - X3) | VV = S1 PPP | ZZZ3 = ZZZ12 PPP
+  if (w == 0) {
+    F rr = S.load(T + T_RR, l), ppp = S.load(T + T_PPP, l), q = S.load(T + T_Q, l), r = S.load(T + T_R, l), x3, t;
+    fsub(x3, rr, ppp);
+    fsub(x3, x3, q);
+    fsub(x3, x3, q);
+    fsub(t, q, x3);
+    fmul(t, r, t);
+    S.store(T + T_RX, l, x3);
+    S.store(T + T_TT, l, t);
+  } else if (w == 1) S.mul(T + T_VV, T + T_S1, T + T_PPP, l);
+  else if (w == 2) S.mul(T + T_RZZZ, T + T_ZZZ12, T + T_PPP, l);
+  __syncthreads();
+  // round 5: Y3 = TT - VV
+  if (w == 0) {
+    F t = S.load(T + T_TT, l), v = S.load(T + T_VV, l), y3;
+    fsub(y3, t, v);
+    S.store(T + T_RY, l, y3);
+  }
+  const bool zero_p = fl->zero_p[l] != 0, zero_r = fl->zero_r[l] != 0;
+  const bool need_dbl = !inf_a && !inf_q && zero_p && zero_r;   // same point: tangent (macros.rs:57-108)
+  if (__syncthreads_or(need_dbl)) {                              // rare; block-uniform branch
+    S.store(T + T_DX + w, l, S.load(A + w, l));                  // warp w copies coordinate w
+    __syncthreads();
+    point_dbl(S, T + T_DX, T);                                   // temporaries U1..VV are free again
+  }
+  // select, warp w handles coordinate w
+  F res;
+  if (inf_q) res = S.load(A + w, l);
+  else if (inf_a) res = S.load(Q + w, l);
+  else if (zero_p) { if (zero_r) res = S.load(T + T_DX + w, l); else fset_zero(res); }   // P + (-P) = infinity
+  else res = S.load(T + T_RX + w, l);
+  __syncthreads();
+  S.store(A + w, l, res);
+  __syncthreads();
+}
+
+template <class F> __device__ __forceinline__ void point_set_inf(const Slots<F>& S, int A) {
+  F z;
+  fset_zero(z);
+  S.store(A + (threadIdx.x >> 5), threadIdx.x & 31, z);
+}
+template <class F> __device__ __forceinline__ void point_copy(const Slots<F>& S, int dst, int src) {
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  S.store(dst + w, l, S.load(src + w, l));
+}
+// warp w moves coordinate w of a global XYZZ point to / from the lane's slot
+template <class F> __device__ __forceinline__ void point_load_global(const Slots<F>& S, int A, const XYZZ<F>* g, bool present) {
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  F v;
+  if (present) v = reinterpret_cast<const F*>(g)[w];
+  else fset_zero(v);
+  S.store(A + w, l, v);
+}
+template <class F> __device__ __forceinline__ void point_store_global(const Slots<F>& S, int A, XYZZ<F>* g) {
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  reinterpret_cast<F*>(g)[w] = S.load(A + w, l);
+}
+
+enum { S_RUN = 0, S_ACC = 4, S_Q = 8, S_BASE = 12, S_TMP = 16, S_TOTAL = S_TMP + T_COUNT };
+
+template <class F> constexpr size_t smem_bytes() { return (size_t)S_TOTAL * (sizeof(F) / 4) * 32 * 4 + sizeof(Flags); }
+
+// 32 chains per block; chain (win, k): out = sum_{i<K} (k K + i + 1) * bucket[win*B + k*K + i]   (as BucketReduce)
+template <class C>
+__global__ void __launch_bounds__(kThreads) bucket_reduce_kernel(MsmPlan p, const uint32_t* offsets,
+                                                                 const XYZZ<typename C::F>* bucket_sums,
+                                                                 XYZZ<typename C::F>* out) {
+  typedef typename C::F F;
+  extern __shared__ __align__(16) uint32_t smem[];
+  Slots<F> S{smem};
+  Flags* fl = reinterpret_cast<Flags*>(smem + (size_t)S_TOTAL * Slots<F>::NL * 32);
+  const int l = threadIdx.x & 31;
+  const uint32_t chunks = p.B / p.K, total = p.nwin * chunks;
+  const uint32_t chain = blockIdx.x * 32 + l;
+  const bool valid = chain < total;
+  const uint32_t win = valid ? chain / chunks : 0, k = valid ? chain % chunks : 0;
+  const size_t base = (size_t)win * p.B + (size_t)k * p.K;
+  point_set_inf(S, S_RUN);
+  point_set_inf(S, S_ACC);
+  __syncthreads();
+  for (int i = (int)p.K - 1; i >= 0; i--) {
+    bool present = valid && offsets[base + i] != offsets[base + i + 1];
+    point_load_global(S, S_Q, bucket_sums + base + i, present);
+    __syncthreads();
+    point_add(S, fl, S_RUN, S_Q, S_TMP, false);
+    point_add(S, fl, S_ACC, S_RUN, S_TMP, false);
+  }
+  // run = (k K) * run, MSB first over the bit length of the largest multiplier (uniform for the grid)
+  const uint32_t s = k * p.K;
+  int nbits = 32 - __clz((chunks - 1) * p.K | 1u);
+  point_copy(S, S_BASE, S_RUN);
+  __syncthreads();
+  point_set_inf(S, S_RUN);
+  __syncthreads();
+  for (int b = nbits - 1; b >= 0; b--) {
+    point_dbl(S, S_RUN, S_TMP);
+    point_add(S, fl, S_RUN, S_BASE, S_TMP, ((s >> b) & 1u) == 0);
+  }
+  point_add(S, fl, S_ACC, S_RUN, S_TMP, false);
+  if (valid) point_store_global(S, S_ACC, out + chain);
+}
+
+// one level of the window tree: row[i] += row[i + half], 32 pairs per block
+template <class C>
+__global__ void __launch_bounds__(kThreads) pair_sum_kernel(uint32_t nwin, uint32_t pitch, uint32_t m, uint32_t half,
+                                                            XYZZ<typename C::F>* arr) {
+  typedef typename C::F F;
+  extern __shared__ __align__(16) uint32_t smem[];
+  Slots<F> S{smem};
+  Flags* fl = reinterpret_cast<Flags*>(smem + (size_t)S_TOTAL * Slots<F>::NL * 32);
+  const int l = threadIdx.x & 31;
+  const uint32_t pair = blockIdx.x * 32 + l;
+  const bool valid = pair < nwin * half;
+  const uint32_t win = valid ? pair / half : 0, i = valid ? pair % half : 0;
+  const bool has_b = valid && i + half < m;
+  XYZZ<F>* row = arr + (size_t)win * pitch;
+  point_load_global(S, S_ACC, row + i, valid);
+  point_load_global(S, S_Q, row + i + half, has_b);
+  __syncthreads();
+  point_add(S, fl, S_ACC, S_Q, S_TMP, false);
+  if (has_b) point_store_global(S, S_ACC, row + i);
+}
+
+}  // namespace coop
+}  // namespace zk

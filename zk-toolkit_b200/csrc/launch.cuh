@@ -9,6 +9,8 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
+#include <type_traits>
 
 namespace zk {
 
@@ -44,6 +46,19 @@ template <class Body> struct Launch : LaunchBase<Body, decltype(Body::run)> {};
 // block-cooperative exclusive scan (tu_sort.cu): offsets[0..n] = scan(hist), hist <- offsets (cursors)
 cudaError_t zk_exclusive_scan(cudaStream_t st, uint32_t n, uint32_t* hist_cursor, uint32_t* offsets, uint32_t* blocksums);
 
+// block-cooperative G1 tail kernels (tu_g1_coop.cu)
+struct MsmPlan;
+struct FqCfg;
+template <class Cfg> struct Mont;
+template <class F> struct XYZZ;
+cudaError_t zk_coop_bucket_reduce_g1(cudaStream_t st, const MsmPlan& p, const uint32_t* offsets,
+                                     const XYZZ<Mont<FqCfg>>* buckets, XYZZ<Mont<FqCfg>>* out);
+cudaError_t zk_coop_pair_sum_g1(cudaStream_t st, uint32_t nwin, uint32_t pitch, uint32_t m, uint32_t half,
+                                XYZZ<Mont<FqCfg>>* arr);
+template <class C> struct BucketReduce;
+template <class C> struct PairSum;
+struct G1;
+
 // optional per-launch timing (zkmsm_profile): CUDA events on the launching stream around every kernel
 struct LaunchProfile {
   static constexpr int MAX = 96;
@@ -74,6 +89,39 @@ struct CudaExec {
     if (slot >= 0) cudaEventRecord(prof->end[slot], st);
     launches++;
     if (e != cudaSuccess) err = e;
+  }
+  // profiling bracket around a non-Body launch
+  template <class Fn> void timed(const char* name, uint32_t threads, int nlaunch, Fn fn) {
+    if (err != cudaSuccess) return;
+    int slot = -1;
+    if (prof && prof->n < LaunchProfile::MAX) {
+      slot = prof->n++;
+      prof->names[slot] = name;
+      prof->threads[slot] = threads;
+      cudaEventRecord(prof->beg[slot], st);
+    }
+    cudaError_t e = fn();
+    if (slot >= 0) cudaEventRecord(prof->end[slot], st);
+    launches += nlaunch;
+    if (e != cudaSuccess) err = e;
+  }
+  // stages 6 / 7 of the MSM: cooperative kernels for G1, per-thread bodies otherwise
+  template <class C, class P, class Pt>
+  void bucket_reduce(const P& p, const uint32_t* offsets, const Pt* buckets, Pt* out) {
+    uint32_t chains = p.nwin * (p.B / p.K);
+    if (chains == 0) return;
+    if (std::is_same<C, G1>::value && p.coop)
+      timed("bucket_reduce", chains, 1, [&] { return zk_coop_bucket_reduce_g1(st, p, offsets, (const XYZZ<Mont<FqCfg>>*)buckets, (XYZZ<Mont<FqCfg>>*)out); });
+    else
+      launch<BucketReduce<C>>(chains, p, offsets, buckets, out);
+  }
+  template <class C, class Pt>
+  void pair_sum(uint32_t nwin, uint32_t pitch, uint32_t m, uint32_t half, Pt* arr) {
+    if (nwin * half == 0) return;
+    if (std::is_same<C, G1>::value && nwin * half <= 16384 && !getenv("ZKMSM_NO_COOP"))   // wide levels: per-thread
+      timed("pair_sum", nwin * half, 1, [&] { return zk_coop_pair_sum_g1(st, nwin, pitch, m, half, (XYZZ<Mont<FqCfg>>*)arr); });
+    else
+      launch<PairSum<C>>(nwin * half, nwin, pitch, m, half, arr);
   }
   void exclusive_scan(uint32_t n, uint32_t* hist_cursor, uint32_t* offsets, uint32_t* blocksums) {
     if (err != cudaSuccess) return;

@@ -66,6 +66,7 @@ struct MsmPlan {
   uint32_t K;          // buckets per reduce thread (power of two, divides B)
   uint32_t max_entries;   // n * W
   uint32_t acc_threads;   // ceil(max_entries / L)
+  uint32_t coop;          // 1: stages 6/7 run as block-cooperative kernels (coop.cuh), K sized for ~one block per SM
   uint32_t half;          // 1: point set is in the prime-order subgroup; scalars s > (r-1)/2 become r - s with
                           //    the point negated, so 254 bits are recoded and no carry-only top window exists
 };
@@ -194,8 +195,10 @@ struct Scatter {
 
 // ---------------------------------------------------------------- bucket accumulation
 static constexpr uint32_t NO_KEY = 0xffffffffu;
-// partials folded per fix-up thread (4-ary tree: short serial chains; upper levels are usually empty)
-inline uint32_t fix_fan(uint32_t level) { (void)level; return 4u; }
+// partials folded per fix-up thread.  Level 0 is wide and throughput-bound (fan 4); the next two levels still carry
+// work for ordinary buckets and are latency-bound at ~13 us per addition (fan 2); above that only giant buckets
+// (skewed scalars) have anything left, so the tree closes quickly (fan 16).
+inline uint32_t fix_fan(uint32_t level) { return level == 0 ? 4u : (level <= 2 ? 2u : 16u); }
 
 template <class C> struct Accumulate {
   typedef typename C::F F;
@@ -507,7 +510,7 @@ inline uint32_t msm_pick_c(uint32_t n, bool precomp, bool half = false) {
   return best;
 }
 
-inline MsmPlan msm_plan(uint32_t n, uint32_t c, bool precomp, uint32_t stride, bool half = false) {
+inline MsmPlan msm_plan(uint32_t n, uint32_t c, bool precomp, uint32_t stride, bool half = false, bool coop_tail = false) {
   MsmPlan p;
   p.n = n;
   p.c = c;
@@ -520,9 +523,17 @@ inline MsmPlan msm_plan(uint32_t n, uint32_t c, bool precomp, uint32_t stride, b
   p.stride = stride;
   p.max_entries = n * p.W;
   p.L = p.max_entries >= (1u << 23) ? 32 : (p.max_entries >= (1u << 21) ? 16 : 8);
-  p.K = 2;                                   // ~16k reduce threads: short chains while the chip stays busy
+  p.K = 2;                                   // per-thread reduction: ~16k threads, short chains, chip busy
   while (p.K < 64 && p.B / p.K > 16384) p.K *= 2;
   if (p.K > p.B) p.K = p.B;
+  p.coop = 0;
+  if (coop_tail) {
+    // cooperative reduction: 32 chains per 4-warp block, aim at <= ~one block per SM (148 x 32 = 4736 chains) so
+    // every chain runs at single-block latency; give up (per-thread kernel) when that needs K > 32
+    uint32_t k = 2;
+    while (k < 32 && (uint64_t)p.nwin * (p.B / k) > 4736) k *= 2;
+    if (k <= p.B && (uint64_t)p.nwin * (p.B / k) <= 2 * 4736) { p.K = k; p.coop = 1; }
+  }
   if (const char* e = getenv("ZKMSM_L")) { uint32_t v = (uint32_t)atoi(e); if (v >= 1 && v <= 4096) p.L = v; }   // tuning overrides
   if (const char* e = getenv("ZKMSM_K")) { uint32_t v = (uint32_t)atoi(e); if (v >= 1 && v <= p.B && (v & (v - 1)) == 0) p.K = v; }
   p.acc_threads = (p.max_entries + p.L - 1) / p.L;
@@ -579,12 +590,13 @@ void msm_launch(Exec& ex, const MsmPlan& p, const MsmBuffers<C>& b, const Affine
     }
   }
   uint32_t chunks = p.B / p.K;
-  ex.template launch<BucketReduce<C>>(p.nwin * chunks, p, (const uint32_t*)b.offsets,
-                                      (const XYZZ<typename C::F>*)b.bucket_sums, b.reduced);
+  // stages 6 and 7 go through the Exec policy: the CUDA build has block-cooperative versions (coop.cuh), the CPU
+  // emulation runs the per-thread bodies BucketReduce / PairSum; both give the same points
+  ex.template bucket_reduce<C>(p, (const uint32_t*)b.offsets, (const XYZZ<typename C::F>*)b.bucket_sums, b.reduced);
   uint32_t m = chunks;
   while (m > 1) {
     uint32_t half = (m + 1) / 2;
-    ex.template launch<PairSum<C>>(p.nwin * half, p.nwin, chunks, m, half, b.reduced);
+    ex.template pair_sum<C>(p.nwin, chunks, m, half, b.reduced);
     m = half;
   }
   ex.template launch<Finish<C>>(1u, p.nwin, chunks, p.c, (const XYZZ<typename C::F>*)b.reduced, out_xyzz, out_affine,

@@ -319,7 +319,7 @@ static int msm_enqueue_impl(zkmsm_ctx* ctx, const zkmsm_points* ps, const uint32
     return ZKMSM_OK;
   }
   unsigned c = ps->precomp ? ps->c : (ctx->window_override ? ctx->window_override : msm_pick_c((uint32_t)n, false, ps->half));
-  MsmPlan p = msm_plan((uint32_t)n, c, ps->precomp, (uint32_t)ps->n, ps->half);
+  MsmPlan p = msm_plan((uint32_t)n, c, ps->precomp, (uint32_t)ps->n, ps->half, curve == 1 && !getenv("ZKMSM_NO_COOP"));
   int rc;
   uint32_t nseg = (p.nb + SCAN_SEG - 1) / SCAN_SEG + 1;
   if ((rc = ws_reserve(ctx, WS_HIST, sizeof(uint32_t) * p.nb)) || (rc = ws_reserve(ctx, WS_OFFSETS, sizeof(uint32_t) * (p.nb + 1))) ||
