@@ -155,6 +155,13 @@ int zkmsm_g1_points_from_scalars(zkmsm_ctx* ctx, const uint32_t base_xy[24], con
 int zkmsm_g2_points_from_scalars(zkmsm_ctx* ctx, const uint32_t base_xy[48], const uint32_t* scalars, size_t n,
                                  unsigned flags, zkmsm_points** out);
 
+/* ---- witness aggregation in Fr (the step in front of the MSMs): out[j] = sum_i wires[i] * polys[i][j] mod r,
+ * i.e. the per-wire loop of Prover::prove (groth16/zktoolkit_based/prover.rs:108-117) / QAP::build_p's
+ * `v += &self.vi[i] * wit` (qap/qap.rs:99-109) collapsed into one coefficient vector.  polys: n_wires x n
+ * elements (8 words each, canonical, row i = wire i, zero padded), wires: n_wires elements, out: n elements. */
+int zkmsm_fr_aggregate(zkmsm_ctx* ctx, const uint32_t* polys, size_t n_wires, size_t n, const uint32_t* wires,
+                       uint32_t* out);
+
 /* ---- diagnostics: integer-multiply throughput of this device (roofline denominator).
  * variant 0: independent mad.wide.u32; 1: carry-chained IMAD.WIDE.U32.X (mad.lo.cc/madc.hi.cc
  * pairs); 2: 32-bit IMAD (half a limb product each); 3: as 1 with data-dependent multipliers (the

@@ -7,6 +7,7 @@
 #include <cstring>
 #include <vector>
 #include "../../zk-toolkit_b200/csrc/msm.cuh"
+#include "../../zk-toolkit_b200/csrc/fr_ops.cuh"
 
 using namespace zk;
 
@@ -112,6 +113,13 @@ int emu_g1_mul_base(const uint32_t* base_xy, const uint32_t* scalars, uint32_t n
   ex.launch<BaseTableAffine<G1>>(256u, (const XYZZ<Fp>*)chain.data(), table.data());
   ex.launch<FixedBaseMul<G1>>(n, n, scalars, (const Affine<Fp>*)table.data(), out.data());
   ex.launch<StorePoints<G1>>(n, n, (const Affine<Fp>*)out.data(), out_xy, out_inf);
+  return 0;
+}
+int emu_fr_aggregate(const uint32_t* polys, uint32_t n_wires, uint32_t n, const uint32_t* wires, uint32_t* out) {
+  HostExec ex;
+  std::vector<Fr> wm(n_wires + 1);
+  ex.launch<FrToMont>(n_wires, n_wires, wires, wm.data());
+  ex.launch<FrAggregate>(n, n_wires, n, (const Fr*)wm.data(), polys, out);
   return 0;
 }
 void emu_plan(uint32_t n, uint32_t c, int precomp, uint32_t* out) {

@@ -79,3 +79,16 @@ def test_synthetic_instance_closed_form_and_verifier(z):
     assert O.verify(got, crs, inst["stmt_wires"])
     bad = (got[0], got[1], O.affine_add(got[2], O.G1_GEN))
     assert not O.verify(bad, crs, inst["stmt_wires"])
+
+
+def test_fr_aggregate_matches_python(z):
+    import numpy as np
+    ctx = z.default_context()
+    rnd = random.Random(3)
+    for n_wires, n in ((1, 1), (7, 5), (200, 1000)):
+        polys = [[rnd.randrange(O.R) for _ in range(n)] for _ in range(n_wires)]
+        wires = [rnd.randrange(O.R) for _ in range(n_wires)]
+        mat = np.stack([z.scalars_to_array(p) for p in polys])
+        out = ctx.fr_aggregate(mat, z.scalars_to_array(wires))
+        exp = [sum(a * p[j] for a, p in zip(wires, polys)) % O.R for j in range(n)]
+        assert [sum(int(w) << (32 * k) for k, w in enumerate(r)) for r in out] == exp

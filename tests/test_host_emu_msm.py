@@ -160,3 +160,32 @@ def test_emu_g2_msm(lib):
         assert rc == 0
         assert got == U.expected_from_dlogs(O.G2_GEN, dlogs, sc)
     assert emu_g2(lib, pts[:3], [4, 5, 6])[1] == O.msm(pts[:3], [4, 5, 6])
+
+
+def test_emu_fr_aggregate(lib):
+    """witness aggregation sum_i a_i * poly_i (prover.rs:108-117 / qap.rs:99-109) vs Python integers and the oracle"""
+    rnd = random.Random(21)
+    for n_wires, n in ((1, 1), (7, 5), (33, 40)):
+        polys = [[rnd.randrange(O.R) for _ in range(n)] for _ in range(n_wires)]
+        polys[0][0] = O.R - 1
+        wires = [rnd.randrange(O.R) for _ in range(n_wires)]
+        wires[-1] = O.R - 1
+        mat = np.stack([U.scalars_to_array(p) for p in polys])
+        w = U.scalars_to_array(wires)
+        out = np.zeros((n, 8), dtype=np.uint32)
+        assert lib.emu_fr_aggregate(ptr(mat), n_wires, n, ptr(w), ptr(out)) == 0
+        exp = [sum(a * p[j] for a, p in zip(wires, polys)) % O.R for j in range(n)]
+        assert [U.limbs_to_int(r) for r in out] == exp
+    # the reference circuit: aggregated u equals the oracle's sum of scaled per-wire polynomials
+    op = O.Prover(**O.CONFIG1)
+    acc = O.Polynomial.zero()
+    for p, a in zip(op.ui, op.wires):
+        acc = acc.plus(p.scale(a))
+    n = max(len(p) for p in op.ui)
+    mat = np.zeros((len(op.ui), n, 8), dtype=np.uint32)
+    for i, p in enumerate(op.ui):
+        mat[i, :len(p)] = U.scalars_to_array(p.coeffs)
+    out = np.zeros((n, 8), dtype=np.uint32)
+    lib.emu_fr_aggregate(ptr(mat), len(op.ui), n, ptr(U.scalars_to_array(op.wires)), ptr(out))
+    got = [U.limbs_to_int(r) for r in out]
+    assert got[:len(acc.coeffs)] == acc.coeffs and not any(got[len(acc.coeffs):])

@@ -235,6 +235,16 @@ class Context:
                                                      ctypes.byref(inf)))
         return out, bool(inf.value)
 
+    def fr_aggregate(self, polys, wires):
+        """out[j] = sum_i wires[i] * polys[i][j] mod r; polys (n_wires, n, 8) uint32, wires (n_wires, 8) -> (n, 8)"""
+        polys = L.as_u32(polys, 8)
+        wires = L.as_u32(wires, 8).reshape(-1, 8)
+        n_wires, n = polys.shape[0], polys.shape[1]
+        assert polys.ndim == 3 and wires.shape[0] == n_wires
+        out = np.zeros((n, 8), dtype=np.uint32)
+        self._check(self.lib.zkmsm_fr_aggregate(self.h, L.dptr(polys), n_wires, n, L.dptr(wires), L.dptr(out)))
+        return out
+
     def bench_imad(self, variant, iters=4096):
         lp, ms = ctypes.c_double(0), ctypes.c_double(0)
         self._check(self.lib.zkmsm_bench_imad(self.h, variant, iters, ctypes.byref(lp), ctypes.byref(ms)))

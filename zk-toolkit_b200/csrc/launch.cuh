@@ -55,9 +55,14 @@ cudaError_t zk_coop_bucket_reduce_g1(cudaStream_t st, const MsmPlan& p, const ui
                                      const XYZZ<Mont<FqCfg>>* buckets, XYZZ<Mont<FqCfg>>* out);
 cudaError_t zk_coop_pair_sum_g1(cudaStream_t st, uint32_t nwin, uint32_t pitch, uint32_t m, uint32_t half,
                                 XYZZ<Mont<FqCfg>>* arr);
+struct Fp2;
+cudaError_t zk_coop_bucket_reduce_g2(cudaStream_t st, const MsmPlan& p, const uint32_t* offsets, const XYZZ<Fp2>* buckets,
+                                     XYZZ<Fp2>* out);
+cudaError_t zk_coop_pair_sum_g2(cudaStream_t st, uint32_t nwin, uint32_t pitch, uint32_t m, uint32_t half, XYZZ<Fp2>* arr);
 template <class C> struct BucketReduce;
 template <class C> struct PairSum;
 struct G1;
+struct G2;
 
 // optional per-launch timing (zkmsm_profile): CUDA events on the launching stream around every kernel
 struct LaunchProfile {
@@ -112,6 +117,8 @@ struct CudaExec {
     if (chains == 0) return;
     if (std::is_same<C, G1>::value && p.coop)
       timed("bucket_reduce", chains, 1, [&] { return zk_coop_bucket_reduce_g1(st, p, offsets, (const XYZZ<Mont<FqCfg>>*)buckets, (XYZZ<Mont<FqCfg>>*)out); });
+    else if (std::is_same<C, G2>::value && p.coop)
+      timed("bucket_reduce", chains, 1, [&] { return zk_coop_bucket_reduce_g2(st, p, offsets, (const XYZZ<Fp2>*)buckets, (XYZZ<Fp2>*)out); });
     else
       launch<BucketReduce<C>>(chains, p, offsets, buckets, out);
   }
@@ -120,6 +127,8 @@ struct CudaExec {
     if (nwin * half == 0) return;
     if (std::is_same<C, G1>::value && nwin * half <= 16384 && !getenv("ZKMSM_NO_COOP"))   // wide levels: per-thread
       timed("pair_sum", nwin * half, 1, [&] { return zk_coop_pair_sum_g1(st, nwin, pitch, m, half, (XYZZ<Mont<FqCfg>>*)arr); });
+    else if (std::is_same<C, G2>::value && nwin * half <= 16384 && !getenv("ZKMSM_NO_COOP"))
+      timed("pair_sum", nwin * half, 1, [&] { return zk_coop_pair_sum_g2(st, nwin, pitch, m, half, (XYZZ<Fp2>*)arr); });
     else
       launch<PairSum<C>>(nwin * half, nwin, pitch, m, half, arr);
   }

@@ -11,6 +11,7 @@
 #include "../../include/zkmsm.h"
 #include "launch.cuh"
 #include "msm.cuh"
+#include "fr_ops.cuh"
 
 using namespace zk;
 
@@ -319,7 +320,7 @@ static int msm_enqueue_impl(zkmsm_ctx* ctx, const zkmsm_points* ps, const uint32
     return ZKMSM_OK;
   }
   unsigned c = ps->precomp ? ps->c : (ctx->window_override ? ctx->window_override : msm_pick_c((uint32_t)n, false, ps->half));
-  MsmPlan p = msm_plan((uint32_t)n, c, ps->precomp, (uint32_t)ps->n, ps->half, curve == 1 && !getenv("ZKMSM_NO_COOP"));
+  MsmPlan p = msm_plan((uint32_t)n, c, ps->precomp, (uint32_t)ps->n, ps->half, !getenv("ZKMSM_NO_COOP"));
   int rc;
   uint32_t nseg = (p.nb + SCAN_SEG - 1) / SCAN_SEG + 1;
   if ((rc = ws_reserve(ctx, WS_HIST, sizeof(uint32_t) * p.nb)) || (rc = ws_reserve(ctx, WS_OFFSETS, sizeof(uint32_t) * (p.nb + 1))) ||
@@ -588,6 +589,35 @@ extern "C" int zkmsm_g1_mul_base(zkmsm_ctx* ctx, const uint32_t* base, const uin
 }
 extern "C" int zkmsm_g2_mul_base(zkmsm_ctx* ctx, const uint32_t* base, const uint32_t* s, size_t n, uint32_t* out, uint8_t* inf) {
   return mul_base_impl<G2>(ctx, base, s, n, 2, out, inf);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fr witness aggregation
+extern "C" int zkmsm_fr_aggregate(zkmsm_ctx* ctx, const uint32_t* polys, size_t n_wires, size_t n, const uint32_t* wires,
+                                  uint32_t* out) {
+  if (!ctx || !out || (n_wires && n && (!polys || !wires)) || n > (1u << 28) || n_wires > (1u << 28))
+    return fail(ctx, ZKMSM_ERR_INVALID_ARG, "bad argument");
+  if (n == 0) return ZKMSM_OK;
+  CU(ctx, cudaSetDevice(ctx->device));
+  size_t mat = sizeof(uint32_t) * 8 * n_wires * n, wb = sizeof(uint32_t) * 8 * n_wires, ob = sizeof(uint32_t) * 8 * n;
+  int rc;
+  if ((rc = ws_reserve(ctx, WS_ENTRIES, mat + 256)) || (rc = ws_reserve(ctx, WS_MISC, 2 * wb + ob + 256))) return rc;
+  uint32_t* d_polys = (uint32_t*)ctx->ws[WS_ENTRIES];
+  char* misc = (char*)ctx->ws[WS_MISC];
+  uint32_t* d_wires = (uint32_t*)misc;
+  Fr* d_wires_mont = (Fr*)(misc + ((wb + 255) / 256) * 256);
+  uint32_t* d_out = (uint32_t*)(misc + 2 * ((wb + 255) / 256) * 256);
+  if (n_wires) {
+    CU(ctx, cudaMemcpyAsync(d_polys, polys, mat, cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(d_wires, wires, wb, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  CudaExec ex(ctx->stream);
+  ex.template launch<FrToMont>((uint32_t)n_wires, (uint32_t)n_wires, (const uint32_t*)d_wires, d_wires_mont);
+  ex.template launch<FrAggregate>((uint32_t)n, (uint32_t)n_wires, (uint32_t)n, (const Fr*)d_wires_mont, (const uint32_t*)d_polys, d_out);
+  if (ex.err != cudaSuccess) return fail(ctx, ZKMSM_ERR_CUDA, "fr_aggregate: %s", cudaGetErrorString(ex.err));
+  CU(ctx, cudaMemcpyAsync(out, d_out, ob, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  return ZKMSM_OK;
 }
 
 // ------------------------------------------------------------------------------------------------

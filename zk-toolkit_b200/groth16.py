@@ -73,17 +73,16 @@ class DeviceCRS:
         return self
 
 
-def aggregate(polys, wires):
-    """sum_i a_i * poly_i as a coefficient list mod r (Prover's per-wire loop, prover.rs:108-117, made one vector)."""
+def aggregate(polys, wires, ctx=None):
+    """sum_i a_i * poly_i as a coefficient list mod r (Prover's per-wire loop, prover.rs:108-117, made one
+    vector) -- computed on the device by zkmsm_fr_aggregate (Montgomery Fr kernel)."""
+    ctx = ctx or default_context()
     n = max(len(p) for p in polys)
-    out = [0] * n
-    for p, a in zip(polys, wires):
-        a = int(a) % R
-        if a == 0:
-            continue
-        for j, c in enumerate(p):
-            out[j] = (out[j] + a * int(c)) % R
-    return out
+    mat = np.zeros((len(polys), n, 8), dtype=np.uint32)
+    for i, p in enumerate(polys):
+        mat[i, :len(p)] = scalars_to_array([int(c) % R for c in p])
+    out = ctx.fr_aggregate(mat, scalars_to_array([int(a) % R for a in wires]))
+    return [sum(int(w) << (32 * k) for k, w in enumerate(row)) for row in out]
 
 
 def _pad(v, n):
