@@ -1,5 +1,6 @@
-// G2 Horner / affine conversion / partial combination (field arithmetic inlined)
+// G2 Horner / affine conversion / partial combination (per-thread fallbacks; the cooperative kernels of coop.cuh do the work)
 #define ZK_DEFINE_LAUNCH
+#define ZK_FMUL_NOINLINE   // fallback / single-thread kernels: field multiplication as a call keeps the build short
 #include "launch.cuh"
 #include "msm.cuh"
 ZK_INSTANTIATE_KERNEL(zk::Finish<zk::G2>);
