@@ -24,12 +24,14 @@ if os.path.exists(lst):
         a[1] += float(r[14]) / 1e6
     total = sum(v[1] for v in agg.values())
     with open(os.path.join(out_dir, f"{tag}_ncu_launch_list_summary.txt"), "w") as f:
-        f.write(f"# ncu --metrics gpu__time_duration.sum --clock-control none -c 700 python bench.py --steps 2 --warmup 3 --skip-cpu-baseline\n")
+        f.write(f"# ncu --metrics gpu__time_duration.sum --clock-control none -c 900 python bench.py --steps 2 --warmup 3 --skip-cpu-baseline\n")
         f.write(f"# {len(rows)} launches, {total:.2f} ms summed (cold-cache, serialised: compare SHARES, not absolutes)\n")
         f.write(f"{'kernel':34s} {'launches':>8s} {'ms':>10s} {'share':>7s}\n")
         for k, (c, ms) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             f.write(f"{k:34s} {c:8d} {ms:10.3f} {100 * ms / total:6.1f}%\n")
-        msm = {k: v for k, v in agg.items() if k.split("<")[0] in ("RecodeCount", "Scatter", "Accumulate", "FixupLevel", "BucketReduce", "PairSum", "Finish", "scan_block_sums", "scan_top_level", "scan_apply")}
+        names = ("RecodeCount", "Scatter", "Accumulate", "FixupLevel", "BucketReduce", "PairSum", "Finish", "scan_block_sums",
+                 "scan_top_level", "scan_apply", "bucket_reduce_kernel", "pair_sum_kernel")
+        msm = {k: v for k, v in agg.items() if any(nm in k for nm in names)}
         t2 = sum(v[1] for v in msm.values())
         f.write(f"\n# MSM pipeline kernels only ({t2:.2f} ms): share of one MSM step\n")
         for k, (c, ms) in sorted(msm.items(), key=lambda kv: -kv[1][1]):

@@ -1,4 +1,4 @@
-// G2 Horner / affine conversion / partial combination (per-thread fallbacks; the cooperative kernels of coop.cuh do the work)
+// G2 Horner / affine conversion / partial combination: single-thread finishing kernels
 #define ZK_DEFINE_LAUNCH
 #define ZK_FMUL_NOINLINE   // fallback / single-thread kernels: field multiplication as a call keeps the build short
 #include "launch.cuh"
