@@ -236,3 +236,50 @@ def test_enqueue_result_split_and_launch_count(z, ctx):
     assert ctx.last_launch_count() >= 8
     out, inf = ctx.msm_result(1)
     assert U.g1_from_array(out, inf) == U.expected_from_dlogs(O.G1_GEN, dlogs, sc)
+
+
+def test_g2_edge_cases(z, ctx):
+    """Appendix B cases for G2: zero scalars, duplicates (tangent inside a bucket), P / -P, AtInfinity inputs"""
+    h = z.G2Point.g()
+    P = [h * k for k in (3, 5, 7)]
+    OP = [O.scalar_mul(O.G2_GEN, k) for k in (3, 5, 7)]
+
+    def run(points, scalars, **kw):
+        out, inf = ctx.msm(z.G2Points(points, **kw).set, z.scalars_to_array(scalars))
+        return U.g2_from_array(out, inf)
+
+    assert run(P, [0, 0, 0]) is O.INF
+    assert run([P[0]] * 5, [2] * 5) == O.scalar_mul(OP[0], 10)
+    assert run([P[0], -P[0], P[1]], [9, 9, 4]) == O.scalar_mul(OP[1], 4)
+    assert run([P[0], z.G2Point.zero(), P[2]], [1, 5, O.R - 1]) == O.msm([OP[0], O.INF, OP[2]], [1, 5, O.R - 1])
+    half = (O.R - 1) // 2
+    for pre in (False, True):
+        assert run(P, [half, half + 1, O.R - 1], precompute=pre, in_subgroup=True) == O.msm(OP, [half, half + 1, O.R - 1])
+    out, inf = ctx.msm(z.G2Points(P).set, z.scalars_to_array([]))
+    assert inf
+
+
+def test_begin_result_and_points_info(z, ctx):
+    rnd = random.Random(8)
+    n = 2000
+    dlogs = [rnd.randrange(1, O.R) for _ in range(n)]
+    sc = U.rand_scalars(rnd, n)
+    exp = U.expected_from_dlogs(O.G1_GEN, dlogs, sc)
+    pts = z.G1Points.generator_multiples(dlogs, precompute=True)
+    info = pts.set.info()
+    assert info["precomputed"] and info["subgroup"] and info["windows"] == 254 // info["c"] + 1
+    plain = z.G1Points.generator_multiples(dlogs, in_subgroup=False)
+    assert plain.set.info() == {"c": 0, "windows": 0, "precomputed": False, "subgroup": False}
+    arr = ctx.pinned_array((n, 8))
+    arr[:] = z.scalars_to_array(sc)
+    other = z.Context(0)                       # a second context (stream + workspace) on the same device
+    ctx.msm_begin(pts.set, arr)
+    other.msm_begin(plain.set, arr)
+    a = ctx.msm_result(1)
+    b = other.msm_result(1)
+    assert U.g1_from_array(*a) == exp == U.g1_from_array(*b)
+    ctx.profile(True)
+    ctx.msm(pts.set, arr)
+    names = [nm for nm, _, _ in ctx.profile_read()]
+    ctx.profile(False)
+    assert "accumulate" in names and "bucket_reduce" in names and "finish" in names
