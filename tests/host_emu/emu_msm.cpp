@@ -58,7 +58,14 @@ static int emu_msm(const uint32_t* xy, const uint8_t* inf, const uint32_t* scala
   // poison what the pipeline must overwrite before reading
   memset(buckets.data(), 0xAB, sizeof(XYZZ<F>) * buckets.size());
   memset(partials.data(), 0xCD, sizeof(XYZZ<F>) * partials.size());
+  const size_t pre_n = (size_t)(p.max_entries + 1) / 2 + p.nb + 1;
+  std::vector<Affine<F>> pre_a(p.batch_rounds ? pre_n : 1), pre_b(p.batch_rounds ? pre_n : 1);
+  std::vector<F> pre_prefix(p.batch_rounds ? pre_n : 1);
+  std::vector<uint32_t> pre_off_a(p.nb + 1), pre_off_b(p.nb + 1), pre_cnt(p.nb + 1);
+  std::vector<Entry> pre_entries(p.batch_rounds ? pre_n : 1);
   MsmBuffers<C> b;
+  b.pre_pts[0] = pre_a.data(); b.pre_pts[1] = pre_b.data(); b.pre_prefix = pre_prefix.data();
+  b.pre_off[0] = pre_off_a.data(); b.pre_off[1] = pre_off_b.data(); b.pre_cnt = pre_cnt.data(); b.pre_entries = pre_entries.data();
   b.hist_cursor = hist.data(); b.offsets = offsets.data(); b.segsum = segsum.data(); b.entries = entries.data();
   b.bucket_sums = buckets.data(); b.partials = partials.data(); b.reduced = reduced.data(); b.err = err.data(); b.partial_keys = pkeys.data();
   XYZZ<F> xyzz;

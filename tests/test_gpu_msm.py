@@ -283,3 +283,24 @@ def test_begin_result_and_points_info(z, ctx):
     names = [nm for nm, _, _ in ctx.profile_read()]
     ctx.profile(False)
     assert "accumulate" in names and "bucket_reduce" in names and "finish" in names
+
+
+def test_batched_affine_prereduction_option(z, ctx, monkeypatch):
+    """ZKMSM_BATCH_ROUNDS > 0 (experimental stage, off by default): identical results"""
+    n = 6000
+    rnd = random.Random(31)
+    dlogs = [rnd.randrange(1, O.R) for _ in range(n)]
+    sc = U.rand_scalars(rnd, n)
+    exp = U.expected_from_dlogs(O.G1_GEN, dlogs, sc)
+    for pre in (False, True):
+        pts = z.G1Points.generator_multiples(dlogs, precompute=pre)
+        for rounds in (1, 3):
+            monkeypatch.setenv("ZKMSM_BATCH_ROUNDS", str(rounds))
+            out, inf = ctx.msm(pts.set, z.scalars_to_array(sc))
+            assert U.g1_from_array(out, inf) == exp
+        monkeypatch.delenv("ZKMSM_BATCH_ROUNDS")
+    monkeypatch.setenv("ZKMSM_BATCH_ROUNDS", "2")
+    g = z.G1Point.g()
+    dup = z.G1Points([g * 7] * 40)
+    out, inf = ctx.msm(dup.set, z.scalars_to_array([5] * 40))
+    assert U.g1_from_array(out, inf) == O.scalar_mul(O.G1_GEN, 7 * 5 * 40)

@@ -189,3 +189,23 @@ def test_emu_fr_aggregate(lib):
     lib.emu_fr_aggregate(ptr(mat), len(op.ui), n, ptr(U.scalars_to_array(op.wires)), ptr(out))
     got = [U.limbs_to_int(r) for r in out]
     assert got[:len(acc.coeffs)] == acc.coeffs and not any(got[len(acc.coeffs):])
+
+
+@pytest.mark.parametrize("rounds,T", [(1, 5), (2, 3), (3, 64)])
+def test_emu_batched_affine_prereduction(lib, g1_set, rounds, T, monkeypatch):
+    """optional stage (ZKMSM_BATCH_ROUNDS): pairwise affine additions sharing one inversion per T additions
+    (Montgomery's trick) before the XYZZ accumulation -- same result, including every exceptional case"""
+    monkeypatch.setenv("ZKMSM_BATCH_ROUNDS", str(rounds))
+    monkeypatch.setenv("ZKMSM_BATCH_T", str(T))
+    dlogs, pts = g1_set
+    rnd = random.Random(rounds * 7 + T)
+    sc = U.rand_scalars(rnd, len(pts))
+    exp = U.expected_from_dlogs(O.G1_GEN, dlogs, sc)
+    for c, pre in ((0, 0), (5, 1), (4, 3), (9, 2)):
+        assert emu_g1(lib, pts, sc, c=c, precomp=pre) == (0, exp)
+    P = pts[:6]
+    assert emu_g1(lib, [P[0]] * 9, [3] * 9, c=5) == (0, O.scalar_mul(P[0], 27))                 # P + P: tangent
+    assert emu_g1(lib, [P[0], O.point_neg(P[0]), P[1], O.point_neg(P[1])], [9, 9, 11, 11], c=4) == (0, O.INF)
+    withinf = [P[0], O.INF, P[1], O.INF, P[2]]
+    assert emu_g1(lib, withinf, [5, 6, 7, 8, 9], c=4) == (0, O.msm(withinf, [5, 6, 7, 8, 9]))
+    assert emu_g1(lib, P, [0] * 6) == (0, O.INF)

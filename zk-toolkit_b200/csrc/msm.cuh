@@ -66,6 +66,8 @@ struct MsmPlan {
   uint32_t K;          // buckets per reduce thread (power of two, divides B)
   uint32_t max_entries;   // n * W
   uint32_t acc_threads;   // ceil(max_entries / L)
+  uint32_t batch_rounds;  // > 0: that many rounds of pairwise batched-affine additions before the XYZZ accumulation
+  uint32_t batch_T;       //      additions per thread and inversion in those rounds
   uint32_t coop;          // 1: stages 6/7 run as block-cooperative kernels (coop.cuh), K sized for ~one block per SM
   uint32_t half;          // 1: point set is in the prime-order subgroup; scalars s > (r-1)/2 become r - s with
                           //    the point negated, so 254 bits are recoded and no carry-only top window exists
@@ -290,6 +292,105 @@ template <class C> struct FixupLevel {
       else { parts_out[tid] = acc; out_key = key; }
     }
     keys_out[tid] = out_key;
+  }
+};
+
+// ---------------------------------------------------------------- batched-affine pre-reduction (optional)
+// Round r halves every bucket: neighbours (2j, 2j+1) of a bucket are added in AFFINE coordinates,
+//   lambda = (y2 - y1) / (x2 - x1),  x3 = lambda^2 - x1 - x2,  y3 = lambda (x1 - x3) - y1      (macros.rs:109-152)
+// which is what the reference does per addition -- but the inversions of T independent additions are shared by
+// Montgomery's trick: prefix products of the denominators on the way forward, ONE inversion, and two
+// multiplications per addition on the way back.  6 field multiplications per addition instead of the 10 of an
+// XYZZ mixed add; the single inversion (binary Euclid, shift/subtract only) stays off the multiplier pipe.
+// Every exceptional case keeps the reference semantics: AtInfinity operands and odd leftovers are copied,
+// P + P takes the tangent (denominator 2y, macros.rs:57-108), P + (-P) gives AtInfinity (macros.rs:53-56);
+// those use the denominator 1 so that the shared product never vanishes.
+struct PairCount {   // cnt[b] = ceil(size_b / 2)
+  static const char* name() { return "pair_count"; }
+  static ZK_HD void run(uint32_t tid, uint32_t nb, const uint32_t* off_in, uint32_t* cnt) {
+    if (tid >= nb) return;
+    cnt[tid] = (off_in[tid + 1] - off_in[tid] + 1) / 2;
+  }
+};
+
+template <class C, bool FIRST> struct BatchedAddRound {
+  typedef typename C::F F;
+  static const char* name() { return FIRST ? "batched_add_first" : "batched_add"; }
+
+  // operands of output o (bucket b): items i1 = off_in[b] + 2j and i1 + 1 (if it exists)
+  struct Ops { Affine<F> p1, p2; int kind; F d; };   // kind 0 add, 1 double, 2 copy p1, 3 copy p2, 4 infinity
+  static ZK_HD Affine<F> item(uint32_t i, const Entry* entries, const Affine<F>* src) {
+    if (FIRST) {
+      Entry e = entries[i];
+      Affine<F> q = src[e.val & 0x7fffffffu];
+      affine_cneg(q, (e.val >> 31) != 0);
+      return q;
+    }
+    return src[i];
+  }
+  static ZK_HD void classify(Ops& op, bool has2) {
+    fset_one(op.d);
+    if (!has2 || is_inf(op.p2)) { op.kind = 2; return; }
+    if (is_inf(op.p1)) { op.kind = 3; return; }
+    if (!feq(op.p1.x, op.p2.x)) { op.kind = 0; fsub(op.d, op.p2.x, op.p1.x); return; }
+    if (feq(op.p1.y, op.p2.y) && !fis_zero(op.p1.y)) { op.kind = 1; fdbl(op.d, op.p1.y); return; }
+    op.kind = 4;
+  }
+
+  static ZK_HD void run(uint32_t tid, MsmPlan p, const uint32_t* off_in, const uint32_t* off_out, const Entry* entries,
+                        const Affine<F>* src, Affine<F>* dst, F* prefix, Entry* entries_out) {
+    const uint32_t total = off_out[p.nb];
+    const uint64_t beg64 = (uint64_t)tid * p.batch_T;
+    if (beg64 >= total) return;
+    const uint32_t beg = (uint32_t)beg64, end = beg + p.batch_T < total ? beg + p.batch_T : total;
+    uint32_t lo = 0, hi = p.nb;                       // largest b with off_out[b] <= beg
+    while (hi - lo > 1) { uint32_t mid = (lo + hi) / 2; if (off_out[mid] <= beg) lo = mid; else hi = mid; }
+    uint32_t b = lo;
+    // forward: exclusive prefix products of the denominators
+    F prod;
+    fset_one(prod);
+    for (uint32_t o = beg; o < end; o++) {
+      while (o >= off_out[b + 1]) b++;
+      uint32_t j = o - off_out[b], i1 = off_in[b] + 2 * j;
+      bool has2 = i1 + 1 < off_in[b + 1];
+      Ops op;
+      op.p1 = item(i1, entries, src);
+      if (has2) op.p2 = item(i1 + 1, entries, src); else set_inf(op.p2);
+      classify(op, has2);
+      prefix[o] = prod;
+      fmul(prod, prod, op.d);
+    }
+    F inv;
+    finv(inv, prod);
+    // backward: inverse of each denominator, then the affine formulas
+    for (uint32_t o = end; o-- > beg;) {
+      while (o < off_out[b]) b--;
+      uint32_t j = o - off_out[b], i1 = off_in[b] + 2 * j;
+      bool has2 = i1 + 1 < off_in[b + 1];
+      Ops op;
+      op.p1 = item(i1, entries, src);
+      if (has2) op.p2 = item(i1 + 1, entries, src); else set_inf(op.p2);
+      classify(op, has2);
+      F pk = prefix[o], dinv, lam, t;
+      fmul(dinv, inv, pk);
+      fmul(inv, inv, op.d);
+      Affine<F> r;
+      if (op.kind == 0 || op.kind == 1) {
+        if (op.kind == 0) fsub(t, op.p2.y, op.p1.y);
+        else { fsqr(t, op.p1.x); fdbl(lam, t); fadd(t, lam, t); }       // 3 x^2
+        fmul(lam, t, dinv);
+        fsqr(t, lam);
+        fsub(t, t, op.p1.x);
+        fsub(r.x, t, op.kind == 0 ? op.p2.x : op.p1.x);
+        fsub(t, op.p1.x, r.x);
+        fmul(t, lam, t);
+        fsub(r.y, t, op.p1.y);
+      } else if (op.kind == 2) r = op.p1;
+      else if (op.kind == 3) r = op.p2;
+      else set_inf(r);
+      dst[o] = r;
+      if (entries_out) { Entry e; e.key = b; e.val = o; entries_out[o] = e; }
+    }
   }
 };
 
@@ -526,6 +627,10 @@ inline MsmPlan msm_plan(uint32_t n, uint32_t c, bool precomp, uint32_t stride, b
   p.K = 2;                                   // per-thread reduction: ~16k threads, short chains, chip busy
   while (p.K < 64 && p.B / p.K > 16384) p.K *= 2;
   if (p.K > p.B) p.K = p.B;
+  p.batch_rounds = 0;
+  p.batch_T = 64;
+  if (const char* e = getenv("ZKMSM_BATCH_ROUNDS")) { uint32_t v = (uint32_t)atoi(e); if (v <= 8) p.batch_rounds = v; }
+  if (const char* e = getenv("ZKMSM_BATCH_T")) { uint32_t v = (uint32_t)atoi(e); if (v >= 2 && v <= 1024) p.batch_T = v; }
   p.coop = 0;
   if (coop_tail) {
     // cooperative reduction: 32 chains per 4-warp block, aim at <= ~one block per SM (148 x 32 = 4736 chains) so
@@ -559,6 +664,12 @@ template <class C> struct MsmBuffers {
   XYZZ<F>* bucket_sums;    // nb
   XYZZ<F>* partials;       // msm_partial_slots(): level 0 (one per accumulate thread), then the fix-up levels
   uint32_t* partial_keys;  // same count
+  // batched-affine pre-reduction (p.batch_rounds > 0): ping-pong point / offset buffers, prefix scratch
+  Affine<F>* pre_pts[2];   // ceil(max_entries / 2) + nb each
+  F* pre_prefix;           // ceil(max_entries / 2) + nb
+  uint32_t* pre_off[2];    // nb + 1 each
+  uint32_t* pre_cnt;       // nb
+  Entry* pre_entries;      // ceil(max_entries / 2) + nb
   XYZZ<F>* reduced;        // nwin * (B / K)
   uint32_t* err;           // 1
 };
@@ -574,8 +685,37 @@ void msm_launch(Exec& ex, const MsmPlan& p, const MsmBuffers<C>& b, const Affine
   // offsets[0..nb] = exclusive scan of the histogram; the histogram array becomes the scatter cursors
   ex.exclusive_scan(p.nb, b.hist_cursor, b.offsets, b.segsum);
   ex.template launch<Scatter>(p.n, p, d_scalars, b.hist_cursor, b.entries);
-  ex.template launch<Accumulate<C>>(p.acc_threads, p, (const uint32_t*)b.offsets, (const Entry*)b.entries, points,
-                                    b.bucket_sums, b.partials, b.partial_keys);
+  const uint32_t* acc_offsets = b.offsets;
+  const Entry* acc_entries = b.entries;
+  const Affine<typename C::F>* acc_points = points;
+  if (p.batch_rounds > 0) {
+    typedef typename C::F F;
+    const uint32_t max_out = (p.max_entries + 1) / 2 + p.nb, threads = (max_out + p.batch_T - 1) / p.batch_T;
+    const uint32_t* off_in = b.offsets;
+    const Affine<F>* src = points;
+    for (uint32_t r = 0; r < p.batch_rounds; r++) {
+      uint32_t* off_out = b.pre_off[r & 1];
+      Affine<F>* dst = b.pre_pts[r & 1];
+      bool last = r + 1 == p.batch_rounds;
+      ex.template launch<PairCount>(p.nb, p.nb, off_in, b.pre_cnt);
+      ex.exclusive_scan(p.nb, b.pre_cnt, off_out, b.segsum);
+      if (r == 0)
+        ex.template launch<BatchedAddRound<C, true>>(threads, p, off_in, (const uint32_t*)off_out, (const Entry*)b.entries, src, dst,
+                                                     b.pre_prefix, last ? b.pre_entries : (Entry*)nullptr);
+      else
+        ex.template launch<BatchedAddRound<C, false>>(threads, p, off_in, (const uint32_t*)off_out, (const Entry*)nullptr, src, dst,
+                                                      b.pre_prefix, last ? b.pre_entries : (Entry*)nullptr);
+      off_in = off_out;
+      src = dst;
+    }
+    acc_offsets = off_in;
+    acc_entries = b.pre_entries;
+    acc_points = src;
+  }
+  MsmPlan pa = p;
+  if (p.batch_rounds > 0) pa.precomp = 0;   // the pre-reduced items are addressed directly
+  ex.template launch<Accumulate<C>>(p.acc_threads, pa, acc_offsets, acc_entries, acc_points, b.bucket_sums, b.partials,
+                                    b.partial_keys);
   {  // fix-up tree over the per-chunk partial sums: level l reads region l, writes region l+1
     uint32_t count = p.acc_threads, level = 0;
     XYZZ<typename C::F>* pin = b.partials;

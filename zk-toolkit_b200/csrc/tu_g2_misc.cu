@@ -9,3 +9,5 @@ ZK_INSTANTIATE_KERNEL(zk::PrecomputeSlabs<zk::G2>);
 ZK_INSTANTIATE_KERNEL(zk::BaseTableChain<zk::G2>);
 ZK_INSTANTIATE_KERNEL(zk::BaseTableAffine<zk::G2>);
 ZK_INSTANTIATE_KERNEL(zk::FixedBaseMul<zk::G2>);
+ZK_INSTANTIATE_KERNEL(zk::BatchedAddRound<zk::G2, true>);
+ZK_INSTANTIATE_KERNEL(zk::BatchedAddRound<zk::G2, false>);

@@ -18,7 +18,8 @@ using namespace zk;
 // ------------------------------------------------------------------------------------------------
 
 // ------------------------------------------------------------------------------------------------
-enum { WS_HIST, WS_OFFSETS, WS_SEGSUM, WS_ENTRIES, WS_BUCKETS, WS_PARTIALS, WS_PKEYS, WS_REDUCED, WS_SCALARS, WS_MISC, WS_COUNT };
+enum { WS_HIST, WS_OFFSETS, WS_SEGSUM, WS_ENTRIES, WS_BUCKETS, WS_PARTIALS, WS_PKEYS, WS_REDUCED, WS_SCALARS, WS_MISC,
+       WS_PRE_A, WS_PRE_B, WS_PRE_PREFIX, WS_PRE_OFF, WS_PRE_ENTRIES, WS_COUNT };
 
 struct alignas(16) ResultBlock {      // device + pinned host mirror
   uint32_t xyzz[96];      // first: XYZZ<F> needs 16-byte alignment
@@ -331,6 +332,22 @@ static int msm_enqueue_impl(zkmsm_ctx* ctx, const zkmsm_points* ps, const uint32
       (rc = ws_reserve(ctx, WS_REDUCED, sizeof(XYZZ<F>) * (size_t)p.nwin * (p.B / p.K))))
     return rc;
   MsmBuffers<C> b;
+  memset(&b, 0, sizeof(b));
+  if (curve != 1) p.batch_rounds = 0;   // the pre-reduction is built for G1 only
+  if (p.batch_rounds > 0) {
+    size_t pre_n = (size_t)(p.max_entries + 1) / 2 + p.nb + 1;
+    if ((rc = ws_reserve(ctx, WS_PRE_A, sizeof(Affine<F>) * pre_n)) || (rc = ws_reserve(ctx, WS_PRE_B, sizeof(Affine<F>) * pre_n)) ||
+        (rc = ws_reserve(ctx, WS_PRE_PREFIX, sizeof(F) * pre_n)) || (rc = ws_reserve(ctx, WS_PRE_OFF, sizeof(uint32_t) * 3 * ((size_t)p.nb + 4))) ||
+        (rc = ws_reserve(ctx, WS_PRE_ENTRIES, sizeof(Entry) * pre_n)))
+      return rc;
+    b.pre_pts[0] = (Affine<F>*)ctx->ws[WS_PRE_A];
+    b.pre_pts[1] = (Affine<F>*)ctx->ws[WS_PRE_B];
+    b.pre_prefix = (F*)ctx->ws[WS_PRE_PREFIX];
+    b.pre_off[0] = (uint32_t*)ctx->ws[WS_PRE_OFF];
+    b.pre_off[1] = b.pre_off[0] + p.nb + 4;
+    b.pre_cnt = b.pre_off[1] + p.nb + 4;
+    b.pre_entries = (Entry*)ctx->ws[WS_PRE_ENTRIES];
+  }
   b.hist_cursor = (uint32_t*)ctx->ws[WS_HIST];
   b.offsets = (uint32_t*)ctx->ws[WS_OFFSETS];
   b.segsum = (uint32_t*)ctx->ws[WS_SEGSUM];
