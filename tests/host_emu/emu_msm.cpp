@@ -26,6 +26,10 @@ struct HostExec {
   template <class C> void pair_sum(uint32_t nwin, uint32_t pitch, uint32_t m, uint32_t half, XYZZ<typename C::F>* arr) {
     launch<PairSum<C>>(nwin * half, nwin, pitch, m, half, arr);
   }
+  template <class C> void finish(uint32_t nwin, uint32_t pitch, uint32_t c, const XYZZ<typename C::F>* arr,
+                                 XYZZ<typename C::F>* out_xyzz, uint32_t* out_affine, uint32_t* out_inf) {
+    launch<Finish<C>>(1u, nwin, pitch, c, arr, out_xyzz, out_affine, out_inf);
+  }
   void exclusive_scan(uint32_t nb, uint32_t* hist_cursor, uint32_t* offsets, uint32_t* segsum) {
     uint32_t nseg = (nb + SCAN_SEG - 1) / SCAN_SEG;
     launch<ScanLocal>(nseg, nb, (const uint32_t*)hist_cursor, segsum);

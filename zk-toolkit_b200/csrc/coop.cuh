@@ -258,5 +258,67 @@ __global__ void __launch_bounds__(kThreads) pair_sum_kernel(uint32_t nwin, uint3
   if (has_b) point_store_global(S, S_ACC, row + i);
 }
 
+// lane 0 of a single block: Horner over the window sums (row w of arr, element 0), then the outputs of Finish
+// (msm.cuh): the XYZZ partial and / or the canonical affine point.  c doublings per window at ~5 us instead of 8.4.
+template <class C>
+__global__ void __launch_bounds__(kThreads) finish_kernel(uint32_t nwin, uint32_t pitch, uint32_t c,
+                                                          const XYZZ<typename C::F>* arr, XYZZ<typename C::F>* out_xyzz,
+                                                          uint32_t* out_affine, uint32_t* out_inf) {
+  typedef typename C::F F;
+  extern __shared__ __align__(16) uint32_t smem[];
+  Slots<F> S{smem};
+  Flags* fl = reinterpret_cast<Flags*>(smem + (size_t)S_TOTAL * Slots<F>::NL * 32);
+  const int l = threadIdx.x & 31;
+  point_load_global(S, S_ACC, arr + (size_t)(nwin - 1) * pitch, l == 0);
+  __syncthreads();
+  for (int w = (int)nwin - 2; w >= 0; w--) {
+    for (uint32_t i = 0; i < c; i++) point_dbl(S, S_ACC, S_TMP);
+    point_load_global(S, S_Q, arr + (size_t)w * pitch, l == 0);
+    __syncthreads();
+    point_add(S, fl, S_ACC, S_Q, S_TMP, false);
+  }
+  if (threadIdx.x == 0) {
+    XYZZ<F> acc;
+    acc.x = S.load(S_ACC + PX, 0); acc.y = S.load(S_ACC + PY, 0);
+    acc.zz = S.load(S_ACC + PZZ, 0); acc.zzz = S.load(S_ACC + PZZZ, 0);
+    if (out_xyzz) *out_xyzz = acc;
+    if (out_affine) {
+      Affine<F> a;
+      xyzz_to_affine(a, acc);
+      store_canonical<F>(out_affine, a);
+      *out_inf = is_inf(acc) ? 1u : 0u;
+    }
+  }
+}
+
+// sum of k <= 32 partial points (multi-GPU combine): lane i holds partial i, 5-level tree across lanes
+template <class C>
+__global__ void __launch_bounds__(kThreads) combine_kernel(uint32_t k, const XYZZ<typename C::F>* parts,
+                                                           uint32_t* out_affine, uint32_t* out_inf) {
+  typedef typename C::F F;
+  extern __shared__ __align__(16) uint32_t smem[];
+  Slots<F> S{smem};
+  Flags* fl = reinterpret_cast<Flags*>(smem + (size_t)S_TOTAL * Slots<F>::NL * 32);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  point_load_global(S, S_ACC, parts + l, (uint32_t)l < k);
+  __syncthreads();
+  for (int stride = 16; stride >= 1; stride >>= 1) {
+    F v = S.load(S_ACC + w, (l + stride) & 31);       // lane l takes lane l+stride's point as its addend
+    __syncthreads();
+    S.store(S_Q + w, l, v);
+    __syncthreads();
+    point_add(S, fl, S_ACC, S_Q, S_TMP, l >= stride);  // only the lower half accumulates
+  }
+  if (threadIdx.x == 0) {
+    XYZZ<F> acc;
+    acc.x = S.load(S_ACC + PX, 0); acc.y = S.load(S_ACC + PY, 0);
+    acc.zz = S.load(S_ACC + PZZ, 0); acc.zzz = S.load(S_ACC + PZZZ, 0);
+    Affine<F> a;
+    xyzz_to_affine(a, acc);
+    store_canonical<F>(out_affine, a);
+    *out_inf = is_inf(acc) ? 1u : 0u;
+  }
+}
+
 }  // namespace coop
 }  // namespace zk

@@ -55,6 +55,11 @@ cudaError_t zk_coop_bucket_reduce_g1(cudaStream_t st, const MsmPlan& p, const ui
                                      const XYZZ<Mont<FqCfg>>* buckets, XYZZ<Mont<FqCfg>>* out);
 cudaError_t zk_coop_pair_sum_g1(cudaStream_t st, uint32_t nwin, uint32_t pitch, uint32_t m, uint32_t half,
                                 XYZZ<Mont<FqCfg>>* arr);
+cudaError_t zk_coop_finish_g1(cudaStream_t st, uint32_t nwin, uint32_t pitch, uint32_t c, const XYZZ<Mont<FqCfg>>* arr,
+                              XYZZ<Mont<FqCfg>>* out_xyzz, uint32_t* out_affine, uint32_t* out_inf);
+cudaError_t zk_coop_combine_g1(cudaStream_t st, uint32_t k, const XYZZ<Mont<FqCfg>>* parts, uint32_t* out_affine,
+                               uint32_t* out_inf);
+template <class C> struct Finish;
 struct Fp2;
 cudaError_t zk_coop_bucket_reduce_g2(cudaStream_t st, const MsmPlan& p, const uint32_t* offsets, const XYZZ<Fp2>* buckets,
                                      XYZZ<Fp2>* out);
@@ -131,6 +136,14 @@ struct CudaExec {
       timed("pair_sum", nwin * half, 1, [&] { return zk_coop_pair_sum_g2(st, nwin, pitch, m, half, (XYZZ<Fp2>*)arr); });
     else
       launch<PairSum<C>>(nwin * half, nwin, pitch, m, half, arr);
+  }
+  // stage 8: Horner over the windows runs cooperatively for G1 when there is more than one window
+  template <class C, class Pt>
+  void finish(uint32_t nwin, uint32_t pitch, uint32_t c, const Pt* arr, Pt* out_xyzz, uint32_t* out_affine, uint32_t* out_inf) {
+    if (std::is_same<C, G1>::value && nwin > 1 && !getenv("ZKMSM_NO_COOP"))
+      timed("finish", 1, 1, [&] { return zk_coop_finish_g1(st, nwin, pitch, c, (const XYZZ<Mont<FqCfg>>*)arr, (XYZZ<Mont<FqCfg>>*)out_xyzz, out_affine, out_inf); });
+    else
+      launch<Finish<C>>(1u, nwin, pitch, c, arr, out_xyzz, out_affine, out_inf);
   }
   void exclusive_scan(uint32_t n, uint32_t* hist_cursor, uint32_t* offsets, uint32_t* blocksums) {
     if (err != cudaSuccess) return;

@@ -739,8 +739,7 @@ void msm_launch(Exec& ex, const MsmPlan& p, const MsmBuffers<C>& b, const Affine
     ex.template pair_sum<C>(p.nwin, chunks, m, half, b.reduced);
     m = half;
   }
-  ex.template launch<Finish<C>>(1u, p.nwin, chunks, p.c, (const XYZZ<typename C::F>*)b.reduced, out_xyzz, out_affine,
-                                out_inf);
+  ex.template finish<C>(p.nwin, chunks, p.c, (const XYZZ<typename C::F>*)b.reduced, out_xyzz, out_affine, out_inf);
 }
 
 }  // namespace zk

@@ -31,4 +31,21 @@ cudaError_t zk_coop_pair_sum_g1(cudaStream_t st, uint32_t nwin, uint32_t pitch, 
   return cudaGetLastError();
 }
 
+cudaError_t zk_coop_finish_g1(cudaStream_t st, uint32_t nwin, uint32_t pitch, uint32_t c, const XYZZ<Fp>* arr,
+                              XYZZ<Fp>* out_xyzz, uint32_t* out_affine, uint32_t* out_inf) {
+  const size_t smem = coop::smem_bytes<Fp>();
+  cudaError_t e = opt_in_smem(coop::finish_kernel<G1>, smem);
+  if (e != cudaSuccess) return e;
+  coop::finish_kernel<G1><<<1, coop::kThreads, smem, st>>>(nwin, pitch, c, arr, out_xyzz, out_affine, out_inf);
+  return cudaGetLastError();
+}
+
+cudaError_t zk_coop_combine_g1(cudaStream_t st, uint32_t k, const XYZZ<Fp>* parts, uint32_t* out_affine, uint32_t* out_inf) {
+  const size_t smem = coop::smem_bytes<Fp>();
+  cudaError_t e = opt_in_smem(coop::combine_kernel<G1>, smem);
+  if (e != cudaSuccess) return e;
+  coop::combine_kernel<G1><<<1, coop::kThreads, smem, st>>>(k, parts, out_affine, out_inf);
+  return cudaGetLastError();
+}
+
 }  // namespace zk

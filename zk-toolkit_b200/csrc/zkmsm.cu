@@ -525,7 +525,10 @@ static int combine_impl(zkmsm_ctx* ctx, const uint32_t* parts, bool on_device, s
   }
   CU(ctx, cudaMemsetAsync(&ctx->d_res->err, 0, sizeof(uint32_t), ctx->stream));
   CudaExec ex(ctx->stream);
-  ex.template launch<CombinePartials<C>>(1u, (uint32_t)k, d_parts, ctx->d_res->affine, &ctx->d_res->inf);
+  if (std::is_same<C, G1>::value && k > 2 && k <= 32 && !getenv("ZKMSM_NO_COOP"))
+    ex.timed("combine_partials", (uint32_t)k, 1, [&] { return zk_coop_combine_g1(ctx->stream, (uint32_t)k, (const XYZZ<Fp>*)d_parts, ctx->d_res->affine, &ctx->d_res->inf); });
+  else
+    ex.template launch<CombinePartials<C>>(1u, (uint32_t)k, d_parts, ctx->d_res->affine, &ctx->d_res->inf);
   if (ex.err != cudaSuccess) return fail(ctx, ZKMSM_ERR_CUDA, "combine: %s", cudaGetErrorString(ex.err));
   ctx->pending = 1;
   ctx->pending_words = C::AFF_LIMBS;
