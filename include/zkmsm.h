@@ -162,6 +162,15 @@ int zkmsm_g2_points_from_scalars(zkmsm_ctx* ctx, const uint32_t base_xy[48], con
 int zkmsm_fr_aggregate(zkmsm_ctx* ctx, const uint32_t* polys, size_t n_wires, size_t n, const uint32_t* wires,
                        uint32_t* out);
 
+/* ---- quotient polynomial of the prover: h = (u v - w) / t with t = prod_{k=1..n} (x - k), i.e. Prover::new's
+ * `p.divide_by(&t)` (groth16/zktoolkit_based/prover.rs:64-71) over QAP::build_p (qap/qap.rs:99-112) and
+ * QAP::build_t (qap.rs:115-135); schoolbook product and long division as the reference (polynomial.rs:173-238).
+ * u, v, w: n coefficients each (8 words, canonical, zero padded; coefficient i multiplies x^i); h_out: n-1
+ * coefficients; *out_exact = 0 when the division leaves a remainder (the reference panics "p should be
+ * divisible by t").  2 <= n <= 2^14. */
+int zkmsm_fr_quotient(zkmsm_ctx* ctx, const uint32_t* u, const uint32_t* v, const uint32_t* w, size_t n,
+                      uint32_t* h_out, int* out_exact);
+
 /* ---- diagnostics: integer-multiply throughput of this device (roofline denominator).
  * variant 0: independent mad.wide.u32; 1: carry-chained IMAD.WIDE.U32.X (mad.lo.cc/madc.hi.cc
  * pairs); 2: 32-bit IMAD (half a limb product each); 3: as 1 with data-dependent multipliers (the

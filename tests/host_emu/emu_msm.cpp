@@ -133,6 +133,31 @@ int emu_fr_aggregate(const uint32_t* polys, uint32_t n_wires, uint32_t n, const 
   ex.launch<FrAggregate>(n, n_wires, n, (const Fr*)wm.data(), polys, out);
   return 0;
 }
+// quotient polynomial: same launch sequence as zkmsm_fr_quotient
+int emu_fr_quotient(const uint32_t* u, const uint32_t* v, const uint32_t* w, uint32_t n, uint32_t* h_out, uint32_t* nonzero_rem) {
+  HostExec ex;
+  std::vector<Fr> du(n), dv(n), dw(n), dp(2 * n), t0(n + 2), t1(n + 2), dh(n);
+  ex.launch<FrVecToMont>(n, n, n, u, du.data());
+  ex.launch<FrVecToMont>(n, n, n, v, dv.data());
+  ex.launch<FrVecToMont>(n, n, n, w, dw.data());
+  ex.launch<FrPolyMulSub>(2 * n - 1, n, (const Fr*)du.data(), (const Fr*)dv.data(), (const Fr*)dw.data(), dp.data());
+  for (auto& x : t0) fset_zero(x);
+  for (auto& x : t1) fset_zero(x);
+  fset_one(t0[0]);
+  Fr* t_old = t0.data();
+  Fr* t_new = t1.data();
+  for (uint32_t k = 1; k <= n; k++) {
+    uint32_t kc[8] = {k, 0, 0, 0, 0, 0, 0, 0};
+    Fr km;
+    fto_mont(km, kc);
+    ex.launch<FrTStep>(k + 1, k, km, (const Fr*)t_old, t_new);
+    Fr* tmp = t_old; t_old = t_new; t_new = tmp;
+  }
+  for (int d = (int)n - 2; d >= 0; d--) ex.launch<FrDivStep>(n, n, (uint32_t)d, (const Fr*)t_old, dp.data(), dh.data());
+  *nonzero_rem = 0;
+  ex.launch<FrQuotientOut>(n, n, (const Fr*)dh.data(), (const Fr*)dp.data(), h_out, nonzero_rem);
+  return 0;
+}
 void emu_plan(uint32_t n, uint32_t c, int precomp, uint32_t* out) {
   if (c == 0) c = msm_pick_c(n, precomp != 0);
   MsmPlan p = msm_plan(n, c, precomp != 0, n);

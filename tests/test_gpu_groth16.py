@@ -50,6 +50,11 @@ def test_config1_proof_identical_to_oracle_and_verifies(z, precompute):
                        g2_to_api(z, crs.g2_delta), [g2_to_api(z, p) for p in crs.g2_xi], precompute=precompute)
     gp = G.Prover.from_per_wire([p.coeffs for p in op.ui], [p.coeffs for p in op.vi], op.h.coeffs, op.wires, op.l)
     proof = gp.prove(dcrs, r, s)
+    # the same with the witness aggregation AND the quotient polynomial h computed on the device
+    gq = G.Prover.from_qap([p.coeffs for p in op.ui], [p.coeffs for p in op.vi], [p.coeffs for p in op.wi], op.wires, op.l, op.n)
+    assert gq.h[:len(op.h.coeffs)] == op.h.coeffs
+    proof_q = gq.prove(dcrs, r, s)
+    assert (proof_q.A, proof_q.B, proof_q.C) == (proof.A, proof.B, proof.C)
     got = (g1_to_o(proof.A), g2_to_o(proof.B), g1_to_o(proof.C))
     assert got == want                                      # identical canonical affine coordinates
     assert O.verify(got, crs, op.statement())               # and the reference verifier equation holds
@@ -92,3 +97,26 @@ def test_fr_aggregate_matches_python(z):
         out = ctx.fr_aggregate(mat, z.scalars_to_array(wires))
         exp = [sum(a * p[j] for a, p in zip(wires, polys)) % O.R for j in range(n)]
         assert [sum(int(w) << (32 * k) for k, w in enumerate(r)) for r in out] == exp
+
+
+def test_fr_quotient_matches_oracle(z):
+    """h = (u v - w) / t on the device vs the oracle's Prover::new (prover.rs:64-71)"""
+    from importlib import import_module
+    G = import_module("zk-toolkit_b200.groth16")
+    op = O.Prover(**O.CONFIG1)
+    u = G.aggregate([p.coeffs for p in op.ui], op.wires)
+    v = G.aggregate([p.coeffs for p in op.vi], op.wires)
+    w = G.aggregate([p.coeffs for p in op.wi], op.wires)
+    h = G.quotient(u, v, w, op.n)
+    assert h[:len(op.h.coeffs)] == op.h.coeffs and not any(h[len(op.h.coeffs):])
+    w[0] = (w[0] + 1) % O.R
+    with pytest.raises(ValueError):
+        G.quotient(u, v, w, op.n)
+    rnd = random.Random(23)
+    n = 300
+    t = O.qap_build_t(n)
+    uu = [rnd.randrange(O.R) for _ in range(n)]
+    vv = [rnd.randrange(O.R) for _ in range(n)]
+    q, rem = O.Polynomial(uu, normalize=False).multiply_by(O.Polynomial(vv, normalize=False)).divide_by(t)
+    remc = ((rem.coeffs if rem is not None else [0]) + [0] * n)[:n]
+    assert G.quotient(uu, vv, remc, n) == (q.coeffs + [0] * n)[:n - 1]

@@ -209,3 +209,39 @@ def test_emu_batched_affine_prereduction(lib, g1_set, rounds, T, monkeypatch):
     withinf = [P[0], O.INF, P[1], O.INF, P[2]]
     assert emu_g1(lib, withinf, [5, 6, 7, 8, 9], c=4) == (0, O.msm(withinf, [5, 6, 7, 8, 9]))
     assert emu_g1(lib, P, [0] * 6) == (0, O.INF)
+
+
+def test_emu_fr_quotient(lib):
+    """h = (u v - w) / t (prover.rs:64-71): the reference circuit's h, and random divisible inputs as in the
+    reference's randomised division test (polynomial.rs:693-727)"""
+    op = O.Prover(**O.CONFIG1)
+    n = op.n
+    agg = lambda polys: [sum(a * (p.coeffs[j] if j < len(p.coeffs) else 0) for a, p in zip(op.wires, polys)) % O.R for j in range(n)]
+    u, v, w = agg(op.ui), agg(op.vi), agg(op.wi)
+
+    def run(u, v, w):
+        n = len(u)
+        out = np.zeros((n - 1, 8), dtype=np.uint32)
+        flag = ctypes.c_uint32(0)
+        lib.emu_fr_quotient(ptr(U.scalars_to_array(u)), ptr(U.scalars_to_array(v)), ptr(U.scalars_to_array(w)), n, ptr(out),
+                            ctypes.byref(flag))
+        return [U.limbs_to_int(r) for r in out], flag.value == 0
+
+    h, exact = run(u, v, w)
+    assert exact and h[:len(op.h.coeffs)] == op.h.coeffs and not any(h[len(op.h.coeffs):])
+    w_bad = list(w); w_bad[0] = (w_bad[0] + 1) % O.R
+    assert run(u, v, w_bad)[1] is False                       # "p should be divisible by t"
+    rnd = random.Random(17)
+    for n in (2, 3, 9, 24):
+        t = O.qap_build_t(n)
+        hh = O.Polynomial([rnd.randrange(O.R) for _ in range(n - 1)], normalize=False)
+        uu = [rnd.randrange(O.R) for _ in range(n)]
+        vv = [rnd.randrange(O.R) for _ in range(n)]
+        uv = O.Polynomial(uu, normalize=False).multiply_by(O.Polynomial(vv, normalize=False))
+        ht = hh.multiply_by(t)                                # degree 2n-2
+        # w := u v - h t must have degree < n for a valid instance; force that by solving the top of h instead:
+        # take h as the true quotient of u v by t and w as the remainder
+        q, rem = uv.divide_by(t)
+        remc = (rem.coeffs if rem is not None else [0]) + [0] * n
+        got, exact = run(uu, vv, remc[:n])
+        assert exact and got == (q.coeffs + [0] * n)[:n - 1]

@@ -37,7 +37,7 @@ SYMBOLS = [
     "zkmsm_g1_msm_partial", "zkmsm_g2_msm_partial", "zkmsm_g1_msm_partial_device",
     "zkmsm_g1_combine", "zkmsm_g2_combine", "zkmsm_g1_combine_device",
     "zkmsm_g1_mul_base", "zkmsm_g2_mul_base", "zkmsm_g1_points_from_scalars", "zkmsm_g2_points_from_scalars",
-    "zkmsm_fr_aggregate", "zkmsm_bench_imad",
+    "zkmsm_fr_aggregate", "zkmsm_fr_quotient", "zkmsm_bench_imad",
 ]
 
 _lib = None
@@ -98,6 +98,7 @@ def load():
         "zkmsm_g1_points_from_scalars": (ci, [vp, vp, vp, sz, cu, vpp]),
         "zkmsm_g2_points_from_scalars": (ci, [vp, vp, vp, sz, cu, vpp]),
         "zkmsm_fr_aggregate": (ci, [vp, vp, sz, sz, vp, vp]),
+        "zkmsm_fr_quotient": (ci, [vp, vp, vp, vp, sz, vp, ip]),
         "zkmsm_bench_imad": (ci, [vp, ci, ci, dp, dp]),
     }
     for name, (res, args) in sig.items():

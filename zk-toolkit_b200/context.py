@@ -245,6 +245,17 @@ class Context:
         self._check(self.lib.zkmsm_fr_aggregate(self.h, L.dptr(polys), n_wires, n, L.dptr(wires), L.dptr(out)))
         return out
 
+    def fr_quotient(self, u, v, w):
+        """h = (u v - w) / prod_{k=1..n} (x - k); u, v, w: (n, 8) uint32 coefficient arrays.  Returns ((n-1, 8) array,
+        exact flag)."""
+        u, v, w = (L.as_u32(a, 8).reshape(-1, 8) for a in (u, v, w))
+        n = u.shape[0]
+        assert v.shape[0] == n and w.shape[0] == n
+        out = np.zeros((n - 1, 8), dtype=np.uint32)
+        exact = ctypes.c_int(0)
+        self._check(self.lib.zkmsm_fr_quotient(self.h, L.dptr(u), L.dptr(v), L.dptr(w), n, L.dptr(out), ctypes.byref(exact)))
+        return out, bool(exact.value)
+
     def bench_imad(self, variant, iters=4096):
         lp, ms = ctypes.c_double(0), ctypes.c_double(0)
         self._check(self.lib.zkmsm_bench_imad(self.h, variant, iters, ctypes.byref(lp), ctypes.byref(ms)))

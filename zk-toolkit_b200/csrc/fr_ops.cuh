@@ -9,6 +9,12 @@
 
 namespace zk {
 
+#if defined(__CUDA_ARCH__)
+ZK_D void zk_atomic_or_u32(uint32_t* p, uint32_t v) { atomicOr(p, v); }
+#else
+inline void zk_atomic_or_u32(uint32_t* p, uint32_t v) { *p |= v; }
+#endif
+
 // wires -> Montgomery form once, so that mont(a_i R, c) = a_i c comes out canonical
 struct FrToMont {
   static const char* name() { return "fr_to_mont"; }
@@ -41,6 +47,81 @@ struct FrAggregate {
     }
 #pragma unroll
     for (int k = 0; k < 8; k++) out[(size_t)tid * 8 + k] = acc.v[k];
+  }
+};
+
+// ---------------------------------------------------------------- quotient polynomial h = (u v - w) / t
+// Reference: Prover::new (groth16/zktoolkit_based/prover.rs:64-71): p = qap.build_p(witness) = u*v - w
+// (qap.rs:99-112, Polynomial::multiply_by polynomial.rs:173-190), t = prod_{k=1..n} (x - k) (QAP::build_t,
+// qap.rs:115-135), h = p.divide_by(t) (polynomial long division, polynomial.rs:204-238; "p should be divisible
+// by t").  Same schoolbook algorithms, parallel over coefficients; all values Montgomery Fr on the device.
+
+struct FrVecToMont {   // in: n x 8 canonical words -> out: Fr (Montgomery); entries beyond n_in are zero
+  static const char* name() { return "fr_vec_to_mont"; }
+  static ZK_HD void run(uint32_t tid, uint32_t n_out, uint32_t n_in, const uint32_t* in, Fr* out) {
+    if (tid >= n_out) return;
+    Fr r;
+    if (tid < n_in) {
+      uint32_t a[8];
+#pragma unroll
+      for (int i = 0; i < 8; i++) a[i] = in[(size_t)tid * 8 + i];
+      fto_mont(r, a);
+    } else fset_zero(r);
+    out[tid] = r;
+  }
+};
+
+struct FrPolyMulSub {   // p[k] = sum_{i+j=k} u[i] v[j] - w[k],  k < 2n-1  (u, v, w have n coefficients)
+  static const char* name() { return "fr_poly_mul_sub"; }
+  static ZK_HD void run(uint32_t tid, uint32_t n, const Fr* u, const Fr* v, const Fr* w, Fr* p) {
+    if (tid >= 2 * n - 1) return;
+    uint32_t lo = tid >= n ? tid - n + 1 : 0, hi = tid < n ? tid : n - 1;
+    Fr acc;
+    fset_zero(acc);
+    for (uint32_t i = lo; i <= hi; i++) {
+      Fr a = u[i], b = v[tid - i], t;
+      fmul(t, a, b);
+      fadd(acc, acc, t);
+    }
+    if (tid < n) { Fr c = w[tid]; fsub(acc, acc, c); }
+    p[tid] = acc;
+  }
+};
+
+// t_k(x) = t_{k-1}(x) (x - k): thread j <= k writes coefficient j; t_0 = 1.  k_mont = k in Montgomery form.
+struct FrTStep {
+  static const char* name() { return "fr_t_step"; }
+  static ZK_HD void run(uint32_t tid, uint32_t k, Fr k_mont, const Fr* t_old, Fr* t_new) {
+    if (tid > k) return;
+    Fr lower, cur, prod, r;
+    if (tid > 0) lower = t_old[tid - 1]; else fset_zero(lower);
+    if (tid < k) cur = t_old[tid]; else fset_zero(cur);
+    fmul(prod, cur, k_mont);
+    fsub(r, lower, prod);
+    t_new[tid] = r;
+  }
+};
+
+// one step of the long division by the monic t (degree n): q = p[d + n]; h[d] = q; p[d + j] -= q t[j], j < n
+struct FrDivStep {
+  static const char* name() { return "fr_div_step"; }
+  static ZK_HD void run(uint32_t tid, uint32_t n, uint32_t d, const Fr* t, Fr* p, Fr* h) {
+    if (tid >= n) return;
+    Fr q = p[d + n], tj = t[tid], prod, cur = p[d + tid];
+    fmul(prod, q, tj);
+    fsub(cur, cur, prod);
+    p[d + tid] = cur;
+    if (tid == 0) h[d] = q;
+  }
+};
+
+// h (Montgomery) -> canonical words; *nonzero_rem |= 1 if any of the low n coefficients of p is not zero
+struct FrQuotientOut {
+  static const char* name() { return "fr_quotient_out"; }
+  static ZK_HD void run(uint32_t tid, uint32_t n, const Fr* h, const Fr* p, uint32_t* out, uint32_t* nonzero_rem) {
+    if (tid >= n) return;
+    if (!fis_zero(p[tid])) zk_atomic_or_u32(nonzero_rem, 1u);
+    if (tid < n - 1) ffrom_mont(out + (size_t)tid * 8, h[tid]);
   }
 };
 

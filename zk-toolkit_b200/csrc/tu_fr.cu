@@ -4,3 +4,8 @@
 #include "fr_ops.cuh"
 ZK_INSTANTIATE_KERNEL(zk::FrToMont);
 ZK_INSTANTIATE_KERNEL(zk::FrAggregate);
+ZK_INSTANTIATE_KERNEL(zk::FrVecToMont);
+ZK_INSTANTIATE_KERNEL(zk::FrPolyMulSub);
+ZK_INSTANTIATE_KERNEL(zk::FrTStep);
+ZK_INSTANTIATE_KERNEL(zk::FrDivStep);
+ZK_INSTANTIATE_KERNEL(zk::FrQuotientOut);

@@ -612,6 +612,21 @@ extern "C" int zkmsm_g2_mul_base(zkmsm_ctx* ctx, const uint32_t* base, const uin
 }
 
 // ------------------------------------------------------------------------------------------------
+// Fr helpers for kernel ARGUMENTS only (the loop index k of t = prod (x - k) in Montgomery form): k R mod r is
+// stepped by adding R mod r with one conditional subtraction of r.  No data-path arithmetic happens on the host.
+static const uint32_t FR_ONE_HOST[8] = {0xfffffffeu, 0x00000001u, 0x00034802u, 0x5884b7fau, 0xecbc4ff5u, 0x998c4fefu, 0xacc5056fu, 0x1824b159u};
+static const uint32_t FR_P_HOST[8] = {0x00000001u, 0xffffffffu, 0xfffe5bfeu, 0x53bda402u, 0x09a1d805u, 0x3339d808u, 0x299d7d48u, 0x73eda753u};
+static void fr_host_add_one_mont(Fr& a) {
+  uint64_t c = 0;
+  uint32_t t[8], d[8];
+  for (int i = 0; i < 8; i++) { uint64_t s = (uint64_t)a.v[i] + FR_ONE_HOST[i] + c; t[i] = (uint32_t)s; c = s >> 32; }
+  uint64_t b = 0;
+  for (int i = 0; i < 8; i++) { uint64_t s = (uint64_t)t[i] - FR_P_HOST[i] - b; d[i] = (uint32_t)s; b = (s >> 32) & 1; }
+  bool ge = c || !b;
+  for (int i = 0; i < 8; i++) a.v[i] = ge ? d[i] : t[i];
+}
+
+// ------------------------------------------------------------------------------------------------
 // Fr witness aggregation
 extern "C" int zkmsm_fr_aggregate(zkmsm_ctx* ctx, const uint32_t* polys, size_t n_wires, size_t n, const uint32_t* wires,
                                   uint32_t* out) {
@@ -637,6 +652,60 @@ extern "C" int zkmsm_fr_aggregate(zkmsm_ctx* ctx, const uint32_t* polys, size_t 
   if (ex.err != cudaSuccess) return fail(ctx, ZKMSM_ERR_CUDA, "fr_aggregate: %s", cudaGetErrorString(ex.err));
   CU(ctx, cudaMemcpyAsync(out, d_out, ob, cudaMemcpyDeviceToHost, ctx->stream));
   CU(ctx, cudaStreamSynchronize(ctx->stream));
+  return ZKMSM_OK;
+}
+
+// quotient polynomial h = (u v - w) / t,  t = prod_{k=1..n} (x - k)
+extern "C" int zkmsm_fr_quotient(zkmsm_ctx* ctx, const uint32_t* u, const uint32_t* v, const uint32_t* w, size_t n,
+                                 uint32_t* h_out, int* out_exact) {
+  if (!ctx || !u || !v || !w || !h_out || !out_exact || n < 2 || n > (1u << 14))
+    return fail(ctx, ZKMSM_ERR_INVALID_ARG, "bad argument (2 <= n <= 2^14)");
+  CU(ctx, cudaSetDevice(ctx->device));
+  const size_t in_bytes = sizeof(uint32_t) * 8 * n;
+  // layout in WS_MISC: raw u | v | w, then Fr arrays u, v, w (n each), p (2n), t0, t1 (n+1 each), h (n), flag
+  size_t off_raw = 0, off_fr = 3 * in_bytes;
+  size_t fr_elems = 3 * n + 2 * n + 2 * (n + 1) + n;
+  int rc = ws_reserve(ctx, WS_MISC, off_fr + sizeof(Fr) * fr_elems + in_bytes + 256);
+  if (rc) return rc;
+  char* base = (char*)ctx->ws[WS_MISC];
+  uint32_t* d_raw = (uint32_t*)(base + off_raw);
+  Fr* du = (Fr*)(base + off_fr);
+  Fr *dv = du + n, *dw = dv + n, *dp = dw + n, *dt0 = dp + 2 * n, *dt1 = dt0 + (n + 1), *dh = dt1 + (n + 1);
+  uint32_t* d_out = (uint32_t*)(dh + n);
+  uint32_t* d_flag = d_out + 8 * n;
+  CU(ctx, cudaMemcpyAsync(d_raw, u, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  CU(ctx, cudaMemcpyAsync(d_raw + 8 * n, v, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  CU(ctx, cudaMemcpyAsync(d_raw + 16 * n, w, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  CU(ctx, cudaMemsetAsync(d_flag, 0, sizeof(uint32_t), ctx->stream));
+  CU(ctx, cudaMemsetAsync(dt0, 0, sizeof(Fr) * 2 * (n + 1), ctx->stream));
+  CudaExec ex(ctx->stream);
+  const uint32_t N = (uint32_t)n;
+  ex.template launch<FrVecToMont>(N, N, N, (const uint32_t*)d_raw, du);
+  ex.template launch<FrVecToMont>(N, N, N, (const uint32_t*)(d_raw + 8 * n), dv);
+  ex.template launch<FrVecToMont>(N, N, N, (const uint32_t*)(d_raw + 16 * n), dw);
+  ex.template launch<FrPolyMulSub>(2 * N - 1, N, (const Fr*)du, (const Fr*)dv, (const Fr*)dw, dp);
+  // t_0 = 1 (Montgomery one), then n steps t_k = t_{k-1} (x - k)
+  Fr one_m, k_m;
+  for (int i = 0; i < 8; i++) one_m.v[i] = FR_ONE_HOST[i];
+  CU(ctx, cudaMemcpyAsync(dt0, &one_m, sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+  Fr* t_old = dt0;
+  Fr* t_new = dt1;
+  fset_zero(k_m);
+  for (uint32_t k = 1; k <= N; k++) {
+    // k in Montgomery form = k * R mod r, accumulated on the host by adding R mod r (exact 256-bit arithmetic)
+    fr_host_add_one_mont(k_m);
+    ex.template launch<FrTStep>(k + 1, k, k_m, (const Fr*)t_old, t_new);
+    Fr* tmp = t_old; t_old = t_new; t_new = tmp;
+  }
+  // long division: quotient degree (2n-2) - n = n-2
+  for (int d = (int)n - 2; d >= 0; d--) ex.template launch<FrDivStep>(N, N, (uint32_t)d, (const Fr*)t_old, dp, dh);
+  ex.template launch<FrQuotientOut>(N, N, (const Fr*)dh, (const Fr*)dp, d_out, d_flag);
+  if (ex.err != cudaSuccess) return fail(ctx, ZKMSM_ERR_CUDA, "fr_quotient: %s", cudaGetErrorString(ex.err));
+  uint32_t flag = 0;
+  CU(ctx, cudaMemcpyAsync(h_out, d_out, sizeof(uint32_t) * 8 * (n - 1), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(ctx, cudaMemcpyAsync(&flag, d_flag, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  *out_exact = flag ? 0 : 1;
   return ZKMSM_OK;
 }
 

@@ -85,6 +85,16 @@ def aggregate(polys, wires, ctx=None):
     return [sum(int(w) << (32 * k) for k, w in enumerate(row)) for row in out]
 
 
+def quotient(u_agg, v_agg, w_agg, n, ctx=None):
+    """h = (u v - w) / t on the device (Prover::new, prover.rs:64-71); raises where the reference panics"""
+    ctx = ctx or default_context()
+    pad = lambda p: scalars_to_array(_pad(p, n))
+    h, exact = ctx.fr_quotient(pad(u_agg), pad(v_agg), pad(w_agg))
+    if not exact:
+        raise ValueError("p should be divisible by t")   # prover.rs:69
+    return [sum(int(x) << (32 * k) for k, x in enumerate(row)) for row in h]
+
+
 def _pad(v, n):
     v = [int(x) % R for x in v]
     if len(v) > n:
@@ -119,6 +129,14 @@ class Prover:
     def from_per_wire(cls, ui, vi, h, wires, l):
         """ui, vi: per-wire coefficient lists (prover.ui / prover.vi), wires a_0..a_m, l = last statement wire"""
         return cls(aggregate(ui, wires), aggregate(vi, wires), list(h), list(wires[l + 1:]))
+
+    @classmethod
+    def from_qap(cls, ui, vi, wi, wires, l, n, ctx=None):
+        """Prover::new's arithmetic part (prover.rs:64-93) on the device: aggregate the per-wire polynomials
+        (zkmsm_fr_aggregate), then h = (u v - w) / t (zkmsm_fr_quotient).  ui, vi, wi: per-wire coefficient
+        lists of the QAP (prover.ui / vi / wi), wires a_0..a_m, l = last statement wire, n = constraints."""
+        u, v, w = (aggregate(p, wires, ctx) for p in (ui, vi, wi))
+        return cls(u, v, quotient(u, v, w, n, ctx), list(wires[l + 1:]))
 
     def prove(self, crs: DeviceCRS, r: int, s: int) -> Proof:
         ctx = crs.ctx
