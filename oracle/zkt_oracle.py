@@ -747,3 +747,117 @@ def g2_to_limbs(p):
     for v in (p[0].u0.e, p[0].u1.e, p[1].u0.e, p[1].u1.e):
         out += [(v >> (32 * i)) & 0xFFFFFFFF for i in range(12)]
     return out
+
+
+# --------------------------------------------------------------------------- Pinocchio (second consumer of the MSM seam)
+class PinocchioProver:
+    """zk/w_trusted_setup/pinocchio/prover.rs:35-93 (Prover::new) on explicit R1CS rows."""
+
+    def __init__(self, rows_a, rows_b, rows_c, witness, mid_beg):
+        r1cs_validate(rows_a, rows_b, rows_c, witness)
+        qap = QAP(rows_a, rows_b, rows_c, len(witness))
+        self.num_constraints = len(rows_a)
+        self.t = qap_build_t(self.num_constraints)
+        self.p = qap.build_p(witness)                                              # :64
+        polys = qap.vi + qap.wi + qap.yi + [self.p, self.t]
+        self.max_degree = max(len(x) - 1 for x in polys) + 1                       # :66-76
+        self.witness = [w % R for w in witness]
+        self.mid_beg = mid_beg
+        self.vi, self.wi, self.yi = qap.vi, qap.wi, qap.yi
+
+    def io(self):   # witness.rs:20-23
+        return self.witness[: self.mid_beg]
+
+    def mid(self):  # witness.rs:25-27
+        return self.witness[self.mid_beg:]
+
+
+class PinocchioCRS:
+    """pinocchio/crs.rs:55-161 with the trapdoor supplied by the caller."""
+
+    def __init__(self, p: PinocchioProver, r_v, r_w, alpha_v, alpha_w, alpha_y, beta, gamma, s):
+        g1, g2 = G1_GEN, G2_GEN
+        m = scalar_mul
+        r_y = (r_v * r_w) % R
+        g1_v, g1_w, g2_w, g1_y = m(g1, r_v), m(g1, r_w), m(g2, r_w), m(g1, r_y)
+        mid = list(range(p.mid_beg, len(p.witness)))
+        io = list(range(p.mid_beg))
+        ev = lambda poly: poly.eval_at(s)
+        self.vk_mid = [m(g1_v, ev(p.vi[i])) for i in mid]
+        self.g1_wk_mid = [m(g1_w, ev(p.wi[i])) for i in mid]
+        self.g2_wk_mid = [m(g2_w, ev(p.wi[i])) for i in mid]
+        self.yk_mid = [m(g1_y, ev(p.yi[i])) for i in mid]
+        self.alpha_vk_mid = [m(m(g1_v, alpha_v), ev(p.vi[i])) for i in mid]
+        self.alpha_wk_mid = [m(m(g1_w, alpha_w), ev(p.wi[i])) for i in mid]
+        self.alpha_yk_mid = [m(m(g1_y, alpha_y), ev(p.yi[i])) for i in mid]
+        spow, self.si = 1, []
+        for _ in range(p.max_degree):                                              # s.pow_seq(max_degree), crs.rs:95-96
+            self.si.append(m(g2, spow))
+            spow = (spow * s) % R
+        self.beta_vwy_k_mid = [
+            affine_add(affine_add(m(m(g1_v, beta), ev(p.vi[i])), m(m(g1_w, beta), ev(p.wi[i]))), m(m(g1_y, beta), ev(p.yi[i])))
+            for i in mid]
+        self.one_g1, self.one_g2 = m(g1, 1), m(g2, 1)
+        self.alpha_v, self.alpha_w, self.alpha_y = m(g2, alpha_v), m(g1, alpha_w), m(g2, alpha_y)
+        self.gamma, self.beta_gamma = m(g2, gamma), m(m(g2, gamma), beta)
+        self.t = m(g1_y, ev(p.t))
+        self.vk_io = [m(g1_v, ev(p.vi[i])) for i in io]
+        self.wk_io = [m(g2_w, ev(p.wi[i])) for i in io]
+        self.yk_io = [m(g1_y, ev(p.yi[i])) for i in io]
+        self.alpha_v_t, self.alpha_y_t, self.beta_t = m(self.t, alpha_v), m(self.t, alpha_y), m(self.t, beta)
+
+
+def pinocchio_prove(p: PinocchioProver, crs: PinocchioCRS, delta_v, delta_y):
+    """Prover::prove, pinocchio/prover.rs:95-171, with delta_v / delta_y supplied by the caller.
+    Returns a dict with the nine proof elements (proof.rs)."""
+    m, add = scalar_mul, affine_add
+    mid = p.mid()
+    v_mid_s = m(crs.t, delta_v)
+    g1_w_mid_s = INF
+    g2_w_mid_s = INF
+    y_mid_s = m(crs.t, delta_y)
+    alpha_v_mid_s = m(crs.alpha_v_t, delta_v)
+    alpha_w_mid_s = INF
+    alpha_y_mid_s = m(crs.alpha_y_t, delta_y)
+    beta_vwy_mid_s = add(m(crs.beta_t, delta_v), m(crs.beta_t, delta_y))
+    for i, w in enumerate(mid):                                                    # :118-128, the inline MSM loops
+        v_mid_s = add(v_mid_s, m(crs.vk_mid[i], w))
+        g1_w_mid_s = add(g1_w_mid_s, m(crs.g1_wk_mid[i], w))
+        g2_w_mid_s = add(g2_w_mid_s, m(crs.g2_wk_mid[i], w))
+        y_mid_s = add(y_mid_s, m(crs.yk_mid[i], w))
+        alpha_v_mid_s = add(alpha_v_mid_s, m(crs.alpha_vk_mid[i], w))
+        alpha_w_mid_s = add(alpha_w_mid_s, m(crs.alpha_wk_mid[i], w))
+        alpha_y_mid_s = add(alpha_y_mid_s, m(crs.alpha_yk_mid[i], w))
+        beta_vwy_mid_s = add(beta_vwy_mid_s, m(crs.beta_vwy_k_mid[i], w))
+    h, rem = p.p.divide_by(p.t)                                                    # :131-134
+    if rem is not None:
+        raise ValueError("p should be divisible by t")
+    h_s = h.eval_with_g2_hidings(crs.si)                                           # :136
+    w_s = g2_w_mid_s
+    for i, w in enumerate(p.io()[: len(crs.wk_io)]):                               # :139-142
+        w_s = add(w_s, m(crs.wk_io[i], w))
+    adj_h_s = add(add(h_s, m(w_s, delta_v)), point_neg(m(crs.one_g2, delta_y)))    # :144
+    return dict(v_mid_s=v_mid_s, g1_w_mid_s=g1_w_mid_s, g2_w_mid_s=g2_w_mid_s, y_mid_s=y_mid_s, h_s=adj_h_s,
+                alpha_v_mid_s=alpha_v_mid_s, alpha_w_mid_s=alpha_w_mid_s, alpha_y_mid_s=alpha_y_mid_s,
+                beta_vwy_mid_s=beta_vwy_mid_s)
+
+
+def pinocchio_verify(proof, crs: PinocchioCRS, witness_io) -> bool:
+    """Verifier::verify, pinocchio/verifier.rs:27-87."""
+    e, add, m = tate, affine_add, scalar_mul
+    pr = proof
+    vwy = add(add(pr["v_mid_s"], pr["g1_w_mid_s"]), pr["y_mid_s"])
+    if e(pr["beta_vwy_mid_s"], crs.gamma) != e(vwy, crs.beta_gamma):
+        return False
+    if e(pr["alpha_v_mid_s"], crs.one_g2) != e(pr["v_mid_s"], crs.alpha_v):
+        return False
+    if e(pr["alpha_w_mid_s"], crs.one_g2) != e(crs.alpha_w, pr["g2_w_mid_s"]):
+        return False
+    if e(pr["alpha_y_mid_s"], crs.one_g2) != e(pr["y_mid_s"], crs.alpha_y):
+        return False
+    v_s, w_s, y_s = pr["v_mid_s"], pr["g2_w_mid_s"], pr["y_mid_s"]
+    for i, w in enumerate(witness_io):
+        v_s = add(v_s, m(crs.vk_io[i], w))
+        w_s = add(w_s, m(crs.wk_io[i], w))
+        y_s = add(y_s, m(crs.yk_io[i], w))
+    return e(v_s, w_s) == e(crs.t, pr["h_s"]) * e(y_s, crs.one_g2)

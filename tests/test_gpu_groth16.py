@@ -120,3 +120,23 @@ def test_fr_quotient_matches_oracle(z):
     q, rem = O.Polynomial(uu, normalize=False).multiply_by(O.Polynomial(vv, normalize=False)).divide_by(t)
     remc = ((rem.coeffs if rem is not None else [0]) + [0] * n)[:n]
     assert G.quotient(uu, vv, remc, n) == (q.coeffs + [0] * n)[:n - 1]
+
+
+def test_pinocchio_proof_identical_to_oracle_and_verifies(z):
+    """pinocchio/prover.rs:178-211: the same circuit through Pinocchio; all nine proof elements must equal the
+    oracle's restatement and pass the restated verifier (verifier.rs:27-87)."""
+    from importlib import import_module
+    P = import_module("zk-toolkit_b200.pinocchio")
+    G = import_module("zk-toolkit_b200.groth16")
+    op = O.PinocchioProver(**O.CONFIG1)
+    crs = O.PinocchioCRS(op, r_v=0x1357, r_w=0x2468ace, alpha_v=0x1111, alpha_w=0x2222, alpha_y=0x3333, beta=0x4444,
+                         gamma=0x5555, s=0x66667777)
+    dv, dy = 0xabcdef, 0x123457
+    want = O.pinocchio_prove(op, crs, dv, dy)
+    keys = P.DeviceKeys(crs, lambda p: g1_to_api(z, p), lambda p: g2_to_api(z, p))
+    agg = lambda polys: G.aggregate([p.coeffs for p in polys], op.witness)
+    h = G.quotient(agg(op.vi), agg(op.wi), agg(op.yi), op.num_constraints)
+    got = P.prove(keys, op.mid(), op.io(), h, dv, dy)
+    conv = {k: (g2_to_o(v) if isinstance(v, z.G2Point) else g1_to_o(v)) for k, v in got.items()}
+    assert conv == want
+    assert O.pinocchio_verify(conv, crs, op.io())

@@ -220,3 +220,16 @@ def test_groth16_config1_prove_verify():
     assert O.verify(proof, crs, prover.statement())
     bad = (O.affine_add(proof[0], O.G1_GEN), proof[1], proof[2])
     assert not O.verify(bad, crs, prover.statement())
+
+
+# ---- Pinocchio end to end: pinocchio/prover.rs:178-211
+@pytest.mark.slow
+def test_pinocchio_config1_prove_verify():
+    op = O.PinocchioProver(**O.CONFIG1)
+    assert op.max_degree == 9 and op.mid() == [9, 27, 8, 35] and op.io() == [1, 3, 35]
+    crs = O.PinocchioCRS(op, r_v=0x1357, r_w=0x2468ace, alpha_v=0x1111, alpha_w=0x2222, alpha_y=0x3333, beta=0x4444,
+                         gamma=0x5555, s=0x66667777)
+    proof = O.pinocchio_prove(op, crs, 0xabcdef, 0x123457)
+    assert O.pinocchio_verify(proof, crs, op.io())
+    bad = dict(proof, y_mid_s=O.affine_add(proof["y_mid_s"], O.G1_GEN))
+    assert not O.pinocchio_verify(bad, crs, op.io())

@@ -9,4 +9,4 @@ from ._lib import LIB_PATH, SYMBOLS, ZkmsmError, load  # noqa: F401
 from .context import Context, PointSet  # noqa: F401
 from .api import (G1Point, G1Points, G2Point, G2Points, Polynomial, Q, R, default_context,  # noqa: F401
                   scalars_to_array)
-from . import groth16, synthetic  # noqa: F401,E402
+from . import groth16, pinocchio, synthetic  # noqa: F401,E402
