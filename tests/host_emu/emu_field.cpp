@@ -24,6 +24,7 @@ int emu_field_op(int field, int op, const uint32_t* a, const uint32_t* b, uint32
       case 7: finv_fermat(z, x); break;
       case 8: fsqr(z, x); break;
       case 9: fmul2(z, x, y, y, y, x); fadd(z, z, y); break;   // x*y + y*x through the lockstep pair
+      case 10: finv_euclid(z, x); break;
       default: return -1;
     }
     memcpy(r, z.v, 48);
@@ -41,6 +42,7 @@ int emu_field_op(int field, int op, const uint32_t* a, const uint32_t* b, uint32
       case 7: finv_fermat(z, x); break;
       case 8: fsqr(z, x); break;
       case 9: fmul2(z, x, y, y, y, x); fadd(z, z, y); break;
+      case 10: finv_euclid(z, x); break;
       default: return -1;
     }
     memcpy(r, z.v, 32);

@@ -19,12 +19,20 @@ struct HostExec {
     launches++;
   }
   void zero(void* p, size_t bytes) { memset(p, 0, bytes); }
-  template <class C> void bucket_reduce(const MsmPlan& p, const uint32_t* offsets, const XYZZ<typename C::F>* buckets,
-                                        XYZZ<typename C::F>* out) {
+  template <class C> uint32_t bucket_reduce(const MsmPlan& p, const uint32_t* offsets, const XYZZ<typename C::F>* buckets,
+                                            XYZZ<typename C::F>* out) {
     launch<BucketReduce<C>>(p.nwin * (p.B / p.K), p, offsets, buckets, out);
+    return p.B / p.K;
   }
-  template <class C> void pair_sum(uint32_t nwin, uint32_t pitch, uint32_t m, uint32_t half, XYZZ<typename C::F>* arr) {
-    launch<PairSum<C>>(nwin * half, nwin, pitch, m, half, arr);
+  template <class Pt> struct Rows { const Pt* arr; uint32_t pitch; };
+  template <class C> Rows<XYZZ<typename C::F>> window_tree(uint32_t nwin, uint32_t pitch, uint32_t m, XYZZ<typename C::F>* arr,
+                                                          XYZZ<typename C::F>*) {
+    while (m > 1) {
+      uint32_t half = (m + 1) / 2;
+      launch<PairSum<C>>(nwin * half, nwin, pitch, m, half, arr);
+      m = half;
+    }
+    return {arr, pitch};
   }
   template <class C> void finish(uint32_t nwin, uint32_t pitch, uint32_t c, const XYZZ<typename C::F>* arr,
                                  XYZZ<typename C::F>* out_xyzz, uint32_t* out_affine, uint32_t* out_inf) {
@@ -57,7 +65,7 @@ static int emu_msm(const uint32_t* xy, const uint8_t* inf, const uint32_t* scala
   if (K) p.K = K;
   std::vector<uint32_t> hist(p.nb), offsets(p.nb + 1), segsum((p.nb + SCAN_SEG - 1) / SCAN_SEG + 1), err(1);
   std::vector<Entry> entries(p.max_entries + 1);
-  std::vector<XYZZ<F>> buckets(p.nb), partials(msm_partial_slots(p)), reduced((size_t)p.nwin * (p.B / p.K));
+  std::vector<XYZZ<F>> buckets(p.nb), partials(msm_partial_slots(p)), reduced(msm_reduced_slots(p));
   std::vector<uint32_t> pkeys(msm_partial_slots(p), 0x12345678u);
   // poison what the pipeline must overwrite before reading
   memset(buckets.data(), 0xAB, sizeof(XYZZ<F>) * buckets.size());

@@ -69,11 +69,31 @@ def test_mont_field_ops(lib, field):
         assert field_op(lib, field, 9, a, b) == 2 * a * b * rinv % p     # lockstep pair
     for a in vals[1:40]:
         am = a * Rm % p
-        assert field_op(lib, field, 4, am) == pow(a, -1, p) * Rm % p      # binary extended Euclid
+        assert field_op(lib, field, 4, am) == pow(a, -1, p) * Rm % p      # division steps in batches of 30
+        assert field_op(lib, field, 10, am) == pow(a, -1, p) * Rm % p     # binary extended Euclid cross-check
     for a in vals[1:8]:
         am = a * Rm % p
         assert field_op(lib, field, 7, am) == pow(a, -1, p) * Rm % p      # Fermat cross-check
     assert field_op(lib, field, 4, 0) == 0
+
+
+@pytest.mark.parametrize("field", [0, 1])
+def test_inverse_many(lib, field):
+    """finv (batched division steps, fp.cuh) against pow(a, -1, p): random values, small values, values near p and
+    near powers of two (long runs of zero bits drive the variable-length inner loop), p - small."""
+    n, p = (12, Q) if field == 0 else (8, R)
+    Rm = 1 << (32 * n)
+    rnd = random.Random(99 + field)
+    vals = [rnd.randrange(1, p) for _ in range(1500)]
+    vals += list(range(1, 40)) + [p - k for k in range(1, 40)]
+    vals += [(1 << k) % p for k in range(0, 32 * n, 7)] + [((1 << k) - 1) % p for k in range(1, 32 * n, 11)]
+    vals += [(p >> k) for k in range(1, 60)] + [(p + 1) // 2, (p - 1) // 2, (p - 1) // 3]
+    for a in vals:
+        if a == 0:
+            continue
+        # the function sees the Montgomery form aR; also feed a itself (then the result is (a/R)^-1 R = a^-1 R^2)
+        assert field_op(lib, field, 4, a * Rm % p) == pow(a, -1, p) * Rm % p
+        assert field_op(lib, field, 4, a) == pow(a, -1, p) * Rm * Rm % p
 
 
 def test_fp2_ops(lib):

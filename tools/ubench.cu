@@ -192,6 +192,19 @@ __global__ void k_fmul2_lat(Fp* io, int iters) {
   io[i] = x; io[i ^ 2] = z;
 }
 
+// MODE 0: finv (batched division steps), 1: finv_euclid, 2: xyzz_to_affine + store_canonical; one thread
+template <int MODE> __global__ void k_inv(Fp* io, uint32_t* out, int iters) {
+  Fp x = io[0], y;
+  if (MODE == 2) {
+    XYZZ<Fp> p; p.x = io[0]; p.y = io[1]; p.zz = io[2]; p.zzz = io[3];
+    for (int it = 0; it < iters; it++) { Affine<Fp> a; xyzz_to_affine(a, p); p.x = a.x; p.y = a.y; }
+    io[4] = p.x; io[5] = p.y;
+    return;
+  }
+  for (int it = 0; it < iters; it++) { if (MODE == 0) finv(y, x); else finv_euclid(y, x); fadd(x, y, io[1]); }
+  io[4] = x;
+}
+
 template <class K, class... A> float timeit(int grid, int block, K k, A... a) {
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   k<<<grid, block>>>(a...);  // warm
@@ -245,6 +258,11 @@ int main() {
       printf("latency @%d warp(s)/SM: fmul %.3f us | fmul2 pair %.3f us | xyzz_add %.2f us, _ilp %.2f us | xyzz_dbl %.2f us, _ilp %.2f us\n",
              warps, f1 * 1e3 / 2000, f2 * 1e3 / 2000, m0 * 1e3 / it3, m1 * 1e3 / it3, m2 * 1e3 / it3, m3 * 1e3 / it3);
     }
+  }
+  {
+    int it4 = 20;
+    float a = timeit(1, 1, k_inv<0>, io, sink, it4), b = timeit(1, 1, k_inv<1>, io, sink, it4), c = timeit(1, 1, k_inv<2>, io, sink, it4);
+    printf("one thread: finv (division steps) %.1f us | finv_euclid %.1f us | xyzz_to_affine %.1f us\n", a * 1e3 / it4, b * 1e3 / it4, c * 1e3 / it4);
   }
   CK(cudaDeviceSynchronize());
   return 0;

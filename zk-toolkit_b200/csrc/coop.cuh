@@ -36,7 +36,11 @@ template <class F> struct Slots {
 #pragma unroll
     for (int j = 0; j < NL; j++) p[j * 32] = w[j];
   }
-  __device__ __forceinline__ void mul(int dst, int a, int b, int lane) const {
+  // The ONLY field multiplication of the cooperative kernels: a real call taking slot numbers (nothing is
+  // passed through local memory), so each kernel holds one copy of the ~6 KB multiplication instead of ~30
+  // and the four warps of a block, which run different products of a round, all fetch the same
+  // instruction lines.  dst may alias a or b (both are loaded first).
+  __device__ __noinline__ void mul(int dst, int a, int b, int lane) const {
     F x = load(a, lane), y = load(b, lane), r;
     fmul(r, x, y);
     store(dst, lane, r);
@@ -57,11 +61,10 @@ template <class F> __device__ __noinline__ void point_dbl(Slots<F> S, int A, int
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
   // round 1: V = (2Y)^2 | XX = X^2
   if (w == 0) {
-    F y = S.load(A + PY, l), u, v;
+    F y = S.load(A + PY, l), u;
     fdbl(u, y);
-    fmul(v, u, u);
-    S.store(T + T_U1, l, u);    // U
-    S.store(T + T_PP, l, v);    // V
+    S.store(T + T_U1, l, u);                  // U
+    S.mul(T + T_PP, T + T_U1, T + T_U1, l);   // V
   } else if (w == 1) {
     S.mul(T + T_RR, A + PX, A + PX, l);   // XX
   }
@@ -70,23 +73,22 @@ template <class F> __device__ __noinline__ void point_dbl(Slots<F> S, int A, int
   if (w == 0) S.mul(T + T_PPP, T + T_U1, T + T_PP, l);        // W
   else if (w == 1) S.mul(T + T_Q, A + PX, T + T_PP, l);       // S
   else if (w == 2) {
-    F xx = S.load(T + T_RR, l), m, mm;
+    F xx = S.load(T + T_RR, l), m;
     fdbl(m, xx);
     fadd(m, m, xx);
-    fmul(mm, m, m);
-    S.store(T + T_P, l, m);     // M
-    S.store(T + T_R, l, mm);    // MM
+    S.store(T + T_P, l, m);                 // M
+    S.mul(T + T_R, T + T_P, T + T_P, l);    // MM
   } else S.mul(A + PZZ, T + T_PP, A + PZZ, l);
   __syncthreads();
   // round 3: X3 = MM - 2S, TT = M (S - X3) | WY = W Y | ZZZ' = W ZZZ
   if (w == 0) {
-    F mm = S.load(T + T_R, l), s = S.load(T + T_Q, l), m = S.load(T + T_P, l), x3, t;
+    F mm = S.load(T + T_R, l), s = S.load(T + T_Q, l), x3, t;
     fsub(x3, mm, s);
     fsub(x3, x3, s);
     fsub(t, s, x3);
-    fmul(t, m, t);
     S.store(T + T_U2, l, x3);
     S.store(T + T_TT, l, t);
+    S.mul(T + T_TT, T + T_P, T + T_TT, l);
   } else if (w == 1) S.mul(T + T_VV, T + T_PPP, A + PY, l);
   else if (w == 2) S.mul(A + PZZZ, T + T_PPP, A + PZZZ, l);
   __syncthreads();
@@ -113,19 +115,17 @@ template <class F> __device__ __noinline__ void point_add(Slots<F> S, Flags* fl,
   __syncthreads();
   // round 2: P = U2 - U1, PP = P^2 | R = S2 - S1, RR = R^2 | ZZ1 ZZ2 | ZZZ1 ZZZ2
   if (w == 0) {
-    F u1 = S.load(T + T_U1, l), u2 = S.load(T + T_U2, l), p, pp;
+    F u1 = S.load(T + T_U1, l), u2 = S.load(T + T_U2, l), p;
     fsub(p, u2, u1);
-    fmul(pp, p, p);
     S.store(T + T_P, l, p);
-    S.store(T + T_PP, l, pp);
     fl->zero_p[l] = fis_zero(p);
+    S.mul(T + T_PP, T + T_P, T + T_P, l);
   } else if (w == 1) {
-    F s1 = S.load(T + T_S1, l), s2 = S.load(T + T_S2, l), r, rr;
+    F s1 = S.load(T + T_S1, l), s2 = S.load(T + T_S2, l), r;
     fsub(r, s2, s1);
-    fmul(rr, r, r);
     S.store(T + T_R, l, r);
-    S.store(T + T_RR, l, rr);
     fl->zero_r[l] = fis_zero(r);
+    S.mul(T + T_RR, T + T_R, T + T_R, l);
   } else if (w == 2) S.mul(T + T_ZZ12, A + PZZ, Q + PZZ, l);
   else S.mul(T + T_ZZZ12, A + PZZZ, Q + PZZZ, l);
   __syncthreads();
@@ -136,14 +136,14 @@ template <class F> __device__ __noinline__ void point_add(Slots<F> S, Flags* fl,
   __syncthreads();
   // round 4: X3 = RR - PPP - 2Q, TT = R (Q - X3) | VV = S1 PPP | ZZZ3 = ZZZ12 PPP
   if (w == 0) {
-    F rr = S.load(T + T_RR, l), ppp = S.load(T + T_PPP, l), q = S.load(T + T_Q, l), r = S.load(T + T_R, l), x3, t;
+    F rr = S.load(T + T_RR, l), ppp = S.load(T + T_PPP, l), q = S.load(T + T_Q, l), x3, t;
     fsub(x3, rr, ppp);
     fsub(x3, x3, q);
     fsub(x3, x3, q);
     fsub(t, q, x3);
-    fmul(t, r, t);
     S.store(T + T_RX, l, x3);
     S.store(T + T_TT, l, t);
+    S.mul(T + T_TT, T + T_R, T + T_TT, l);
   } else if (w == 1) S.mul(T + T_VV, T + T_S1, T + T_PPP, l);
   else if (w == 2) S.mul(T + T_RZZZ, T + T_ZZZ12, T + T_PPP, l);
   __syncthreads();
@@ -195,13 +195,26 @@ template <class F> __device__ __forceinline__ void point_store_global(const Slot
 
 enum { S_RUN = 0, S_ACC = 4, S_Q = 8, S_BASE = 12, S_TMP = 16, S_TOTAL = S_TMP + T_COUNT };
 
+// Sum over the lanes of a block: lane 0's S_ACC += the S_ACC of lanes 1 .. cnt-1 (log2 levels; lane l takes lane
+// l + stride's point as its addend, only the lower half accumulates).  cnt is block-uniform; the caller has synced.
+template <class F> __device__ __forceinline__ void lane_tree(const Slots<F>& S, Flags* fl, uint32_t cnt) {
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  for (int stride = 16; stride >= 1; stride >>= 1) {
+    if ((uint32_t)stride >= cnt) continue;
+    F v = S.load(S_ACC + w, (l + stride) & 31);
+    S.store(S_Q + w, l, v);
+    __syncthreads();
+    point_add(S, fl, S_ACC, S_Q, S_TMP, l >= stride);
+  }
+}
+
 template <class F> constexpr size_t smem_bytes() { return (size_t)S_TOTAL * (sizeof(F) / 4) * 32 * 4 + sizeof(Flags); }
 
 // 32 chains per block; chain (win, k): out = sum_{i<K} (k K + i + 1) * bucket[win*B + k*K + i]   (as BucketReduce)
 template <class C>
 __global__ void __launch_bounds__(kThreads) bucket_reduce_kernel(MsmPlan p, const uint32_t* offsets,
                                                                  const XYZZ<typename C::F>* bucket_sums,
-                                                                 XYZZ<typename C::F>* out) {
+                                                                 XYZZ<typename C::F>* out, int tree) {
   typedef typename C::F F;
   extern __shared__ __align__(16) uint32_t smem[];
   Slots<F> S{smem};
@@ -229,33 +242,46 @@ __global__ void __launch_bounds__(kThreads) bucket_reduce_kernel(MsmPlan p, cons
   __syncthreads();
   point_set_inf(S, S_RUN);
   __syncthreads();
+  const int low = __ffs((int)p.K) - 1;   // k K has at least this many trailing zero bits: no addition there
   for (int b = nbits - 1; b >= 0; b--) {
-    point_dbl(S, S_RUN, S_TMP);
-    point_add(S, fl, S_RUN, S_BASE, S_TMP, ((s >> b) & 1u) == 0);
+    if (b != nbits - 1) point_dbl(S, S_RUN, S_TMP);   // the first doubling would double infinity
+    if (b >= low) point_add(S, fl, S_RUN, S_BASE, S_TMP, ((s >> b) & 1u) == 0);
   }
   point_add(S, fl, S_ACC, S_RUN, S_TMP, false);
-  if (valid) point_store_global(S, S_ACC, out + chain);
+  if (!tree) {
+    if (valid) point_store_global(S, S_ACC, out + chain);
+    return;
+  }
+  // chunks % 32 == 0: the block's 32 chains belong to one window; their sum is element k / 32 of that window's row
+  lane_tree(S, fl, 32);
+  if (l == 0 && valid) point_store_global(S, S_ACC, out + (size_t)win * chunks + k / 32);
 }
 
-// one level of the window tree: row[i] += row[i + half], 32 pairs per block
+// One level of the window tree: block (win, j) sums elements [j per_block, (j + 1) per_block) of row win of `in`
+// (row length m) into element j of row win of `out` (a different buffer).  per_block / 32 - 1 additions per lane,
+// then the lane tree.
 template <class C>
-__global__ void __launch_bounds__(kThreads) pair_sum_kernel(uint32_t nwin, uint32_t pitch, uint32_t m, uint32_t half,
-                                                            XYZZ<typename C::F>* arr) {
+__global__ void __launch_bounds__(kThreads) row_sum_kernel(uint32_t pitch_in, uint32_t m, uint32_t per_block,
+                                                           uint32_t blocks_per_row, const XYZZ<typename C::F>* in,
+                                                           uint32_t pitch_out, XYZZ<typename C::F>* out) {
   typedef typename C::F F;
   extern __shared__ __align__(16) uint32_t smem[];
   Slots<F> S{smem};
   Flags* fl = reinterpret_cast<Flags*>(smem + (size_t)S_TOTAL * Slots<F>::NL * 32);
-  const int l = threadIdx.x & 31;
-  const uint32_t pair = blockIdx.x * 32 + l;
-  const bool valid = pair < nwin * half;
-  const uint32_t win = valid ? pair / half : 0, i = valid ? pair % half : 0;
-  const bool has_b = valid && i + half < m;
-  XYZZ<F>* row = arr + (size_t)win * pitch;
-  point_load_global(S, S_ACC, row + i, valid);
-  point_load_global(S, S_Q, row + i + half, has_b);
+  const uint32_t l = threadIdx.x & 31;
+  const uint32_t win = blockIdx.x / blocks_per_row, j = blockIdx.x % blocks_per_row;
+  const uint32_t first = j * per_block;
+  const uint32_t cnt = m - first < per_block ? m - first : per_block;
+  const XYZZ<F>* row = in + (size_t)win * pitch_in + first;
+  point_load_global(S, S_ACC, row + l, l < cnt);
   __syncthreads();
-  point_add(S, fl, S_ACC, S_Q, S_TMP, false);
-  if (has_b) point_store_global(S, S_ACC, row + i);
+  for (uint32_t t = 32; t < cnt; t += 32) {
+    point_load_global(S, S_Q, row + t + l, t + l < cnt);
+    __syncthreads();
+    point_add(S, fl, S_ACC, S_Q, S_TMP, false);
+  }
+  lane_tree(S, fl, cnt);
+  if (l == 0) point_store_global(S, S_ACC, out + (size_t)win * pitch_out + j);
 }
 
 // lane 0 of a single block: Horner over the window sums (row w of arr, element 0), then the outputs of Finish
@@ -299,16 +325,10 @@ __global__ void __launch_bounds__(kThreads) combine_kernel(uint32_t k, const XYZ
   extern __shared__ __align__(16) uint32_t smem[];
   Slots<F> S{smem};
   Flags* fl = reinterpret_cast<Flags*>(smem + (size_t)S_TOTAL * Slots<F>::NL * 32);
-  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  const int l = threadIdx.x & 31;
   point_load_global(S, S_ACC, parts + l, (uint32_t)l < k);
   __syncthreads();
-  for (int stride = 16; stride >= 1; stride >>= 1) {
-    F v = S.load(S_ACC + w, (l + stride) & 31);       // lane l takes lane l+stride's point as its addend
-    __syncthreads();
-    S.store(S_Q + w, l, v);
-    __syncthreads();
-    point_add(S, fl, S_ACC, S_Q, S_TMP, l >= stride);  // only the lower half accumulates
-  }
+  lane_tree(S, fl, k);
   if (threadIdx.x == 0) {
     XYZZ<F> acc;
     acc.x = S.load(S_ACC + PX, 0); acc.y = S.load(S_ACC + PY, 0);

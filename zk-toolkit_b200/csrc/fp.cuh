@@ -427,11 +427,9 @@ template <int n> ZK_HD bool limbs_ge(const uint32_t* a, const uint32_t* b) {
 }
 }  // namespace detail
 
-// Modular inverse by the binary extended Euclid (shift / subtract only: ~760 short carry-chain
-// steps instead of ~570 Montgomery multiplications, which matters because exactly ONE thread runs
-// it at the end of an MSM).  Replaces the extended-Euclid inverse of prime_field_elem.rs:379-432;
-// same value since p is prime.  Montgomery in, Montgomery out; inv(0) = 0.
-template <class C> ZK_HD void finv(Mont<C>& r, const Mont<C>& a) {
+// Modular inverse by the binary extended Euclid (shift / subtract only, ~760 short carry-chain steps of ~250
+// cycles).  Kept as the second cross-check of finv (tests/test_host_emu_field.py); Montgomery in / out, inv(0) = 0.
+template <class C> ZK_HD void finv_euclid(Mont<C>& r, const Mont<C>& a) {
   constexpr int n = C::N;
   if (fis_zero(a)) { fset_zero(r); return; }
   uint32_t u[n], v[n];
@@ -450,6 +448,164 @@ template <class C> ZK_HD void finv(Mont<C>& r, const Mont<C>& a) {
 #pragma unroll
   for (int i = 0; i < n; i++) r3.v[i] = C::r3(i);
   fmul(r, t, r3);
+}
+
+// ---- finv: division steps in batches of 30 (Bernstein-Yang "safegcd", variable-time form) ------------------
+// Exactly ONE thread inverts at the end of an MSM, so what counts is the length of its dependent instruction
+// chain.  The binary Euclid above touches all limbs of four numbers at every one of its ~760 steps; here 30
+// steps run on the low 32 bits of (f, g) alone and leave a 2x2 integer matrix t with 2^30 (f, g)' = t (f, g),
+// which is then applied once to the full numbers (f, g) and, modulo p, to the cofactors (d, e):
+// ~27 batches x (13-limb multiply-accumulate passes) ~ 20 us instead of ~100 us.  Numbers are held in 30-bit
+// signed limbs so the division by 2^30 is a limb drop and every product is one 32x32->64 signed multiply-add.
+// Invariants: d x = f, e x = g (mod p); |f|, |g| <= p; d, e in (-2p, p).  Ends when g = 0: f = +-1, d = +-x^-1.
+namespace detail {
+static constexpr uint32_t M30 = 0x3fffffffu;
+
+ZK_HD int ctz32(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+  return __ffs((int)x) - 1;
+#else
+  return __builtin_ctz(x);
+#endif
+}
+
+template <int NL, int M> ZK_HD void to_s30(const uint32_t* a, int32_t* out) {
+#pragma unroll
+  for (int i = 0; i < M; i++) {
+    const int bit = 30 * i, w = bit / 32, s = bit % 32;
+    uint32_t x = w < NL ? a[w] >> s : 0u;
+    if (s > 2 && w + 1 < NL) x |= a[w + 1] << (32 - s);
+    out[i] = (int32_t)(x & M30);
+  }
+}
+// limbs already in [0, 2^30)
+template <int NL, int M> ZK_HD void from_s30(const int32_t* v, uint32_t* a) {
+#pragma unroll
+  for (int w = 0; w < NL; w++) {
+    const int bit = 32 * w, i = bit / 30, s = bit % 30;   // s is even and <= 28
+    uint32_t x = (uint32_t)v[i] >> s;
+    if (i + 1 < M) x |= (uint32_t)v[i + 1] << (30 - s);
+    a[w] = x;
+  }
+}
+
+// 30 division steps on the low words; t = (u, v, q, r) with 2^30 f' = u f + v g, 2^30 g' = q f + r g.
+// eta = -delta of the paper.  g is made even by adding a multiple of f (both odd), after swapping (f, g) <- (g, -f)
+// when eta < 0.
+ZK_HD int32_t divsteps30(int32_t eta, uint32_t f, uint32_t g, int32_t* t) {
+  uint32_t u = 1, v = 0, q = 0, r = 1;
+  int i = 30;
+  for (;;) {
+    int zeros = ctz32(g | (0xffffffffu << i));
+    g >>= zeros; u <<= zeros; v <<= zeros;
+    eta -= zeros; i -= zeros;
+    if (i == 0) break;
+    if (eta < 0) {
+      uint32_t x;
+      eta = -eta;
+      x = f; f = g; g = 0u - x;
+      x = u; u = q; q = 0u - x;
+      x = v; v = r; r = 0u - x;
+    }
+    // cancel up to 6 low bits of g at once: w = -g / f mod 2^limit (f (f^2 - 2) = -1/f mod 64), which is `limit`
+    // consecutive steps of the "add f" kind -- allowed while eta stays >= 0, i.e. limit <= eta + 1
+    int limit = eta + 1 > i ? i : eta + 1;
+    uint32_t w = (f * g * (f * f - 2u)) & (0xffffffffu >> (32 - limit)) & 63u;
+    g += f * w; q += u * w; r += v * w;
+  }
+  t[0] = (int32_t)u; t[1] = (int32_t)v; t[2] = (int32_t)q; t[3] = (int32_t)r;
+  return eta;
+}
+
+// (f, g) <- t (f, g) / 2^30   (exact)
+template <int M> ZK_HD void update_fg30(int32_t* f, int32_t* g, const int32_t* t) {
+  const int64_t u = t[0], v = t[1], q = t[2], r = t[3];
+  int64_t cf = u * f[0] + v * g[0], cg = q * f[0] + r * g[0];
+  cf >>= 30; cg >>= 30;
+#pragma unroll
+  for (int i = 1; i < M; i++) {
+    cf += u * f[i] + v * g[i];
+    cg += q * f[i] + r * g[i];
+    f[i - 1] = (int32_t)((uint32_t)cf & M30); cf >>= 30;
+    g[i - 1] = (int32_t)((uint32_t)cg & M30); cg >>= 30;
+  }
+  f[M - 1] = (int32_t)cf;
+  g[M - 1] = (int32_t)cg;
+}
+
+// (d, e) <- t (d, e) / 2^30 mod p: multiples md p, me p are added so that the low 30 bits cancel
+// (minv = p^-1 mod 2^30); keeps d, e in (-2p, p).
+template <int M> ZK_HD void update_de30(int32_t* d, int32_t* e, const int32_t* t, const int32_t* m, uint32_t minv) {
+  const int64_t u = t[0], v = t[1], q = t[2], r = t[3];
+  const int32_t sd = d[M - 1] >> 31, se = e[M - 1] >> 31;
+  int32_t md = (t[0] & sd) + (t[1] & se), me = (t[2] & sd) + (t[3] & se);
+  int64_t cd = u * d[0] + v * e[0], ce = q * d[0] + r * e[0];
+  md -= (int32_t)((minv * (uint32_t)cd + (uint32_t)md) & M30);
+  me -= (int32_t)((minv * (uint32_t)ce + (uint32_t)me) & M30);
+  cd += (int64_t)m[0] * md;
+  ce += (int64_t)m[0] * me;
+  cd >>= 30; ce >>= 30;
+#pragma unroll
+  for (int i = 1; i < M; i++) {
+    cd += u * d[i] + v * e[i] + (int64_t)m[i] * md;
+    ce += q * d[i] + r * e[i] + (int64_t)m[i] * me;
+    d[i - 1] = (int32_t)((uint32_t)cd & M30); cd >>= 30;
+    e[i - 1] = (int32_t)((uint32_t)ce & M30); ce >>= 30;
+  }
+  d[M - 1] = (int32_t)cd;
+  e[M - 1] = (int32_t)ce;
+}
+
+template <int M> ZK_HD void carry30(int32_t* x) {
+#pragma unroll
+  for (int i = 0; i < M - 1; i++) { x[i + 1] += x[i] >> 30; x[i] &= (int32_t)M30; }
+}
+// x in (-2p, p)  ->  sign * x mod p in [0, p), limbs in [0, 2^30)
+template <int M> ZK_HD void normalize30(int32_t* x, int32_t sign, const int32_t* m) {
+  int32_t add = x[M - 1] >> 31;
+  const int32_t neg = sign >> 31;
+#pragma unroll
+  for (int i = 0; i < M; i++) { x[i] += m[i] & add; x[i] = (x[i] ^ neg) - neg; }
+  carry30<M>(x);
+  add = x[M - 1] >> 31;
+#pragma unroll
+  for (int i = 0; i < M; i++) x[i] += m[i] & add;
+  carry30<M>(x);
+}
+}  // namespace detail
+
+// Replaces the extended-Euclid inverse of prime_field_elem.rs:379-432; same value since p is prime.
+// Montgomery in, Montgomery out; inv(0) = 0.
+template <class C> ZK_HD void finv(Mont<C>& r, const Mont<C>& a) {
+  constexpr int NL = C::N, M = NL * 32 / 30 + 1;
+  int32_t m[M], f[M], g[M], d[M], e[M];
+  uint32_t pl[NL];
+#pragma unroll
+  for (int i = 0; i < NL; i++) pl[i] = C::p(i);
+  detail::to_s30<NL, M>(pl, m);
+  detail::to_s30<NL, M>(a.v, g);
+#pragma unroll
+  for (int i = 0; i < M; i++) { f[i] = m[i]; d[i] = 0; e[i] = 0; }
+  e[0] = 1;
+  const uint32_t minv = (0u - C::INV) & detail::M30;
+  int32_t eta = -1;
+  for (int batch = 0; batch < 64; batch++) {   // <= (49 bits + 57) / 17 steps: 37 batches for 381 bits
+    int32_t nz = 0;
+#pragma unroll
+    for (int i = 0; i < M; i++) nz |= g[i];
+    if (nz == 0) break;
+    int32_t t[4];
+    eta = detail::divsteps30(eta, (uint32_t)f[0] | ((uint32_t)f[1] << 30), (uint32_t)g[0] | ((uint32_t)g[1] << 30), t);
+    detail::update_de30<M>(d, e, t, m, minv);
+    detail::update_fg30<M>(f, g, t);
+  }
+  detail::normalize30<M>(d, f[M - 1], m);
+  // plain inverse of the Montgomery representative aR is a^-1 R^-1; times R^3 (Montgomery) = a^-1 R
+  Mont<C> r3, x;
+  detail::from_s30<NL, M>(d, x.v);
+#pragma unroll
+  for (int i = 0; i < NL; i++) r3.v[i] = C::r3(i);
+  fmul(r, x, r3);
 }
 
 }  // namespace zk

@@ -52,9 +52,9 @@ struct FqCfg;
 template <class Cfg> struct Mont;
 template <class F> struct XYZZ;
 cudaError_t zk_coop_bucket_reduce_g1(cudaStream_t st, const MsmPlan& p, const uint32_t* offsets,
-                                     const XYZZ<Mont<FqCfg>>* buckets, XYZZ<Mont<FqCfg>>* out);
-cudaError_t zk_coop_pair_sum_g1(cudaStream_t st, uint32_t nwin, uint32_t pitch, uint32_t m, uint32_t half,
-                                XYZZ<Mont<FqCfg>>* arr);
+                                     const XYZZ<Mont<FqCfg>>* buckets, XYZZ<Mont<FqCfg>>* out, int tree);
+cudaError_t zk_coop_row_sum_g1(cudaStream_t st, uint32_t nwin, uint32_t pitch_in, uint32_t m, uint32_t per_block,
+                               const XYZZ<Mont<FqCfg>>* in, uint32_t pitch_out, XYZZ<Mont<FqCfg>>* out);
 cudaError_t zk_coop_finish_g1(cudaStream_t st, uint32_t nwin, uint32_t pitch, uint32_t c, const XYZZ<Mont<FqCfg>>* arr,
                               XYZZ<Mont<FqCfg>>* out_xyzz, uint32_t* out_affine, uint32_t* out_inf);
 cudaError_t zk_coop_combine_g1(cudaStream_t st, uint32_t k, const XYZZ<Mont<FqCfg>>* parts, uint32_t* out_affine,
@@ -62,8 +62,9 @@ cudaError_t zk_coop_combine_g1(cudaStream_t st, uint32_t k, const XYZZ<Mont<FqCf
 template <class C> struct Finish;
 struct Fp2;
 cudaError_t zk_coop_bucket_reduce_g2(cudaStream_t st, const MsmPlan& p, const uint32_t* offsets, const XYZZ<Fp2>* buckets,
-                                     XYZZ<Fp2>* out);
-cudaError_t zk_coop_pair_sum_g2(cudaStream_t st, uint32_t nwin, uint32_t pitch, uint32_t m, uint32_t half, XYZZ<Fp2>* arr);
+                                     XYZZ<Fp2>* out, int tree);
+cudaError_t zk_coop_row_sum_g2(cudaStream_t st, uint32_t nwin, uint32_t pitch_in, uint32_t m, uint32_t per_block,
+                               const XYZZ<Fp2>* in, uint32_t pitch_out, XYZZ<Fp2>* out);
 template <class C> struct BucketReduce;
 template <class C> struct PairSum;
 struct G1;
@@ -78,6 +79,8 @@ struct LaunchProfile {
   cudaEvent_t beg[MAX], end[MAX];
   bool have_events = false;
 };
+
+template <class Pt> struct RowRef { const Pt* arr; uint32_t pitch; };
 
 struct CudaExec {
   cudaStream_t st;
@@ -115,27 +118,50 @@ struct CudaExec {
     launches += nlaunch;
     if (e != cudaSuccess) err = e;
   }
-  // stages 6 / 7 of the MSM: cooperative kernels for G1, per-thread bodies otherwise
+  // stages 6 / 7 of the MSM: block-cooperative kernels (coop.cuh), per-thread bodies as the wide / fallback path.
+  // bucket_reduce returns the row length it left per window (row pitch stays B / K): the cooperative kernel also
+  // sums the 32 chains of each block when they share a window.
   template <class C, class P, class Pt>
-  void bucket_reduce(const P& p, const uint32_t* offsets, const Pt* buckets, Pt* out) {
-    uint32_t chains = p.nwin * (p.B / p.K);
-    if (chains == 0) return;
-    if (std::is_same<C, G1>::value && p.coop)
-      timed("bucket_reduce", chains, 1, [&] { return zk_coop_bucket_reduce_g1(st, p, offsets, (const XYZZ<Mont<FqCfg>>*)buckets, (XYZZ<Mont<FqCfg>>*)out); });
-    else if (std::is_same<C, G2>::value && p.coop)
-      timed("bucket_reduce", chains, 1, [&] { return zk_coop_bucket_reduce_g2(st, p, offsets, (const XYZZ<Fp2>*)buckets, (XYZZ<Fp2>*)out); });
-    else
-      launch<BucketReduce<C>>(chains, p, offsets, buckets, out);
+  uint32_t bucket_reduce(const P& p, const uint32_t* offsets, const Pt* buckets, Pt* out) {
+    uint32_t chunks = p.B / p.K, chains = p.nwin * chunks;
+    if (chains == 0) return chunks;
+    if (p.coop) {
+      int tree = chunks % 32 == 0 ? 1 : 0;
+      if (std::is_same<C, G1>::value)
+        timed("bucket_reduce", chains, 1, [&] { return zk_coop_bucket_reduce_g1(st, p, offsets, (const XYZZ<Mont<FqCfg>>*)buckets, (XYZZ<Mont<FqCfg>>*)out, tree); });
+      else
+        timed("bucket_reduce", chains, 1, [&] { return zk_coop_bucket_reduce_g2(st, p, offsets, (const XYZZ<Fp2>*)buckets, (XYZZ<Fp2>*)out, tree); });
+      return tree ? chunks / 32 : chunks;
+    }
+    launch<BucketReduce<C>>(chains, p, offsets, buckets, out);
+    return chunks;
   }
+  // Reduces every window's row (m elements, pitch apart) to one point; returns where the sums are (element 0 of
+  // each row of the returned buffer).  Wide levels halve in place with one thread per pair; once a level fits
+  // the cooperative kernels a block sums up to 128 elements (3 additions per lane, then the lane tree), the
+  // levels alternating between arr and scratch (nwin * (pitch / 32 + 1) points).
   template <class C, class Pt>
-  void pair_sum(uint32_t nwin, uint32_t pitch, uint32_t m, uint32_t half, Pt* arr) {
-    if (nwin * half == 0) return;
-    if (std::is_same<C, G1>::value && nwin * half <= 16384 && !getenv("ZKMSM_NO_COOP"))   // wide levels: per-thread
-      timed("pair_sum", nwin * half, 1, [&] { return zk_coop_pair_sum_g1(st, nwin, pitch, m, half, (XYZZ<Mont<FqCfg>>*)arr); });
-    else if (std::is_same<C, G2>::value && nwin * half <= 16384 && !getenv("ZKMSM_NO_COOP"))
-      timed("pair_sum", nwin * half, 1, [&] { return zk_coop_pair_sum_g2(st, nwin, pitch, m, half, (XYZZ<Fp2>*)arr); });
-    else
+  RowRef<Pt> window_tree(uint32_t nwin, uint32_t pitch, uint32_t m, Pt* arr, Pt* scratch) {
+    const bool coop_ok = !getenv("ZKMSM_NO_COOP");
+    while (m > 1 && (!coop_ok || (uint64_t)nwin * m > 16384)) {
+      uint32_t half = (m + 1) / 2;
       launch<PairSum<C>>(nwin * half, nwin, pitch, m, half, arr);
+      m = half;
+    }
+    Pt* in = arr;
+    Pt* out = scratch;
+    uint32_t pitch_in = pitch, pitch_out = pitch / 32 + 1;
+    while (m > 1) {
+      uint32_t per_block = m <= 128 ? m : 128, next = (m + per_block - 1) / per_block;
+      if (std::is_same<C, G1>::value)
+        timed("row_sum", nwin * next * 32, 1, [&] { return zk_coop_row_sum_g1(st, nwin, pitch_in, m, per_block, (const XYZZ<Mont<FqCfg>>*)in, pitch_out, (XYZZ<Mont<FqCfg>>*)out); });
+      else
+        timed("row_sum", nwin * next * 32, 1, [&] { return zk_coop_row_sum_g2(st, nwin, pitch_in, m, per_block, (const XYZZ<Fp2>*)in, pitch_out, (XYZZ<Fp2>*)out); });
+      Pt* t = in; in = out; out = t;
+      uint32_t tp = pitch_in; pitch_in = pitch_out; pitch_out = tp;
+      m = next;
+    }
+    return RowRef<Pt>{in, pitch_in};
   }
   // stage 8: Horner over the windows runs cooperatively for G1 when there is more than one window
   template <class C, class Pt>

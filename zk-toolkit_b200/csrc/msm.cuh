@@ -611,7 +611,9 @@ inline uint32_t msm_pick_c(uint32_t n, bool precomp, bool half = false) {
   return best;
 }
 
-inline MsmPlan msm_plan(uint32_t n, uint32_t c, bool precomp, uint32_t stride, bool half = false, bool coop_tail = false) {
+// acc_slots: accumulate threads the device keeps resident (SMs x 256 at 2 blocks of 128 per SM), 0 = unknown.
+inline MsmPlan msm_plan(uint32_t n, uint32_t c, bool precomp, uint32_t stride, bool half = false, bool coop_tail = false,
+                        uint32_t acc_slots = 0) {
   MsmPlan p;
   p.n = n;
   p.c = c;
@@ -624,6 +626,18 @@ inline MsmPlan msm_plan(uint32_t n, uint32_t c, bool precomp, uint32_t stride, b
   p.stride = stride;
   p.max_entries = n * p.W;
   p.L = p.max_entries >= (1u << 23) ? 32 : (p.max_entries >= (1u << 21) ? 16 : 8);
+  if (acc_slots) {
+    // Wave quantisation: every resident slot runs ceil(threads / slots) threads of L mixed additions one after the
+    // other, so with few waves (small n) the last, partly filled wave costs a whole one.  Take the L near the
+    // default that minimises waves x L (ties: the larger L, fewer partial sums for the fix-up tree).
+    uint32_t best = p.L;
+    uint64_t best_cost = ~0ull;
+    for (uint32_t l = p.L - p.L / 4; l <= p.L + p.L / 2; l++) {
+      uint64_t threads = ((uint64_t)p.max_entries + l - 1) / l, waves = (threads + acc_slots - 1) / acc_slots;
+      if (waves * l <= best_cost) { best_cost = waves * l; best = l; }
+    }
+    p.L = best;
+  }
   p.K = 2;                                   // per-thread reduction: ~16k threads, short chains, chip busy
   while (p.K < 64 && p.B / p.K > 16384) p.K *= 2;
   if (p.K > p.B) p.K = p.B;
@@ -654,6 +668,12 @@ inline size_t msm_partial_slots(const MsmPlan& p) {
   return total + 1;
 }
 
+// chunk sums of the bucket reduction (nwin rows of B / K) + scratch rows of the window tree
+inline size_t msm_reduced_slots(const MsmPlan& p) {
+  size_t chunks = p.B / p.K;
+  return (size_t)p.nwin * chunks + (size_t)p.nwin * (chunks / 32 + 1);
+}
+
 // device buffers one MSM needs (sizes in elements), all owned by the caller
 template <class C> struct MsmBuffers {
   typedef typename C::F F;
@@ -670,7 +690,7 @@ template <class C> struct MsmBuffers {
   uint32_t* pre_off[2];    // nb + 1 each
   uint32_t* pre_cnt;       // nb
   Entry* pre_entries;      // ceil(max_entries / 2) + nb
-  XYZZ<F>* reduced;        // nwin * (B / K)
+  XYZZ<F>* reduced;        // msm_reduced_slots(): nwin rows of B / K, then the window tree's scratch
   uint32_t* err;           // 1
 };
 
@@ -732,14 +752,9 @@ void msm_launch(Exec& ex, const MsmPlan& p, const MsmBuffers<C>& b, const Affine
   uint32_t chunks = p.B / p.K;
   // stages 6 and 7 go through the Exec policy: the CUDA build has block-cooperative versions (coop.cuh), the CPU
   // emulation runs the per-thread bodies BucketReduce / PairSum; both give the same points
-  ex.template bucket_reduce<C>(p, (const uint32_t*)b.offsets, (const XYZZ<typename C::F>*)b.bucket_sums, b.reduced);
-  uint32_t m = chunks;
-  while (m > 1) {
-    uint32_t half = (m + 1) / 2;
-    ex.template pair_sum<C>(p.nwin, chunks, m, half, b.reduced);
-    m = half;
-  }
-  ex.template finish<C>(p.nwin, chunks, p.c, (const XYZZ<typename C::F>*)b.reduced, out_xyzz, out_affine, out_inf);
+  uint32_t m = ex.template bucket_reduce<C>(p, (const uint32_t*)b.offsets, (const XYZZ<typename C::F>*)b.bucket_sums, b.reduced);
+  auto rows = ex.template window_tree<C>(p.nwin, chunks, m, b.reduced, b.reduced + (size_t)p.nwin * chunks);
+  ex.template finish<C>(p.nwin, rows.pitch, p.c, rows.arr, out_xyzz, out_affine, out_inf);
 }
 
 }  // namespace zk

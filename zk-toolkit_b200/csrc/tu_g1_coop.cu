@@ -13,21 +13,23 @@ template <class K> static cudaError_t opt_in_smem(K kernel, size_t bytes) {
 }
 
 cudaError_t zk_coop_bucket_reduce_g1(cudaStream_t st, const MsmPlan& p, const uint32_t* offsets, const XYZZ<Fp>* buckets,
-                                     XYZZ<Fp>* out) {
+                                     XYZZ<Fp>* out, int tree) {
   const size_t smem = coop::smem_bytes<Fp>();
   cudaError_t e = opt_in_smem(coop::bucket_reduce_kernel<G1>, smem);
   if (e != cudaSuccess) return e;
   uint32_t chains = p.nwin * (p.B / p.K);
-  coop::bucket_reduce_kernel<G1><<<(chains + 31) / 32, coop::kThreads, smem, st>>>(p, offsets, buckets, out);
+  coop::bucket_reduce_kernel<G1><<<(chains + 31) / 32, coop::kThreads, smem, st>>>(p, offsets, buckets, out, tree);
   return cudaGetLastError();
 }
 
-cudaError_t zk_coop_pair_sum_g1(cudaStream_t st, uint32_t nwin, uint32_t pitch, uint32_t m, uint32_t half, XYZZ<Fp>* arr) {
+cudaError_t zk_coop_row_sum_g1(cudaStream_t st, uint32_t nwin, uint32_t pitch_in, uint32_t m, uint32_t per_block,
+                               const XYZZ<Fp>* in, uint32_t pitch_out, XYZZ<Fp>* out) {
   const size_t smem = coop::smem_bytes<Fp>();
-  cudaError_t e = opt_in_smem(coop::pair_sum_kernel<G1>, smem);
+  cudaError_t e = opt_in_smem(coop::row_sum_kernel<G1>, smem);
   if (e != cudaSuccess) return e;
-  uint32_t pairs = nwin * half;
-  coop::pair_sum_kernel<G1><<<(pairs + 31) / 32, coop::kThreads, smem, st>>>(nwin, pitch, m, half, arr);
+  uint32_t blocks_per_row = (m + per_block - 1) / per_block;
+  coop::row_sum_kernel<G1><<<nwin * blocks_per_row, coop::kThreads, smem, st>>>(pitch_in, m, per_block, blocks_per_row, in,
+                                                                               pitch_out, out);
   return cudaGetLastError();
 }
 

@@ -30,6 +30,7 @@ struct alignas(16) ResultBlock {      // device + pinned host mirror
 
 struct zkmsm_ctx {
   int device;
+  int sms;
   cudaStream_t own_stream, stream;
   char err[512];
   unsigned window_override;
@@ -104,6 +105,7 @@ extern "C" int zkmsm_create(int device, zkmsm_ctx** out) {
   if (!ctx) return ZKMSM_ERR_NOMEM;
   memset(ctx, 0, sizeof(*ctx));
   ctx->device = device;
+  ctx->sms = prop.multiProcessorCount;
   strcpy(ctx->err, "ok");
   if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaMalloc(&ctx->d_res, sizeof(ResultBlock)) != cudaSuccess ||
@@ -321,7 +323,8 @@ static int msm_enqueue_impl(zkmsm_ctx* ctx, const zkmsm_points* ps, const uint32
     return ZKMSM_OK;
   }
   unsigned c = ps->precomp ? ps->c : (ctx->window_override ? ctx->window_override : msm_pick_c((uint32_t)n, false, ps->half));
-  MsmPlan p = msm_plan((uint32_t)n, c, ps->precomp, (uint32_t)ps->n, ps->half, !getenv("ZKMSM_NO_COOP"));
+  MsmPlan p = msm_plan((uint32_t)n, c, ps->precomp, (uint32_t)ps->n, ps->half, !getenv("ZKMSM_NO_COOP"),
+                          getenv("ZKMSM_NO_WAVE_L") ? 0u : (uint32_t)ctx->sms * 256u);
   int rc;
   uint32_t nseg = (p.nb + SCAN_SEG - 1) / SCAN_SEG + 1;
   if ((rc = ws_reserve(ctx, WS_HIST, sizeof(uint32_t) * p.nb)) || (rc = ws_reserve(ctx, WS_OFFSETS, sizeof(uint32_t) * (p.nb + 1))) ||
@@ -329,7 +332,7 @@ static int msm_enqueue_impl(zkmsm_ctx* ctx, const zkmsm_points* ps, const uint32
       (rc = ws_reserve(ctx, WS_BUCKETS, sizeof(XYZZ<F>) * (size_t)p.nb)) ||
       (rc = ws_reserve(ctx, WS_PARTIALS, sizeof(XYZZ<F>) * msm_partial_slots(p))) ||
       (rc = ws_reserve(ctx, WS_PKEYS, sizeof(uint32_t) * msm_partial_slots(p))) ||
-      (rc = ws_reserve(ctx, WS_REDUCED, sizeof(XYZZ<F>) * (size_t)p.nwin * (p.B / p.K))))
+      (rc = ws_reserve(ctx, WS_REDUCED, sizeof(XYZZ<F>) * msm_reduced_slots(p))))
     return rc;
   MsmBuffers<C> b;
   memset(&b, 0, sizeof(b));
