@@ -27,6 +27,7 @@ sys.path.insert(0, ROOT)
 R = 0x73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001
 LP_PER_G1_POINT = 48000       # 16 windows x 10 modmul x 300 limb products
 BYTES_PER_G1_POINT = 128      # 96 B affine point + 32 B scalar
+ACC_STAGES = ("accumulate", "batched_add_first", "batched_add")   # the kernels that add points into buckets
 
 
 def log(*a):
@@ -222,7 +223,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
         t_wall0 = time.time()
-        step_ms, acc_ms, launches, phase_ms = [], [], 0, {}
+        step_ms, acc_ms, launches, phase_ms, batch_rounds = [], [], 0, {}, 0
         for _ in range(args.steps):
             flush.zero_()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -245,7 +246,8 @@ def main():
             e1.synchronize()
             step_ms.append(e0.elapsed_time(e1))
             prof = ctx.profile_read()
-            acc_ms.append(sum(ms for name, ms, _ in prof if name == "accumulate"))
+            acc_ms.append(sum(ms for name, ms, _ in prof if name in ACC_STAGES))
+            batch_rounds = sum(1 for name, _, _ in prof if name in ("batched_add_first", "batched_add"))
             launches += ctx.last_launch_count() + (1 if world > 1 else 0)
         if world > 1:
             dist.barrier()
@@ -316,7 +318,8 @@ def main():
         pass
     roofline = {
         "bound": "int32 multiplier (IMAD.WIDE on the fma pipe); not hbm, not tensor",
-        "kernel": "Accumulate<G1> (XYZZ mixed adds into buckets)",
+        "kernel": "bucket accumulation = BatchedAddRound<G1> x rounds (affine adds, shared inversion) + Accumulate<G1> "
+                  "(XYZZ mixed adds); one 'launch' is this group, durations summed",
         "achieved": round(achieved / 1e12, 3) if achieved else None,
         "peak": round(lp_peak / 1e12, 3) if lp_peak else None,
         "unit": "T limb-products/s (32x32->64 multiply-accumulate)",
@@ -336,9 +339,12 @@ def main():
 
     info = pts.info()
     if info["precomputed"]:
-        # what the kernel really multiplies: windows used x 10 modmul x 300 LP (fewer windows than the canonical 16
-        # with precomputed tables): multiplier-pipe utilisation ~ frac * actual / canonical
-        roofline["actual_lp_per_point"] = info["windows"] * 3000
+        # what the kernels really multiply (fewer windows than the canonical 16 with precomputed tables; a batched
+        # affine addition is 6 modmul, an XYZZ mixed addition 10, 300 LP each): after R halving rounds a fraction
+        # 2^-R of the entries is left for the mixed additions.  multiplier-pipe utilisation ~ frac * actual / canonical
+        left = 0.5 ** batch_rounds
+        roofline["actual_lp_per_point"] = round(info["windows"] * ((1 - left) * 1800 + left * 3000))
+        roofline["batched_affine_rounds"] = batch_rounds
         roofline["window_bits"] = info["c"]
 
     # ---- CPU baseline beside it (rank 0, N = 1 only): the reference algorithm on a bounded sample

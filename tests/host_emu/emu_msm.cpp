@@ -70,9 +70,9 @@ static int emu_msm(const uint32_t* xy, const uint8_t* inf, const uint32_t* scala
   // poison what the pipeline must overwrite before reading
   memset(buckets.data(), 0xAB, sizeof(XYZZ<F>) * buckets.size());
   memset(partials.data(), 0xCD, sizeof(XYZZ<F>) * partials.size());
-  const size_t pre_n = (size_t)(p.max_entries + 1) / 2 + p.nb + 1;
+  const size_t pre_n = msm_pre_slots(p);
   std::vector<Affine<F>> pre_a(p.batch_rounds ? pre_n : 1), pre_b(p.batch_rounds ? pre_n : 1);
-  std::vector<F> pre_prefix(p.batch_rounds ? pre_n : 1);
+  std::vector<F> pre_prefix(p.batch_rounds ? 2 * msm_prefix_slots(p) : 1);
   std::vector<uint32_t> pre_off_a(p.nb + 1), pre_off_b(p.nb + 1), pre_cnt(p.nb + 1);
   std::vector<Entry> pre_entries(p.batch_rounds ? pre_n : 1);
   MsmBuffers<C> b;

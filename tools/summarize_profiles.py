@@ -9,7 +9,7 @@ out_dir = os.path.join(root, "profiles")
 os.makedirs(out_dir, exist_ok=True)
 
 def short(name):
-    m = re.search(r"body_kernel<zk::(\w+)(<zk::(G\d)>)?", name)
+    m = re.search(r"body_kernel<zk::(\w+)(<zk::(G\d)[^>]*>)?", name)
     if m:
         return m.group(1) + (f"<{m.group(3)}>" if m.group(3) else "")
     return re.sub(r"\(.*", "", name.replace("void ", ""))[:60]
@@ -30,7 +30,7 @@ if os.path.exists(lst):
         for k, (c, ms) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             f.write(f"{k:34s} {c:8d} {ms:10.3f} {100 * ms / total:6.1f}%\n")
         names = ("RecodeCount", "Scatter", "Accumulate", "FixupLevel", "BucketReduce", "PairSum", "Finish", "scan_block_sums",
-                 "scan_top_level", "scan_apply", "bucket_reduce_kernel", "pair_sum_kernel")
+                 "scan_top_level", "scan_apply", "bucket_reduce_kernel", "pair_sum_kernel", "row_sum_kernel", "BatchedAddRound", "PairCount")
         msm = {k: v for k, v in agg.items() if any(nm in k for nm in names)}
         t2 = sum(v[1] for v in msm.values())
         f.write(f"\n# MSM pipeline kernels only ({t2:.2f} ms): share of one MSM step\n")
@@ -55,7 +55,7 @@ if os.path.exists(rep):
             "smsp__pcsamp_warps_issue_stalled_math_pipe_throttle", "smsp__pcsamp_warps_issue_stalled_not_selected", "smsp__pcsamp_warps_issue_stalled_short_scoreboard",
             "smsp__pcsamp_warps_issue_stalled_no_instructions", "smsp__pcsamp_warps_issue_stalled_dispatch_stall", "smsp__pcsamp_sample_buffer_full"]
     with open(os.path.join(out_dir, f"{tag}_accumulate_ncu_full.txt"), "w") as f:
-        f.write("# ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:Accumulate -s 3 -c 2 python bench.py --steps 2 --warmup 3 --skip-cpu-baseline\n")
+        f.write("# ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k 'regex:Accumulate|BatchedAddRound' -s <one warm step's group> -c <one step's group> python bench.py --steps 2 --warmup 3 --skip-cpu-baseline\n")
         for r in data:
             f.write(f"\n== {r[hdr.index('Kernel Name')][:100]}\n")
             for k in keys:
@@ -70,11 +70,12 @@ if os.path.exists(rep):
         v = float(r[i])
         u = units[i].lower()
         return v * {"gbyte": 1e9, "mbyte": 1e6, "kbyte": 1e3, "byte": 1}.get(u, 1)
-    rd = sum(col(r, "dram__bytes_read.sum") for r in data) / len(data)
-    wr = sum(col(r, "dram__bytes_write.sum") for r in data) / len(data)
+    # the capture holds the accumulation group of ONE MSM step (batched-affine rounds + Accumulate): bytes are summed
+    rd = sum(col(r, "dram__bytes_read.sum") for r in data)
+    wr = sum(col(r, "dram__bytes_write.sum") for r in data)
     n = int(os.environ.get("TRAFFIC_N", str(1 << 20)))
-    json.dump({"kernel": "Accumulate<G1>", "n": n, "n_gpus": 1, "dram_bytes_read": round(rd), "dram_bytes_write": round(wr),
+    json.dump({"kernel": "bucket accumulation group (BatchedAddRound<G1> rounds + Accumulate<G1>), one MSM step", "launches": len(data), "n": n, "n_gpus": 1, "dram_bytes_read": round(rd), "dram_bytes_write": round(wr),
                "dram_bytes_total": round(rd + wr), "algorithmic_bytes": n * 128, "source": f"profiles/{tag}_accumulate_ncu_full.txt",
-               "note": "gathers of 96-byte points from the precomputed tables (W slabs) dominate; DRAM stays at ~6% of peak"},
+               "note": "first round: random gathers of 96-byte points from the precomputed tables (x in the forward pass, x and y on the way back) plus 96 B of prefix/denominator scratch and 96 B of output per addition; later rounds stream"},
               open(os.path.join(out_dir, "accumulate_traffic.json"), "w"), indent=1)
     print("wrote accumulate_traffic.json")

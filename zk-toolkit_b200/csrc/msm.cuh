@@ -41,7 +41,15 @@ ZK_D void zk_prefetch(const void* p, uint32_t bytes) {
   if ((((uintptr_t)c) & 127u) + bytes > 128u) asm volatile("prefetch.global.L1 [%0];" ::"l"(c + bytes - 1));
   if (bytes > 128u) asm volatile("prefetch.global.L1 [%0];" ::"l"(c + 128));
 }
+// start the DRAM -> L2 fetch of [p, p + bytes) two iterations ahead of a gather (holds no registers)
+ZK_D void zk_prefetch_l2(const void* p, uint32_t bytes) {
+  const char* c = (const char*)p;
+#pragma unroll
+  for (uint32_t off = 0; off < bytes; off += 64) asm volatile("prefetch.global.L2 [%0];" ::"l"(c + off));
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(c + bytes - 1));
+}
 #else
+inline void zk_prefetch_l2(const void*, uint32_t) {}
 inline void zk_prefetch(const void*, uint32_t) {}
 inline uint32_t zk_atomic_add(uint32_t* p, uint32_t v) { uint32_t o = *p; *p = o + v; return o; }
 inline void zk_atomic_or(uint32_t* p, uint32_t v) { *p |= v; }
@@ -69,6 +77,7 @@ struct MsmPlan {
   uint32_t batch_rounds;  // > 0: that many rounds of pairwise batched-affine additions before the XYZZ accumulation
   uint32_t batch_T;       //      additions per thread and inversion in those rounds
   uint32_t coop;          // 1: stages 6/7 run as block-cooperative kernels (coop.cuh), K sized for ~one block per SM
+  uint32_t acc_slots;     // accumulate threads the device keeps resident at 2 blocks of 128 per SM (0 = unknown)
   uint32_t half;          // 1: point set is in the prime-order subgroup; scalars s > (r-1)/2 become r - s with
                           //    the point negated, so 254 bits are recoded and no carry-only top window exists
 };
@@ -317,79 +326,166 @@ template <class C, bool FIRST> struct BatchedAddRound {
   typedef typename C::F F;
   static const char* name() { return FIRST ? "batched_add_first" : "batched_add"; }
 
-  // operands of output o (bucket b): items i1 = off_in[b] + 2j and i1 + 1 (if it exists)
-  struct Ops { Affine<F> p1, p2; int kind; F d; };   // kind 0 add, 1 double, 2 copy p1, 3 copy p2, 4 infinity
-  static ZK_HD Affine<F> item(uint32_t i, const Entry* entries, const Affine<F>* src) {
-    if (FIRST) {
-      Entry e = entries[i];
-      Affine<F> q = src[e.val & 0x7fffffffu];
-      affine_cneg(q, (e.val >> 31) != 0);
-      return q;
-    }
-    return src[i];
+  // operands of output o: items i1 = off_in[b] + 2j and i1 + 1 (if it exists), b = bucket of o, j = o - off_out[b]
+  struct Where { uint32_t i1; bool has2; };
+  static ZK_HD Where where(uint32_t o, uint32_t b, const uint32_t* off_in, const uint32_t* off_out) {
+    uint32_t i1 = off_in[b] + 2 * (o - off_out[b]);
+    return Where{i1, i1 + 1 < off_in[b + 1]};
   }
-  static ZK_HD void classify(Ops& op, bool has2) {
-    fset_one(op.d);
-    if (!has2 || is_inf(op.p2)) { op.kind = 2; return; }
-    if (is_inf(op.p1)) { op.kind = 3; return; }
-    if (!feq(op.p1.x, op.p2.x)) { op.kind = 0; fsub(op.d, op.p2.x, op.p1.x); return; }
-    if (feq(op.p1.y, op.p2.y) && !fis_zero(op.p1.y)) { op.kind = 1; fdbl(op.d, op.p1.y); return; }
-    op.kind = 4;
+  // kind 0 add, 1 double, 2 copy p1, 3 copy p2, 4 infinity; d = the denominator (1 for the kinds without one).
+  // The common case -- two points with different non-zero x -- is decided from x alone (d = x2 - x1 is already set).
+  static ZK_HD bool common_case(bool has2, const F& x1, const F& x2, const F& d) {
+    return has2 && !fis_zero(d) && !fis_zero(x1) && !fis_zero(x2);
+  }
+  static ZK_HD int classify_rare(F& d, bool has2, const F& x1, const F& y1, const F& x2, const F& y2) {
+    const bool inf1 = fis_zero(x1) && fis_zero(y1), inf2 = fis_zero(x2) && fis_zero(y2);
+    int kind;
+    if (!has2 || inf2) kind = 2;
+    else if (inf1) kind = 3;
+    else if (!fis_zero(d)) return 0;                               // x differs (one x is zero: the points (0, +-2))
+    else if (feq(y1, y2) && !fis_zero(y1)) { fdbl(d, y1); return 1; }
+    else kind = 4;
+    fset_one(d);
+    return kind;
   }
 
+  // thread tid owns outputs [tid T, (tid + 1) T); its prefix products sit at stride kBlockT so that the 32 lanes
+  // of a warp read and write neighbouring elements
+  static constexpr uint32_t kBlockT = 128;
+  static ZK_HD size_t prefix_at(uint32_t tid, uint32_t T, uint32_t i) {
+    return (size_t)(tid / kBlockT) * kBlockT * T + (size_t)i * kBlockT + tid % kBlockT;
+  }
+
+  // Locating one output's operands takes two dependent steps in the first round (sorted entry -> point address),
+  // so both passes run a three-stage software pipeline: entries of output o + 2 (Loc), x coordinates of o + 1
+  // (Item + registers), arithmetic of o -- in-order issue would otherwise stall every warp on the entry load.
+  struct Loc { uint32_t b, i1; bool has2; Entry e1, e2; };
+  struct Item {
+    uint32_t b;      // bucket
+    bool has2, neg1, neg2;
+    const Affine<F>* p1;
+    const Affine<F>* p2;
+  };
+  static ZK_HD void find(Loc& l, uint32_t o, uint32_t b, const uint32_t* off_in, const uint32_t* off_out, const Entry* entries) {
+    Where w = where(o, b, off_in, off_out);
+    l.b = b; l.i1 = w.i1; l.has2 = w.has2;
+    if (FIRST) { l.e1 = entries[w.i1]; l.e2 = entries[w.has2 ? w.i1 + 1 : w.i1]; }
+  }
+  static ZK_HD void resolve(Item& it, const Loc& l, const Affine<F>* src) {
+    it.b = l.b; it.has2 = l.has2;
+    if (FIRST) {
+      it.p1 = src + (l.e1.val & 0x7fffffffu); it.neg1 = (l.e1.val >> 31) != 0;
+      it.p2 = src + (l.e2.val & 0x7fffffffu); it.neg2 = (l.e2.val >> 31) != 0;
+    } else {
+      it.p1 = src + l.i1; it.p2 = src + (l.has2 ? l.i1 + 1 : l.i1);
+      it.neg1 = it.neg2 = false;
+    }
+  }
+
+  // Forward pass: d_o = denominator of output o, prefix_o = d_beg ... d_(o-1); both are stored (dstride apart) so
+  // that the way back starts each output from two coalesced loads and fetches the four coordinates while the
+  // first two multiplications run.
   static ZK_HD void run(uint32_t tid, MsmPlan p, const uint32_t* off_in, const uint32_t* off_out, const Entry* entries,
-                        const Affine<F>* src, Affine<F>* dst, F* prefix, Entry* entries_out) {
-    const uint32_t total = off_out[p.nb];
-    const uint64_t beg64 = (uint64_t)tid * p.batch_T;
+                        const Affine<F>* src, Affine<F>* dst, F* prefix, size_t dstride, Entry* entries_out) {
+    const uint32_t total = off_out[p.nb], T = p.batch_T;
+    const uint64_t beg64 = (uint64_t)tid * T;
     if (beg64 >= total) return;
-    const uint32_t beg = (uint32_t)beg64, end = beg + p.batch_T < total ? beg + p.batch_T : total;
+    const uint32_t beg = (uint32_t)beg64, end = beg + T < total ? beg + T : total;
     uint32_t lo = 0, hi = p.nb;                       // largest b with off_out[b] <= beg
     while (hi - lo > 1) { uint32_t mid = (lo + hi) / 2; if (off_out[mid] <= beg) lo = mid; else hi = mid; }
-    uint32_t b = lo;
-    // forward: exclusive prefix products of the denominators
+    uint32_t b = lo;                                  // bucket of the output the Loc stage is at
     F prod;
     fset_one(prod);
+    Loc loc;
+    Item cur, nxt;
+    find(loc, beg, b, off_in, off_out, entries);
+    resolve(cur, loc, src);
+    F x1 = cur.p1->x, x2 = cur.p2->x;
+    if (beg + 1 < end) {
+      while (beg + 1 >= off_out[b + 1]) b++;
+      find(loc, beg + 1, b, off_in, off_out, entries);
+    }
+    uint64_t rare_lo = 0, rare_hi = 0;   // stack of "not the common case" flags, one bit per output (T <= 128)
     for (uint32_t o = beg; o < end; o++) {
-      while (o >= off_out[b + 1]) b++;
-      uint32_t j = o - off_out[b], i1 = off_in[b] + 2 * j;
-      bool has2 = i1 + 1 < off_in[b + 1];
-      Ops op;
-      op.p1 = item(i1, entries, src);
-      if (has2) op.p2 = item(i1 + 1, entries, src); else set_inf(op.p2);
-      classify(op, has2);
-      prefix[o] = prod;
-      fmul(prod, prod, op.d);
+      F nx1, nx2;
+      if (o + 1 < end) {
+        resolve(nxt, loc, src);
+        nx1 = nxt.p1->x; nx2 = nxt.p2->x;
+        if (o + 2 < end) {
+          while (o + 2 >= off_out[b + 1]) b++;
+          find(loc, o + 2, b, off_in, off_out, entries);
+        }
+      }
+      F d;
+      fsub(d, x2, x1);
+      const bool rare = !common_case(cur.has2, x1, x2, d);
+      rare_hi = (rare_hi << 1) | (rare_lo >> 63);
+      rare_lo = (rare_lo << 1) | (rare ? 1u : 0u);
+      if (rare) {
+        F y1 = cur.p1->y, y2 = cur.p2->y;
+        fcneg(y1, y1, cur.neg1);
+        fcneg(y2, y2, cur.neg2);
+        classify_rare(d, cur.has2, x1, y1, x2, y2);
+      }
+      const size_t at = prefix_at(tid, T, o - beg);
+      prefix[at] = prod;
+      prefix[dstride + at] = d;
+      fmul(prod, prod, d);
+      if (o + 1 < end) { cur = nxt; x1 = nx1; x2 = nx2; }
     }
     F inv;
     finv(inv, prod);
-    // backward: inverse of each denominator, then the affine formulas
+    // backward: inverse of each denominator, then the affine formulas.  cur is the last output's item, b its bucket.
+    size_t at = prefix_at(tid, T, end - 1 - beg);
+    F pk = prefix[at], d = prefix[dstride + at];
+    if (end - 1 > beg) {
+      while (end - 2 < off_out[b]) b--;
+      find(loc, end - 2, b, off_in, off_out, entries);
+    }
     for (uint32_t o = end; o-- > beg;) {
-      while (o < off_out[b]) b--;
-      uint32_t j = o - off_out[b], i1 = off_in[b] + 2 * j;
-      bool has2 = i1 + 1 < off_in[b + 1];
-      Ops op;
-      op.p1 = item(i1, entries, src);
-      if (has2) op.p2 = item(i1 + 1, entries, src); else set_inf(op.p2);
-      classify(op, has2);
-      F pk = prefix[o], dinv, lam, t;
+      const Item me = cur;
+      F y1 = me.p1->y, y2 = me.p2->y, dinv, lam, t;
+      x1 = me.p1->x; x2 = me.p2->x;
       fmul(dinv, inv, pk);
-      fmul(inv, inv, op.d);
+      fmul(inv, inv, d);
+      if (FIRST) {
+        fcneg(y1, y1, me.neg1);
+        fcneg(y2, y2, me.neg2);
+      }
+      int kind = 0;
+      const bool rare = (rare_lo & 1u) != 0;
+      rare_lo = (rare_lo >> 1) | (rare_hi << 63);
+      rare_hi >>= 1;
+      if (rare) {
+        fsub(t, x2, x1);   // the raw difference decides the case (the stored d is 1 or 2y here)
+        kind = classify_rare(t, me.has2, x1, y1, x2, y2);
+      }
+      if (o > beg) {   // next output: its prefix / denominator three multiplications ahead of their use
+        resolve(cur, loc, src);
+        at = prefix_at(tid, T, o - 1 - beg);
+        pk = prefix[at]; d = prefix[dstride + at];
+        if (o - 1 > beg) {
+          while (o - 2 < off_out[b]) b--;
+          find(loc, o - 2, b, off_in, off_out, entries);
+        }
+      }
+      fsub(t, y2, y1);
+      if (kind == 1) { fmul(t, x1, x1); fdbl(lam, t); fadd(t, lam, t); x2 = x1; }   // tangent: 3 x^2 / 2 y
+      fmul(lam, t, dinv);
       Affine<F> r;
-      if (op.kind == 0 || op.kind == 1) {
-        if (op.kind == 0) fsub(t, op.p2.y, op.p1.y);
-        else { fsqr(t, op.p1.x); fdbl(lam, t); fadd(t, lam, t); }       // 3 x^2
-        fmul(lam, t, dinv);
-        fsqr(t, lam);
-        fsub(t, t, op.p1.x);
-        fsub(r.x, t, op.kind == 0 ? op.p2.x : op.p1.x);
-        fsub(t, op.p1.x, r.x);
-        fmul(t, lam, t);
-        fsub(r.y, t, op.p1.y);
-      } else if (op.kind == 2) r = op.p1;
-      else if (op.kind == 3) r = op.p2;
-      else set_inf(r);
+      fmul(t, lam, lam);
+      fsub(t, t, x1);
+      fsub(r.x, t, x2);
+      fsub(t, x1, r.x);
+      fmul(t, lam, t);
+      fsub(r.y, t, y1);
+      if (kind >= 2) {
+        if (kind == 2) { r.x = x1; r.y = y1; }
+        else if (kind == 3) { r.x = x2; r.y = y2; }
+        else set_inf(r);
+      }
       dst[o] = r;
-      if (entries_out) { Entry e; e.key = b; e.val = o; entries_out[o] = e; }
+      if (entries_out) { Entry e; e.key = me.b; e.val = o; entries_out[o] = e; }
     }
   }
 };
@@ -604,7 +700,9 @@ inline uint32_t msm_pick_c(uint32_t n, bool precomp, bool half = false) {
     uint32_t bits = half ? 254u : 255u, full = bits / c, tb = bits - full * c;
     double W = full + 1, B = (double)(1u << (c - 1));
     double entries = (double)n * (full + (tb == 0 ? 0.5 : 1.0 - 1.0 / (double)(1u << (tb > 30 ? 30 : tb))));
-    double cost = entries + 11.0 * B * (precomp ? 1.0 : W);
+    // per-bucket cost in units of one mixed addition: with precomputed slabs the single bucket set is reduced
+    // by the latency-bound cooperative tail (measured crossover ~6), otherwise W sets are work-bound (~11)
+    double cost = entries + (precomp ? 6.0 : 11.0) * B * (precomp ? 1.0 : W);
     if (2 * tb < c) cost += 0.5 * (double)n;   // carry-only or narrow top window: a few giant buckets
     if (cost < best_cost) { best_cost = cost; best = c; }
   }
@@ -625,6 +723,7 @@ inline MsmPlan msm_plan(uint32_t n, uint32_t c, bool precomp, uint32_t stride, b
   p.nb = p.nwin * p.B;
   p.stride = stride;
   p.max_entries = n * p.W;
+  p.acc_slots = acc_slots;
   p.L = p.max_entries >= (1u << 23) ? 32 : (p.max_entries >= (1u << 21) ? 16 : 8);
   if (acc_slots) {
     // Wave quantisation: every resident slot runs ceil(threads / slots) threads of L mixed additions one after the
@@ -641,10 +740,10 @@ inline MsmPlan msm_plan(uint32_t n, uint32_t c, bool precomp, uint32_t stride, b
   p.K = 2;                                   // per-thread reduction: ~16k threads, short chains, chip busy
   while (p.K < 64 && p.B / p.K > 16384) p.K *= 2;
   if (p.K > p.B) p.K = p.B;
-  p.batch_rounds = 0;
-  p.batch_T = 64;
+  p.batch_rounds = 0;                        // see msm_default_batch_rounds()
+  p.batch_T = 128;
   if (const char* e = getenv("ZKMSM_BATCH_ROUNDS")) { uint32_t v = (uint32_t)atoi(e); if (v <= 8) p.batch_rounds = v; }
-  if (const char* e = getenv("ZKMSM_BATCH_T")) { uint32_t v = (uint32_t)atoi(e); if (v >= 2 && v <= 1024) p.batch_T = v; }
+  if (const char* e = getenv("ZKMSM_BATCH_T")) { uint32_t v = (uint32_t)atoi(e); if (v >= 2 && v <= 128) p.batch_T = v; }   // <= 128: one flag bit per output in two words
   p.coop = 0;
   if (coop_tail) {
     // cooperative reduction: 32 chains per 4-warp block, aim at <= ~one block per SM (148 x 32 = 4736 chains) so
@@ -668,6 +767,37 @@ inline size_t msm_partial_slots(const MsmPlan& p) {
   return total + 1;
 }
 
+// Rounds of batched-affine pre-reduction for a G1 set with precomputed slabs on a real device (measured on B200,
+// profiles/r1_batched_affine.log): an affine addition sharing its inversion costs ~0.29 ns against 0.31 ns for
+// the XYZZ mixed addition, so the rounds pay once the buckets are large and the per-round fixed costs (pair
+// count, scan, launch) are amortised; below 2^18 terms they do not.  The scratch (~300 bytes per pair) is capped.
+inline uint32_t msm_default_batch_rounds(const MsmPlan& p) {
+  if (!p.precomp || !p.acc_slots || p.n < (1u << 18)) return 0;
+  if ((uint64_t)p.max_entries / 2 * 300 > (40ull << 30)) return 0;
+  const uint32_t per_bucket = p.max_entries / p.nb;
+  if (per_bucket < 100) return 0;
+  if (p.n < (1u << 19)) return 2;
+  return per_bucket >= 200 ? 4 : 3;
+}
+
+// items a batched-affine round can leave (every bucket rounds up), and the prefix-product scratch: a block of
+// 128 threads owns 128 * T consecutive slots, so the last block may reach past the item count
+inline size_t msm_pre_slots(const MsmPlan& p) { return (size_t)(p.max_entries + 1) / 2 + p.nb + 1; }
+inline size_t msm_prefix_slots(const MsmPlan& p) { return msm_pre_slots(p) + (size_t)129 * p.batch_T; }
+// additions per thread in a round with about `items` outputs: whole waves of the resident threads (2 blocks of
+// 128 per SM, like Accumulate), at most p.batch_T and at least a quarter of it
+inline uint32_t msm_batch_T(const MsmPlan& p, uint64_t items) {
+  if (!p.acc_slots) return p.batch_T;
+  uint64_t half_blocks = 3;   // resident blocks per SM of the batched kernel (tuning override for A/B builds)
+  if (const char* e = getenv("ZKMSM_BATCH_BLOCKS")) { int v = atoi(e); if (v >= 1 && v <= 8) half_blocks = (uint64_t)v; }
+  const uint64_t slots = (uint64_t)p.acc_slots * half_blocks / 2;
+  uint32_t lo = p.batch_T / 4 ? p.batch_T / 4 : 1;
+  for (uint64_t waves = 1;; waves++) {
+    uint64_t t = (items + waves * slots - 1) / (waves * slots);
+    if (t <= p.batch_T) return t < lo ? lo : (uint32_t)t;
+  }
+}
+
 // chunk sums of the bucket reduction (nwin rows of B / K) + scratch rows of the window tree
 inline size_t msm_reduced_slots(const MsmPlan& p) {
   size_t chunks = p.B / p.K;
@@ -686,7 +816,7 @@ template <class C> struct MsmBuffers {
   uint32_t* partial_keys;  // same count
   // batched-affine pre-reduction (p.batch_rounds > 0): ping-pong point / offset buffers, prefix scratch
   Affine<F>* pre_pts[2];   // ceil(max_entries / 2) + nb each
-  F* pre_prefix;           // ceil(max_entries / 2) + nb
+  F* pre_prefix;           // 2 * msm_prefix_slots(): prefix products, then the denominators
   uint32_t* pre_off[2];    // nb + 1 each
   uint32_t* pre_cnt;       // nb
   Entry* pre_entries;      // ceil(max_entries / 2) + nb
@@ -710,21 +840,25 @@ void msm_launch(Exec& ex, const MsmPlan& p, const MsmBuffers<C>& b, const Affine
   const Affine<typename C::F>* acc_points = points;
   if (p.batch_rounds > 0) {
     typedef typename C::F F;
-    const uint32_t max_out = (p.max_entries + 1) / 2 + p.nb, threads = (max_out + p.batch_T - 1) / p.batch_T;
+    uint64_t items = p.max_entries;
     const uint32_t* off_in = b.offsets;
     const Affine<F>* src = points;
     for (uint32_t r = 0; r < p.batch_rounds; r++) {
       uint32_t* off_out = b.pre_off[r & 1];
       Affine<F>* dst = b.pre_pts[r & 1];
       bool last = r + 1 == p.batch_rounds;
+      items = (items + 1) / 2 + p.nb;                 // upper bound of this round's outputs
+      MsmPlan pr = p;
+      pr.batch_T = msm_batch_T(p, items);
+      const uint32_t threads = (uint32_t)((items + pr.batch_T - 1) / pr.batch_T);
       ex.template launch<PairCount>(p.nb, p.nb, off_in, b.pre_cnt);
       ex.exclusive_scan(p.nb, b.pre_cnt, off_out, b.segsum);
       if (r == 0)
-        ex.template launch<BatchedAddRound<C, true>>(threads, p, off_in, (const uint32_t*)off_out, (const Entry*)b.entries, src, dst,
-                                                     b.pre_prefix, last ? b.pre_entries : (Entry*)nullptr);
+        ex.template launch<BatchedAddRound<C, true>>(threads, pr, off_in, (const uint32_t*)off_out, (const Entry*)b.entries, src, dst,
+                                                     b.pre_prefix, msm_prefix_slots(p), last ? b.pre_entries : (Entry*)nullptr);
       else
-        ex.template launch<BatchedAddRound<C, false>>(threads, p, off_in, (const uint32_t*)off_out, (const Entry*)nullptr, src, dst,
-                                                      b.pre_prefix, last ? b.pre_entries : (Entry*)nullptr);
+        ex.template launch<BatchedAddRound<C, false>>(threads, pr, off_in, (const uint32_t*)off_out, (const Entry*)nullptr, src, dst,
+                                                      b.pre_prefix, msm_prefix_slots(p), last ? b.pre_entries : (Entry*)nullptr);
       off_in = off_out;
       src = dst;
     }
@@ -733,11 +867,25 @@ void msm_launch(Exec& ex, const MsmPlan& p, const MsmBuffers<C>& b, const Affine
     acc_points = src;
   }
   MsmPlan pa = p;
-  if (p.batch_rounds > 0) pa.precomp = 0;   // the pre-reduced items are addressed directly
-  ex.template launch<Accumulate<C>>(p.acc_threads, pa, acc_offsets, acc_entries, acc_points, b.bucket_sums, b.partials,
+  if (p.batch_rounds > 0) {
+    pa.precomp = 0;   // the pre-reduced items are addressed directly
+    // far fewer items are left: shorter chunks keep about two waves of threads busy (never more threads than
+    // the partial-sum buffers were sized for)
+    uint64_t left = p.max_entries;
+    for (uint32_t r = 0; r < p.batch_rounds; r++) left = (left + 1) / 2 + p.nb;
+    uint64_t l = p.acc_slots ? left / (2ull * p.acc_slots) : p.L;
+    uint64_t lmin = (left * p.L + p.max_entries - 1) / p.max_entries;
+    if (l < 4) l = 4;
+    if (l < lmin) l = lmin;
+    if (l > p.L) l = p.L;
+    pa.L = (uint32_t)l;
+    pa.acc_threads = (uint32_t)((left + pa.L - 1) / pa.L);
+    if (pa.acc_threads > p.acc_threads) { pa.L = p.L; pa.acc_threads = p.acc_threads; }
+  }
+  ex.template launch<Accumulate<C>>(pa.acc_threads, pa, acc_offsets, acc_entries, acc_points, b.bucket_sums, b.partials,
                                     b.partial_keys);
   {  // fix-up tree over the per-chunk partial sums: level l reads region l, writes region l+1
-    uint32_t count = p.acc_threads, level = 0;
+    uint32_t count = pa.acc_threads, level = 0;
     XYZZ<typename C::F>* pin = b.partials;
     uint32_t* kin = b.partial_keys;
     while (count > 1) {

@@ -337,10 +337,11 @@ static int msm_enqueue_impl(zkmsm_ctx* ctx, const zkmsm_points* ps, const uint32
   MsmBuffers<C> b;
   memset(&b, 0, sizeof(b));
   if (curve != 1) p.batch_rounds = 0;   // the pre-reduction is built for G1 only
+  else if (!getenv("ZKMSM_BATCH_ROUNDS")) p.batch_rounds = msm_default_batch_rounds(p);
   if (p.batch_rounds > 0) {
-    size_t pre_n = (size_t)(p.max_entries + 1) / 2 + p.nb + 1;
+    size_t pre_n = msm_pre_slots(p);
     if ((rc = ws_reserve(ctx, WS_PRE_A, sizeof(Affine<F>) * pre_n)) || (rc = ws_reserve(ctx, WS_PRE_B, sizeof(Affine<F>) * pre_n)) ||
-        (rc = ws_reserve(ctx, WS_PRE_PREFIX, sizeof(F) * pre_n)) || (rc = ws_reserve(ctx, WS_PRE_OFF, sizeof(uint32_t) * 3 * ((size_t)p.nb + 4))) ||
+        (rc = ws_reserve(ctx, WS_PRE_PREFIX, sizeof(F) * 2 * msm_prefix_slots(p))) || (rc = ws_reserve(ctx, WS_PRE_OFF, sizeof(uint32_t) * 3 * ((size_t)p.nb + 4))) ||
         (rc = ws_reserve(ctx, WS_PRE_ENTRIES, sizeof(Entry) * pre_n)))
       return rc;
     b.pre_pts[0] = (Affine<F>*)ctx->ws[WS_PRE_A];
