@@ -775,9 +775,11 @@ inline uint32_t msm_default_batch_rounds(const MsmPlan& p) {
   if (!p.precomp || !p.acc_slots || p.n < (1u << 18)) return 0;
   if ((uint64_t)p.max_entries / 2 * 300 > (40ull << 30)) return 0;
   const uint32_t per_bucket = p.max_entries / p.nb;
-  if (per_bucket < 100) return 0;
-  if (p.n < (1u << 19)) return 2;
-  return per_bucket >= 200 ? 4 : 3;
+  if (p.n < (1u << 19)) return per_bucket >= 100 ? 2 : 0;
+  if (per_bucket < 40) return 0;
+  uint32_t r = 0;
+  while ((12u << (r + 1)) <= per_bucket) r++;           // floor(log2(per_bucket / 12)): ~12-24 entries left
+  return r < 2 ? 2 : (r > 4 ? 4 : r);
 }
 
 // items a batched-affine round can leave (every bucket rounds up), and the prefix-product scratch: a block of
