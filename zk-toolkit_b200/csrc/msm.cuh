@@ -9,11 +9,13 @@
 //   1 RecodeCount   scalar -> W signed c-bit digits; histogram of bucket sizes (atomics)
 //   2 Scan*         exclusive scan of the histogram -> bucket offsets, scatter cursors
 //   3 Scatter       counting sort: (bucket, +-point index) pairs grouped by bucket
+//   3b BatchedAddRound  (large G1 sets) R rounds of pairwise affine additions per bucket, the inversions of T
+//                   additions shared by Montgomery's trick; 2^R times fewer items reach stage 4
 //   4 Accumulate    fixed-size chunks of L sorted pairs per thread, XYZZ mixed adds; a bucket
 //                   that spans several chunks leaves one head sum + per-chunk partial sums
 //   5 FixupLevel    16-ary tree over the per-chunk partial sums -> complete bucket sums
 //   6 BucketReduce  per K consecutive buckets: sum_j (j+1) * bucket_j by running sums
-//   7 PairSum       pairwise tree over the chunk results of each window -> window sums
+//   7 window tree   chunk results of each window -> window sums (coop::row_sum_kernel; PairSum for wide levels)
 //   8 Finish        Horner over windows (c doublings each), to canonical affine
 //
 // Work is independent of the scalar distribution: stage 4 always runs ceil(total/L) threads of
