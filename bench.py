@@ -345,6 +345,13 @@ def main():
         left = 0.5 ** batch_rounds
         roofline["actual_lp_per_point"] = round(info["windows"] * ((1 - left) * 1800 + left * 3000))
         roofline["batched_affine_rounds"] = batch_rounds
+        if achieved and lp_peak:
+            # frac above counts the CANONICAL 48 000 LP per point and can exceed 1 once the
+            # algorithm executes fewer products than that; this is what the multiplier pipe really does
+            ex = achieved * roofline["actual_lp_per_point"] / LP_PER_G1_POINT
+            roofline["executed"] = {"T_lp_per_s": round(ex / 1e12, 3), "frac_of_peak": round(ex / lp_peak, 4),
+                                    "note": "limb products actually issued by the accumulation group / its time; "
+                                            "ncu sm__pipe_fmaheavy_cycles_active of the same kernels is in profiles/"}
         roofline["window_bits"] = info["c"]
 
     # ---- CPU baseline beside it (rank 0, N = 1 only): the reference algorithm on a bounded sample

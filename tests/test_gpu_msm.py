@@ -286,7 +286,8 @@ def test_begin_result_and_points_info(z, ctx):
 
 
 def test_batched_affine_prereduction_option(z, ctx, monkeypatch):
-    """ZKMSM_BATCH_ROUNDS > 0 (experimental stage, off by default): identical results"""
+    """batched-affine pre-reduction rounds forced on small inputs (ZKMSM_BATCH_ROUNDS / ZKMSM_BATCH_T): identical
+    results, including P + P (tangent), P + (-P), AtInfinity operands and odd leftovers inside the rounds"""
     n = 6000
     rnd = random.Random(31)
     dlogs = [rnd.randrange(1, O.R) for _ in range(n)]
@@ -294,13 +295,42 @@ def test_batched_affine_prereduction_option(z, ctx, monkeypatch):
     exp = U.expected_from_dlogs(O.G1_GEN, dlogs, sc)
     for pre in (False, True):
         pts = z.G1Points.generator_multiples(dlogs, precompute=pre)
-        for rounds in (1, 3):
+        for rounds, T in ((1, 128), (3, 7), (4, 64)):
             monkeypatch.setenv("ZKMSM_BATCH_ROUNDS", str(rounds))
+            monkeypatch.setenv("ZKMSM_BATCH_T", str(T))
             out, inf = ctx.msm(pts.set, z.scalars_to_array(sc))
             assert U.g1_from_array(out, inf) == exp
         monkeypatch.delenv("ZKMSM_BATCH_ROUNDS")
     monkeypatch.setenv("ZKMSM_BATCH_ROUNDS", "2")
+    monkeypatch.setenv("ZKMSM_BATCH_T", "5")
     g = z.G1Point.g()
     dup = z.G1Points([g * 7] * 40)
     out, inf = ctx.msm(dup.set, z.scalars_to_array([5] * 40))
     assert U.g1_from_array(out, inf) == O.scalar_mul(O.G1_GEN, 7 * 5 * 40)
+    P, Q = g * 11, g * 13
+    opp = z.G1Points([P, -P, Q, -Q, P, -P])
+    out, inf = ctx.msm(opp.set, z.scalars_to_array([9, 9, 11, 11, 3, 3]))
+    assert U.g1_from_array(out, inf) == O.INF
+    withinf = z.G1Points([P, z.G1Point.zero(), Q, z.G1Point.zero(), g * 17, P])
+    scs = [5, 5, 5, 5, 5, 5]
+    out, inf = ctx.msm(withinf.set, z.scalars_to_array(scs))
+    assert U.g1_from_array(out, inf) == O.scalar_mul(O.G1_GEN, 5 * (11 + 13 + 17 + 11))
+
+
+def test_default_batched_path_at_2p19(z, ctx):
+    """n = 2^19 with resident CRS tables takes the default batched-affine rounds (msm_default_batch_rounds): the
+    stage profile shows them and the result has its closed form; duplicates of one point in one bucket too"""
+    n = 1 << 19
+    rnd = random.Random(519)
+    dlogs = [rnd.randrange(1, O.R) for _ in range(n)]
+    pts = z.G1Points.generator_multiples(dlogs, precompute=True)
+    sc = U.rand_scalars(rnd, n)
+    ctx.profile(True)
+    out, inf = ctx.msm(pts.set, z.scalars_to_array(sc))
+    names = [name for name, _, _ in ctx.profile_read()]
+    ctx.profile(False)
+    assert "batched_add_first" in names and "batched_add" in names and "accumulate" in names
+    assert U.g1_from_array(out, inf) == U.expected_from_dlogs(O.G1_GEN, dlogs, sc)
+    same = [12345] * n                                   # every term lands in the same buckets: long runs of pairs
+    out, inf = ctx.msm(pts.set, z.scalars_to_array(same))
+    assert U.g1_from_array(out, inf) == U.expected_from_dlogs(O.G1_GEN, dlogs, same)
