@@ -336,7 +336,7 @@ static int msm_enqueue_impl(zkmsm_ctx* ctx, const zkmsm_points* ps, const uint32
     return rc;
   MsmBuffers<C> b;
   memset(&b, 0, sizeof(b));
-  if (curve != 1) p.batch_rounds = 0;   // the pre-reduction is built for G1 only
+  if (curve != 1) { if (!getenv("ZKMSM_BATCH_G2")) p.batch_rounds = 0; }   // G2: off unless forced (the Fq2 kernel spills)
   else if (!getenv("ZKMSM_BATCH_ROUNDS")) p.batch_rounds = msm_default_batch_rounds(p);
   if (p.batch_rounds > 0) {
     size_t pre_n = msm_pre_slots(p);
