@@ -167,7 +167,9 @@ int zkmsm_fr_aggregate(zkmsm_ctx* ctx, const uint32_t* polys, size_t n_wires, si
  * QAP::build_t (qap.rs:115-135); schoolbook product and long division as the reference (polynomial.rs:173-238).
  * u, v, w: n coefficients each (8 words, canonical, zero padded; coefficient i multiplies x^i); h_out: n-1
  * coefficients; *out_exact = 0 when the division leaves a remainder (the reference panics "p should be
- * divisible by t").  2 <= n <= 2^14. */
+ * divisible by t").  2 <= n <= 2^22.  From 32 coefficients on the division runs on number-theoretic transforms
+ * (O(n log n); the tables for n are built on the first call and kept in the context); the coefficients are those of
+ * the reference's schoolbook product and long division, which remain the path below 32 and the cross-check. */
 int zkmsm_fr_quotient(zkmsm_ctx* ctx, const uint32_t* u, const uint32_t* v, const uint32_t* w, size_t n,
                       uint32_t* h_out, int* out_exact);
 

@@ -8,6 +8,7 @@
 #include <vector>
 #include "../../zk-toolkit_b200/csrc/msm.cuh"
 #include "../../zk-toolkit_b200/csrc/fr_ops.cuh"
+#include "../../zk-toolkit_b200/csrc/fr_ntt.cuh"
 
 using namespace zk;
 
@@ -165,6 +166,21 @@ int emu_fr_quotient(const uint32_t* u, const uint32_t* v, const uint32_t* w, uin
   *nonzero_rem = 0;
   ex.launch<FrQuotientOut>(n, n, (const Fr*)dh.data(), (const Fr*)dp.data(), h_out, nonzero_rem);
   return 0;
+}
+// the transform-based quotient (fr_ntt.cuh): same pipeline as zkmsm_fr_quotient's n >= 32 path
+int emu_fr_quotient_ntt(const uint32_t* u, const uint32_t* v, const uint32_t* w, uint32_t n, uint32_t* h_out, uint32_t* nonzero_rem,
+                        uint32_t* t_out) {
+  HostExec ex;
+  const FrNttPlan p = FrNttPlan::make(n);
+  std::vector<Fr> tables(fr_ntt_table_elems(p)), scratch(5 * (size_t)p.m);
+  FrNttTables tb;
+  fr_ntt_tables_at(tb, p, tables.data());
+  fr_quotient_setup(ex, p, tb, scratch.data());
+  if (t_out)
+    for (uint32_t i = 0; i <= n; i++) ffrom_mont(t_out + (size_t)i * 8, tb.t[i]);
+  *nonzero_rem = 0;
+  fr_quotient_run(ex, p, tb, u, v, w, scratch.data(), h_out, nonzero_rem);
+  return ex.launches;
 }
 void emu_plan(uint32_t n, uint32_t c, int precomp, uint32_t* out) {
   if (c == 0) c = msm_pick_c(n, precomp != 0);

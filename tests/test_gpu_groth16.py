@@ -122,6 +122,37 @@ def test_fr_quotient_matches_oracle(z):
     assert G.quotient(uu, vv, remc, n) == (q.coeffs + [0] * n)[:n - 1]
 
 
+def test_fr_quotient_transforms_vs_schoolbook_and_identity(z, monkeypatch):
+    """the transform path of zkmsm_fr_quotient (n >= 32) against the reference-style schoolbook path forced by
+    ZKMSM_QUOTIENT_SCHOOLBOOK, and the defining identity u v - w == h t checked with Python integers at n = 1024"""
+    ctx = z.default_context()
+    rnd = random.Random(77)
+    for n in (32, 33, 1000, 2048):
+        u, v, w = ([rnd.randrange(O.R) for _ in range(n)] for _ in range(3))
+        arrs = [z.scalars_to_array(x) for x in (u, v, w)]
+        h1, exact1 = ctx.fr_quotient(*arrs)
+        monkeypatch.setenv("ZKMSM_QUOTIENT_SCHOOLBOOK", "1")
+        h2, exact2 = ctx.fr_quotient(*arrs)
+        monkeypatch.delenv("ZKMSM_QUOTIENT_SCHOOLBOOK")
+        assert h1.tolist() == h2.tolist() and exact1 == exact2 == False   # random w: Euclidean quotient + remainder
+    n = 1024
+    t = O.qap_build_t(n).coeffs
+    u, v = ([rnd.randrange(O.R) for _ in range(n)] for _ in range(2))
+    h0, _ = ctx.fr_quotient(z.scalars_to_array(u), z.scalars_to_array(v), z.scalars_to_array([0] * n))
+    h0 = [sum(int(x) << (32 * k) for k, x in enumerate(r)) for r in h0]
+    p = [0] * (2 * n - 1)
+    for i, a in enumerate(u):
+        for j, b in enumerate(v):
+            p[i + j] += a * b
+    for i, a in enumerate(h0):
+        for j, b in enumerate(t):
+            p[i + j] -= a * b
+    p = [x % O.R for x in p]
+    assert not any(p[n:])                                        # u v - h t has degree < n: h0 is the quotient
+    h, exact = ctx.fr_quotient(z.scalars_to_array(u), z.scalars_to_array(v), z.scalars_to_array(p[:n]))
+    assert exact and [sum(int(x) << (32 * k) for k, x in enumerate(r)) for r in h] == h0
+
+
 def test_pinocchio_proof_identical_to_oracle_and_verifies(z):
     """pinocchio/prover.rs:178-211: the same circuit through Pinocchio; all nine proof elements must equal the
     oracle's restatement and pass the restated verifier (verifier.rs:27-87)."""

@@ -245,3 +245,43 @@ def test_emu_fr_quotient(lib):
         remc = (rem.coeffs if rem is not None else [0]) + [0] * n
         got, exact = run(uu, vv, remc[:n])
         assert exact and got == (q.coeffs + [0] * n)[:n - 1]
+
+
+@pytest.mark.parametrize("n", [2, 3, 5, 8, 9, 33, 64, 100])
+def test_emu_fr_quotient_by_transforms(lib, n):
+    """the O(n log n) quotient (fr_ntt.cuh: product tree for t, Newton inverse of rev(t), 7 transforms per proof)
+    against the oracle's schoolbook multiplication / long division (polynomial.rs:173-238) and against the
+    reference-style device path: t itself, exact instances, and an instance with a remainder"""
+    rnd = random.Random(900 + n)
+    t = O.qap_build_t(n)
+
+    def run(u, v, w):
+        out = np.zeros((max(n - 1, 1), 8), dtype=np.uint32)
+        tt = np.zeros((n + 1, 8), dtype=np.uint32)
+        flag = ctypes.c_uint32(0)
+        lib.emu_fr_quotient_ntt(ptr(U.scalars_to_array(u)), ptr(U.scalars_to_array(v)), ptr(U.scalars_to_array(w)), n, ptr(out),
+                                ctypes.byref(flag), ptr(tt))
+        return [U.limbs_to_int(r) for r in out][:n - 1], flag.value == 0, [U.limbs_to_int(r) for r in tt]
+
+    for trial in range(3):
+        uu = [rnd.randrange(O.R) for _ in range(n)]
+        vv = [rnd.randrange(O.R) for _ in range(n)]
+        if trial == 2:
+            uu[-1] = 0                                           # product of lower degree than 2n - 2
+        uv = O.Polynomial(uu, normalize=False).multiply_by(O.Polynomial(vv, normalize=False))
+        q, rem = uv.divide_by(t)
+        remc = (rem.coeffs if rem is not None else [0]) + [0] * n
+        qc = ((q.coeffs if q is not None else [0]) + [0] * n)[:n - 1]
+        got, exact, tt = run(uu, vv, remc[:n])
+        assert tt == (t.coeffs + [0] * (n + 1))[:n + 1]
+        assert exact and got == qc
+        w_bad = list(remc[:n]); w_bad[rnd.randrange(n)] = (w_bad[0] + 1 + rnd.randrange(O.R - 1)) % O.R
+        if w_bad != remc[:n]:
+            got2, exact2, _ = run(uu, vv, w_bad)
+            assert exact2 is False and got2 == qc                  # same Euclidean quotient, remainder reported
+        # the schoolbook device path gives the same coefficients
+        out = np.zeros((max(n - 1, 1), 8), dtype=np.uint32)
+        flag = ctypes.c_uint32(0)
+        lib.emu_fr_quotient(ptr(U.scalars_to_array(uu)), ptr(U.scalars_to_array(vv)), ptr(U.scalars_to_array(remc[:n])), n, ptr(out),
+                            ctypes.byref(flag))
+        assert [U.limbs_to_int(r) for r in out][:n - 1] == qc and flag.value == 0

@@ -12,6 +12,7 @@
 #include "launch.cuh"
 #include "msm.cuh"
 #include "fr_ops.cuh"
+#include "fr_ntt.cuh"
 
 using namespace zk;
 
@@ -42,6 +43,8 @@ struct zkmsm_ctx {
   int pending;          // 0 none, 1 kernels enqueued, 2 trivially infinity (n == 0)
   int pending_words;    // 24 or 48
   LaunchProfile* prof;  // non-null while profiling is enabled
+  Fr* ntt_tables;       // quotient polynomial: twiddles, transforms of t and of rev(t)^-1 for ntt_n (fr_ntt.cuh)
+  size_t ntt_n;
 };
 
 struct zkmsm_points {
@@ -124,6 +127,7 @@ extern "C" int zkmsm_destroy(zkmsm_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   for (int i = 0; i < WS_COUNT; i++)
     if (ctx->ws[i]) cudaFree(ctx->ws[i]);
+  if (ctx->ntt_tables) cudaFree(ctx->ntt_tables);
   if (ctx->prof) zkmsm_profile(ctx, 0);
   cudaFree(ctx->d_res);
   cudaFreeHost(ctx->h_res);
@@ -659,12 +663,63 @@ extern "C" int zkmsm_fr_aggregate(zkmsm_ctx* ctx, const uint32_t* polys, size_t 
   return ZKMSM_OK;
 }
 
+// quotient polynomial by transforms (fr_ntt.cuh): tables for n are built on first use and kept in the context
+static int fr_quotient_ntt(zkmsm_ctx* ctx, const uint32_t* u, const uint32_t* v, const uint32_t* w, size_t n,
+                           uint32_t* h_out, int* out_exact) {
+  const FrNttPlan p = FrNttPlan::make((uint32_t)n);
+  const size_t in_bytes = sizeof(uint32_t) * 8 * n, m = p.m;
+  // WS_MISC: raw u | v | w | out (n x 8 words each), flag, then 5 m Fr of scratch
+  size_t off_fr = (4 * in_bytes + 256 + 31) / 32 * 32;
+  int rc = ws_reserve(ctx, WS_MISC, off_fr + sizeof(Fr) * 5 * m);
+  if (rc) return rc;
+  char* base = (char*)ctx->ws[WS_MISC];
+  uint32_t* d_raw = (uint32_t*)base;
+  uint32_t* d_out = d_raw + 24 * n;
+  uint32_t* d_flag = d_raw + 32 * n;
+  Fr* scratch = (Fr*)(base + off_fr);
+  CudaExec ex(ctx->stream);
+  FrNttTables tb;
+  if (ctx->ntt_n != n) {
+    if (ctx->ntt_tables) { CU(ctx, cudaStreamSynchronize(ctx->stream)); cudaFree(ctx->ntt_tables); ctx->ntt_tables = nullptr; }
+    ctx->ntt_n = 0;
+    if (cudaMalloc(&ctx->ntt_tables, sizeof(Fr) * fr_ntt_table_elems(p)) != cudaSuccess) {
+      cudaGetLastError();
+      ctx->ntt_tables = nullptr;
+      return fail(ctx, ZKMSM_ERR_NOMEM, "fr_quotient: out of device memory for the transform tables");
+    }
+    fr_ntt_tables_at(tb, p, ctx->ntt_tables);
+    fr_quotient_setup(ex, p, tb, scratch);
+    if (ex.err != cudaSuccess) return fail(ctx, ZKMSM_ERR_CUDA, "fr_quotient setup: %s", cudaGetErrorString(ex.err));
+    ctx->ntt_n = n;
+  }
+  fr_ntt_tables_at(tb, p, ctx->ntt_tables);
+  CU(ctx, cudaMemcpyAsync(d_raw, u, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  CU(ctx, cudaMemcpyAsync(d_raw + 8 * n, v, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  CU(ctx, cudaMemcpyAsync(d_raw + 16 * n, w, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  CU(ctx, cudaMemsetAsync(d_flag, 0, sizeof(uint32_t), ctx->stream));
+  fr_quotient_run(ex, p, tb, (const uint32_t*)d_raw, (const uint32_t*)(d_raw + 8 * n), (const uint32_t*)(d_raw + 16 * n), scratch,
+                  d_out, d_flag);
+  if (ex.err != cudaSuccess) return fail(ctx, ZKMSM_ERR_CUDA, "fr_quotient: %s", cudaGetErrorString(ex.err));
+  ctx->last_launches = ex.launches;
+  uint32_t flag = 0;
+  CU(ctx, cudaMemcpyAsync(h_out, d_out, sizeof(uint32_t) * 8 * (n - 1), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(ctx, cudaMemcpyAsync(&flag, d_flag, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  *out_exact = flag ? 0 : 1;
+  return ZKMSM_OK;
+}
+
 // quotient polynomial h = (u v - w) / t,  t = prod_{k=1..n} (x - k)
 extern "C" int zkmsm_fr_quotient(zkmsm_ctx* ctx, const uint32_t* u, const uint32_t* v, const uint32_t* w, size_t n,
                                  uint32_t* h_out, int* out_exact) {
-  if (!ctx || !u || !v || !w || !h_out || !out_exact || n < 2 || n > (1u << 14))
-    return fail(ctx, ZKMSM_ERR_INVALID_ARG, "bad argument (2 <= n <= 2^14)");
+  if (!ctx || !u || !v || !w || !h_out || !out_exact || n < 2 || n > (1u << 22))
+    return fail(ctx, ZKMSM_ERR_INVALID_ARG, "bad argument (2 <= n <= 2^22)");
   CU(ctx, cudaSetDevice(ctx->device));
+  // transforms from 32 coefficients on; below that (and on request, as the cross-check) the reference's schoolbook
+  // multiplication and long division, one launch per step
+  const bool schoolbook = getenv("ZKMSM_QUOTIENT_SCHOOLBOOK") != nullptr;
+  if (n >= 32 && !schoolbook) return fr_quotient_ntt(ctx, u, v, w, n, h_out, out_exact);
+  if (n > (1u << 14)) return fail(ctx, ZKMSM_ERR_INVALID_ARG, "schoolbook quotient: n <= 2^14");
   const size_t in_bytes = sizeof(uint32_t) * 8 * n;
   // layout in WS_MISC: raw u | v | w, then Fr arrays u, v, w (n each), p (2n), t0, t1 (n+1 each), h (n), flag
   size_t off_raw = 0, off_fr = 3 * in_bytes;
