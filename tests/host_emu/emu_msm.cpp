@@ -39,6 +39,7 @@ struct HostExec {
                                  XYZZ<typename C::F>* out_xyzz, uint32_t* out_affine, uint32_t* out_inf) {
     launch<Finish<C>>(1u, nwin, pitch, c, arr, out_xyzz, out_affine, out_inf);
   }
+  bool ntt_fused(bool, Fr*, uint32_t, uint32_t, uint32_t, const Fr*, uint32_t) { return false; }   // per-stage bodies
   void exclusive_scan(uint32_t nb, uint32_t* hist_cursor, uint32_t* offsets, uint32_t* segsum) {
     uint32_t nseg = (nb + SCAN_SEG - 1) / SCAN_SEG;
     launch<ScanLocal>(nseg, nb, (const uint32_t*)hist_cursor, segsum);

@@ -18,9 +18,15 @@ for logn in [int(x) for x in (sys.argv[1] if len(sys.argv) > 1 else "10,14,16,18
     ts = []
     for _ in range(3):
         s = time.perf_counter(); ctx.fr_quotient(*arrs); ts.append(time.perf_counter() - s)
+    ctx.profile(True); ctx.fr_quotient(*arrs); prof = ctx.profile_read(); ctx.profile(False)
+    agg = {}
+    for name, ms, _ in prof:
+        a = agg.setdefault(name, [0, 0.0]); a[0] += 1; a[1] += ms
+    kern = sum(v[1] for v in agg.values())
+    detail = ", ".join(f"{k} x{c} {ms:.3f}" for k, (c, ms) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:6])
     line = f"n=2^{logn}: first call (tables + proof) {1e3 * (t1 - t0):.2f} ms, then {1e3 * min(ts):.2f} ms per quotient (host buffers in, host out)"
     if logn <= 13:
         os.environ["ZKMSM_QUOTIENT_SCHOOLBOOK"] = "1"
         s = time.perf_counter(); ctx.fr_quotient(*arrs); line += f"; schoolbook path {1e3 * (time.perf_counter() - s):.1f} ms"
         del os.environ["ZKMSM_QUOTIENT_SCHOOLBOOK"]
-    print(line, flush=True)
+    print(line + f"; kernels {kern:.3f} ms in {len(prof)} launches ({detail})", flush=True)

@@ -259,15 +259,46 @@ static inline void fr_ntt_tables_at(FrNttTables& tb, const FrNttPlan& p, Fr* bas
   tb.t = tb.ihat + p.m;
 }
 
+// A transform of 2^q points is cut into passes of up to 8 stages: block lengths 2^q .. 2^9 in strided passes, the
+// last 8 stages (contiguous blocks of 256) in one local pass.  Exec::ntt_fused runs a pass through shared memory
+// (tu_fr_ntt.cu) or reports that it cannot (CPU emulation, small or oddly shaped batches): then the stages of
+// the pass are launched one by one.
+struct FrNttPass { uint32_t len, k; };
+static inline int fr_ntt_passes(uint32_t size, FrNttPass* out) {
+  int n = 0;
+  uint32_t len = size;
+  while (len >= 2) {
+    uint32_t lg = 0;
+    while ((1u << lg) < len) lg++;
+    uint32_t k = lg <= 8 ? lg : (lg - 8 < 8 ? lg - 8 : 8);
+    out[n].len = len; out[n].k = k; n++;
+    len >>= k;
+  }
+  return n;
+}
 // forward transform of `total / size` concatenated blocks of `size` (natural -> bit-reversed)
 template <class Exec> void fr_ntt_forward(Exec& ex, const FrNttPlan& p, const FrNttTables& tb, Fr* a, uint32_t total, uint32_t size) {
-  for (uint32_t len = size; len >= 2; len >>= 1)
-    ex.template launch<FrNttDif>(total / 2, total / 2, len, p.m / len, (const Fr*)tb.tw, a);
+  FrNttPass pass[8];
+  const int np = fr_ntt_passes(size, pass);
+  for (int i = 0; i < np; i++) {
+    if (ex.ntt_fused(false, a, total, pass[i].len, pass[i].k, (const Fr*)tb.tw, p.m)) continue;
+    for (uint32_t s = 0; s < pass[i].k; s++) {
+      uint32_t len = pass[i].len >> s;
+      ex.template launch<FrNttDif>(total / 2, total / 2, len, p.m / len, (const Fr*)tb.tw, a);
+    }
+  }
 }
 // inverse (bit-reversed -> natural), scaled by 1 / size
 template <class Exec> void fr_ntt_inverse(Exec& ex, const FrNttPlan& p, const FrNttTables& tb, Fr* a, uint32_t total, uint32_t size) {
-  for (uint32_t len = 2; len <= size; len <<= 1)
-    ex.template launch<FrNttDit>(total / 2, total / 2, len, p.m / len, (const Fr*)tb.twi, a);
+  FrNttPass pass[8];
+  const int np = fr_ntt_passes(size, pass);
+  for (int i = np - 1; i >= 0; i--) {
+    if (ex.ntt_fused(true, a, total, pass[i].len, pass[i].k, (const Fr*)tb.twi, p.m)) continue;
+    for (uint32_t s = pass[i].k; s-- > 0;) {
+      uint32_t len = pass[i].len >> s;
+      ex.template launch<FrNttDit>(total / 2, total / 2, len, p.m / len, (const Fr*)tb.twi, a);
+    }
+  }
   uint32_t shift = 0;
   while ((size << shift) < p.m) shift++;
   ex.template launch<FrScalePow2>(total, total, shift, (const Fr*)tb.consts, a);

@@ -65,6 +65,9 @@ cudaError_t zk_coop_bucket_reduce_g2(cudaStream_t st, const MsmPlan& p, const ui
                                      XYZZ<Fp2>* out, int tree);
 cudaError_t zk_coop_row_sum_g2(cudaStream_t st, uint32_t nwin, uint32_t pitch_in, uint32_t m, uint32_t per_block,
                                const XYZZ<Fp2>* in, uint32_t pitch_out, XYZZ<Fp2>* out);
+struct FrCfg;
+cudaError_t zk_ntt_fused(cudaStream_t st, bool inverse, Mont<FrCfg>* a, uint32_t total, uint32_t L0, uint32_t k,
+                         const Mont<FrCfg>* tw, uint32_t m);
 template <class C> struct BucketReduce;
 template <class C> struct PairSum;
 struct G1;
@@ -72,7 +75,7 @@ struct G2;
 
 // optional per-launch timing (zkmsm_profile): CUDA events on the launching stream around every kernel
 struct LaunchProfile {
-  static constexpr int MAX = 96;
+  static constexpr int MAX = 256;
   int n = 0;
   const char* names[MAX];
   uint32_t threads[MAX];
@@ -170,6 +173,24 @@ struct CudaExec {
       timed("finish", 1, 1, [&] { return zk_coop_finish_g1(st, nwin, pitch, c, (const XYZZ<Mont<FqCfg>>*)arr, (XYZZ<Mont<FqCfg>>*)out_xyzz, out_affine, out_inf); });
     else
       launch<Finish<C>>(1u, nwin, pitch, c, arr, out_xyzz, out_affine, out_inf);
+  }
+  // several transform stages in one shared-memory pass (tu_fr_ntt.cu); false = shape not supported, launch the stages
+  bool ntt_fused(bool inverse, Mont<FrCfg>* a, uint32_t total, uint32_t L0, uint32_t k, const Mont<FrCfg>* tw, uint32_t m) {
+    if (err != cudaSuccess) return true;
+    if (getenv("ZKMSM_NTT_NO_FUSE")) return false;
+    int slot = -1;
+    if (prof && prof->n < LaunchProfile::MAX) {
+      slot = prof->n;
+      prof->names[slot] = "ntt_fused";
+      prof->threads[slot] = total;
+      cudaEventRecord(prof->beg[slot], st);
+    }
+    cudaError_t e = zk_ntt_fused(st, inverse, a, total, L0, k, tw, m);
+    if (e == cudaErrorNotSupported) { cudaGetLastError(); return false; }
+    if (slot >= 0) { cudaEventRecord(prof->end[slot], st); prof->n++; }
+    launches++;
+    if (e != cudaSuccess) err = e;
+    return true;
   }
   void exclusive_scan(uint32_t n, uint32_t* hist_cursor, uint32_t* offsets, uint32_t* blocksums) {
     if (err != cudaSuccess) return;

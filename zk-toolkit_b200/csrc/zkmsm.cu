@@ -677,7 +677,8 @@ static int fr_quotient_ntt(zkmsm_ctx* ctx, const uint32_t* u, const uint32_t* v,
   uint32_t* d_out = d_raw + 24 * n;
   uint32_t* d_flag = d_raw + 32 * n;
   Fr* scratch = (Fr*)(base + off_fr);
-  CudaExec ex(ctx->stream);
+  if (ctx->prof) ctx->prof->n = 0;
+  CudaExec ex(ctx->stream, ctx->prof);
   FrNttTables tb;
   if (ctx->ntt_n != n) {
     if (ctx->ntt_tables) { CU(ctx, cudaStreamSynchronize(ctx->stream)); cudaFree(ctx->ntt_tables); ctx->ntt_tables = nullptr; }
