@@ -181,7 +181,7 @@ class Context:
 
     def profile_read(self):
         """[(kernel name, ms, logical threads)] of the last MSM, in launch order"""
-        cap, stride = 96, 32
+        cap, stride = 256, 32
         names = ctypes.create_string_buffer(cap * stride)
         ms = np.zeros(cap, dtype=np.float32)
         thr = np.zeros(cap, dtype=np.uint32)

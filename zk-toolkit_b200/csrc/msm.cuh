@@ -306,13 +306,14 @@ template <class C> struct FixupLevel {
   }
 };
 
-// ---------------------------------------------------------------- batched-affine pre-reduction (optional)
+// ---------------------------------------------------------------- batched-affine pre-reduction
+// (on by default for large G1 sets with precomputed slabs, see msm_default_batch_rounds)
 // Round r halves every bucket: neighbours (2j, 2j+1) of a bucket are added in AFFINE coordinates,
 //   lambda = (y2 - y1) / (x2 - x1),  x3 = lambda^2 - x1 - x2,  y3 = lambda (x1 - x3) - y1      (macros.rs:109-152)
 // which is what the reference does per addition -- but the inversions of T independent additions are shared by
 // Montgomery's trick: prefix products of the denominators on the way forward, ONE inversion, and two
 // multiplications per addition on the way back.  6 field multiplications per addition instead of the 10 of an
-// XYZZ mixed add; the single inversion (binary Euclid, shift/subtract only) stays off the multiplier pipe.
+// XYZZ mixed add; the single inversion (division steps in batches of 30, fp.cuh) costs ~5 % of a 128-addition batch.
 // Every exceptional case keeps the reference semantics: AtInfinity operands and odd leftovers are copied,
 // P + P takes the tangent (denominator 2y, macros.rs:57-108), P + (-P) gives AtInfinity (macros.rs:53-56);
 // those use the denominator 1 so that the shared product never vanishes.
