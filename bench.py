@@ -285,6 +285,31 @@ def main():
         e2e = {"value": round(n_total / e2e_s / 1e6, 3), "unit": "Mpoints/s", "ms_per_step": round(e2e_s * 1e3, 4),
                "h2d_bytes_per_step": n_total * 32, "d2h_bytes_per_step": 24 * 4 + 8,
                "api": "zkmsm_g1_msm(ctx, resident CRS points, host scalars) -> host affine point"}
+        if world == 1:
+            # the same steps issued through the asynchronous pair of calls on two contexts, so that the copy of step
+            # k + 1 runs under the kernels of step k (what a prover with several MSMs per proof does, groth16.py);
+            # every step still copies its scalars from pinned host memory and reads its result back
+            ctx_b = z.Context(local_rank)
+            h_sc_b = h_sc.clone().pin_memory()
+            lanes = [(ctx, h_sc), (ctx_b, h_sc_b)]
+
+            def pipelined(steps):
+                lanes[0][0].msm_begin_ptr(pts, lanes[0][1].data_ptr(), n)
+                for k in range(1, steps):
+                    lanes[k % 2][0].msm_begin_ptr(pts, lanes[k % 2][1].data_ptr(), n)
+                    out = lanes[(k - 1) % 2][0].msm_result(1)
+                return lanes[(steps - 1) % 2][0].msm_result(1)
+
+            out = pipelined(3)
+            if out[0].tolist() != res[0].tolist():
+                raise SystemExit("pipelined end-to-end result differs")
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            pipelined(args.steps)
+            torch.cuda.synchronize()
+            pip_s = (time.perf_counter() - t0) / args.steps
+            e2e["pipelined"] = {"value": round(n_total / pip_s / 1e6, 3), "ms_per_step": round(pip_s * 1e3, 4),
+                                "api": "zkmsm_g1_msm_begin / zkmsm_g1_msm_result alternating on two contexts"}
 
     # ---- roofline of the dominant kernel (bucket accumulation), measured live above
     # Denominator: a limb product (32x32->64 multiply-accumulate) is one IMAD.WIDE, which issues at HALF the

@@ -162,6 +162,11 @@ class Context:
         self._check(fn(self.h, pts.handle, L.dptr(sc), n))
         self._inflight = sc
 
+    def msm_begin_ptr(self, pts: PointSet, scalars_ptr, n):
+        """msm_begin with a raw host pointer (e.g. pinned memory, which makes the copy asynchronous)"""
+        fn = self.lib.zkmsm_g1_msm_begin if pts.group == 1 else self.lib.zkmsm_g2_msm_begin
+        self._check(fn(self.h, pts.handle, ctypes.c_void_p(scalars_ptr), n))
+
     def msm_enqueue(self, pts: PointSet, scalars_dev_ptr, n):
         fn = self.lib.zkmsm_g1_msm_enqueue if pts.group == 1 else self.lib.zkmsm_g2_msm_enqueue
         self._check(fn(self.h, pts.handle, ctypes.c_void_p(scalars_dev_ptr), n))
