@@ -334,3 +334,11 @@ def test_default_batched_path_at_2p19(z, ctx):
     same = [12345] * n                                   # every term lands in the same buckets: long runs of pairs
     out, inf = ctx.msm(pts.set, z.scalars_to_array(same))
     assert U.g1_from_array(out, inf) == U.expected_from_dlogs(O.G1_GEN, dlogs, same)
+    # a set made of P, P, -P and AtInfinity only: inside the rounds nearly every pair is a tangent, a cancellation
+    # or a copy (the rare-case paths of BatchedAddRound at full size)
+    dl2 = [7, 7, O.R - 7, 0] * (n // 4)
+    pts2 = z.G1Points.generator_multiples(dl2, precompute=True)
+    assert pts2[3].is_zero() and to_o1(pts2[2]) == O.point_neg(O.scalar_mul(O.G1_GEN, 7))
+    sc2 = U.rand_scalars(rnd, n)
+    out, inf = ctx.msm(pts2.set, z.scalars_to_array(sc2))
+    assert U.g1_from_array(out, inf) == U.expected_from_dlogs(O.G1_GEN, dl2, sc2)
