@@ -790,11 +790,11 @@ inline uint32_t msm_default_batch_rounds(const MsmPlan& p) {
 // 128 threads owns 128 * T consecutive slots, so the last block may reach past the item count
 inline size_t msm_pre_slots(const MsmPlan& p) { return (size_t)(p.max_entries + 1) / 2 + p.nb + 1; }
 inline size_t msm_prefix_slots(const MsmPlan& p) { return msm_pre_slots(p) + (size_t)129 * p.batch_T; }
-// additions per thread in a round with about `items` outputs: whole waves of the resident threads (2 blocks of
-// 128 per SM, like Accumulate), at most p.batch_T and at least a quarter of it
+// additions per thread in a round with about `items` outputs: whole waves of the resident threads (3 blocks of
+// 128 per SM, ZK_MIN_BLOCKS in tu_g1_batch.cu, i.e. 1.5 x acc_slots), at most p.batch_T and at least a quarter of it
 inline uint32_t msm_batch_T(const MsmPlan& p, uint64_t items) {
   if (!p.acc_slots) return p.batch_T;
-  uint64_t half_blocks = 3;   // resident blocks per SM of the batched kernel (tuning override for A/B builds)
+  uint64_t half_blocks = 3;   // resident blocks per SM of the batched kernel (override for A/B builds of that TU)
   if (const char* e = getenv("ZKMSM_BATCH_BLOCKS")) { int v = atoi(e); if (v >= 1 && v <= 8) half_blocks = (uint64_t)v; }
   const uint64_t slots = (uint64_t)p.acc_slots * half_blocks / 2;
   uint32_t lo = p.batch_T / 4 ? p.batch_T / 4 : 1;
