@@ -728,7 +728,7 @@ inline MsmPlan msm_plan(uint32_t n, uint32_t c, bool precomp, uint32_t stride, b
   p.max_entries = n * p.W;
   p.acc_slots = acc_slots;
   p.L = p.max_entries >= (1u << 23) ? 32 : (p.max_entries >= (1u << 21) ? 16 : 8);
-  if (acc_slots) {
+  if (acc_slots && !getenv("ZKMSM_NO_WAVE_L")) {
     // Wave quantisation: every resident slot runs ceil(threads / slots) threads of L mixed additions one after the
     // other, so with few waves (small n) the last, partly filled wave costs a whole one.  Take the L near the
     // default that minimises waves x L (ties: the larger L, fewer partial sums for the fix-up tree).

@@ -328,7 +328,7 @@ static int msm_enqueue_impl(zkmsm_ctx* ctx, const zkmsm_points* ps, const uint32
   }
   unsigned c = ps->precomp ? ps->c : (ctx->window_override ? ctx->window_override : msm_pick_c((uint32_t)n, false, ps->half));
   MsmPlan p = msm_plan((uint32_t)n, c, ps->precomp, (uint32_t)ps->n, ps->half, !getenv("ZKMSM_NO_COOP"),
-                          getenv("ZKMSM_NO_WAVE_L") ? 0u : (uint32_t)ctx->sms * 256u);
+                          (uint32_t)ctx->sms * 256u);
   int rc;
   uint32_t nseg = (p.nb + SCAN_SEG - 1) / SCAN_SEG + 1;
   if ((rc = ws_reserve(ctx, WS_HIST, sizeof(uint32_t) * p.nb)) || (rc = ws_reserve(ctx, WS_OFFSETS, sizeof(uint32_t) * (p.nb + 1))) ||
