@@ -346,8 +346,17 @@ static int msm_enqueue_impl(zkmsm_ctx* ctx, const zkmsm_points* ps, const uint32
     size_t pre_n = msm_pre_slots(p);
     if ((rc = ws_reserve(ctx, WS_PRE_A, sizeof(Affine<F>) * pre_n)) || (rc = ws_reserve(ctx, WS_PRE_B, sizeof(Affine<F>) * pre_n)) ||
         (rc = ws_reserve(ctx, WS_PRE_PREFIX, sizeof(F) * 2 * msm_prefix_slots(p))) || (rc = ws_reserve(ctx, WS_PRE_OFF, sizeof(uint32_t) * 3 * ((size_t)p.nb + 4))) ||
-        (rc = ws_reserve(ctx, WS_PRE_ENTRIES, sizeof(Entry) * pre_n)))
-      return rc;
+        (rc = ws_reserve(ctx, WS_PRE_ENTRIES, sizeof(Entry) * pre_n))) {
+      // the rounds are an optimisation: without room for their scratch the MSM runs on the XYZZ accumulation alone
+      // (a forced ZKMSM_BATCH_ROUNDS still reports the failure)
+      if (rc != ZKMSM_ERR_NOMEM || getenv("ZKMSM_BATCH_ROUNDS")) return rc;
+      for (int slot : {WS_PRE_A, WS_PRE_B, WS_PRE_PREFIX, WS_PRE_ENTRIES})
+        if (ctx->ws[slot]) { cudaFree(ctx->ws[slot]); ctx->ws[slot] = nullptr; ctx->ws_bytes[slot] = 0; }
+      strcpy(ctx->err, "ok");
+      p.batch_rounds = 0;
+    }
+  }
+  if (p.batch_rounds > 0) {
     b.pre_pts[0] = (Affine<F>*)ctx->ws[WS_PRE_A];
     b.pre_pts[1] = (Affine<F>*)ctx->ws[WS_PRE_B];
     b.pre_prefix = (F*)ctx->ws[WS_PRE_PREFIX];
