@@ -183,6 +183,16 @@ int emu_fr_quotient_ntt(const uint32_t* u, const uint32_t* v, const uint32_t* w,
   fr_quotient_run(ex, p, tb, u, v, w, scratch.data(), h_out, nonzero_rem);
   return ex.launches;
 }
+// host-side policies of the launch plan on a device with `acc_slots` resident accumulate threads:
+// out = {c, L, default batched-affine rounds, additions per thread of the first round, its thread count, K, coop}
+void emu_policy(uint32_t n, uint32_t c, int precomp, int half, uint32_t acc_slots, uint32_t* out) {
+  if (c == 0) c = msm_pick_c(n, precomp != 0, half != 0);
+  MsmPlan p = msm_plan(n, c, precomp != 0, n, half != 0, true, acc_slots);
+  uint32_t rounds = msm_default_batch_rounds(p);
+  uint64_t items = ((uint64_t)p.max_entries + 1) / 2 + p.nb;
+  uint32_t T = msm_batch_T(p, items);
+  out[0] = c; out[1] = p.L; out[2] = rounds; out[3] = T; out[4] = (uint32_t)((items + T - 1) / T); out[5] = p.K; out[6] = p.coop;
+}
 void emu_plan(uint32_t n, uint32_t c, int precomp, uint32_t* out) {
   if (c == 0) c = msm_pick_c(n, precomp != 0);
   MsmPlan p = msm_plan(n, c, precomp != 0, n);

@@ -285,3 +285,33 @@ def test_emu_fr_quotient_by_transforms(lib, n):
         lib.emu_fr_quotient(ptr(U.scalars_to_array(uu)), ptr(U.scalars_to_array(vv)), ptr(U.scalars_to_array(remc[:n])), n, ptr(out),
                             ctypes.byref(flag))
         assert [U.limbs_to_int(r) for r in out][:n - 1] == qc and flag.value == 0
+
+
+def test_launch_plan_policies(lib):
+    """host logic of the launch plan for a 148-SM device: window width, wave-aware chunk length, default rounds of
+    batched-affine pre-reduction (msm_default_batch_rounds) and the additions per thread of a round (msm_batch_T)"""
+    slots = 148 * 256
+
+    def policy(logn, c=0, precomp=1, half=1, s=slots):
+        out = (ctypes.c_uint32 * 7)()
+        lib.emu_policy(1 << logn, c, precomp, half, s, out)
+        return dict(zip(("c", "L", "rounds", "T", "threads", "K", "coop"), out))
+
+    assert policy(17)["rounds"] == 0 and policy(16)["rounds"] == 0          # small sets: XYZZ accumulation only
+    assert policy(20, precomp=0)["rounds"] == 0                             # plain point sets: per-window buckets
+    assert policy(20, s=0)["rounds"] == 0                                   # unknown device (CPU emulation)
+    p20 = policy(20)
+    assert p20["c"] == 17 and p20["rounds"] == 4 and p20["coop"] == 1 and p20["K"] == 16
+    assert policy(19)["rounds"] == 3 and policy(22)["rounds"] == 3 and policy(21)["rounds"] == 2
+    assert policy(18, c=16)["rounds"] == 2 and policy(18, c=17)["rounds"] == 0
+    for logn in (19, 20, 21, 22, 24):
+        p = policy(logn)
+        assert 32 <= p["T"] <= 128
+        waves = p["threads"] / (slots * 3 // 2)                             # 3 blocks of 128 per SM
+        assert waves <= round(waves) + 1e-9 or waves - int(waves) > 0.85     # whole waves (or nearly)
+    # the chunk length of Accumulate fills whole waves of 2 x 128 threads per SM at small n
+    for logn in (16, 17, 18):
+        p = policy(logn)
+        entries = (1 << logn) * (254 // p["c"] + 1)
+        threads = -(-entries // p["L"])
+        assert threads / slots - int(threads / slots) > 0.8 or threads % slots == 0
