@@ -22,4 +22,12 @@ for rounds in ("0","2"):
     rc=lib.emu_g1_msm(ptr(xy),None,ptr(s),n,len(pts),c,pre,L,K,ptr(out),ctypes.byref(oi))
     got=U.g1_from_array(out,oi.value); exp=U.expected_from_dlogs(O.G1_GEN,dl[:n],sc)
     ok = ok and rc==0 and got==exp
+# the transform-based quotient (fr_ntt.cuh): product tree, Newton inverse, batched transforms with awkward n
+for n in (2, 3, 7, 33, 70):
+  u,v,w=([rnd.randrange(O.R) for _ in range(n)] for _ in range(3))
+  out=np.zeros((max(n-1,1),8),dtype=np.uint32); tt=np.zeros((n+1,8),dtype=np.uint32); flag=ctypes.c_uint32(0)
+  lib.emu_fr_quotient_ntt(ptr(U.scalars_to_array(u)),ptr(U.scalars_to_array(v)),ptr(U.scalars_to_array(w)),n,ptr(out),ctypes.byref(flag),ptr(tt))
+  out2=np.zeros((max(n-1,1),8),dtype=np.uint32); flag2=ctypes.c_uint32(0)
+  lib.emu_fr_quotient(ptr(U.scalars_to_array(u)),ptr(U.scalars_to_array(v)),ptr(U.scalars_to_array(w)),n,ptr(out2),ctypes.byref(flag2))
+  ok = ok and out[:n-1].tolist()==out2[:n-1].tolist() and (flag.value!=0)==(flag2.value!=0)
 print("asan run ok:", ok)
