@@ -66,6 +66,12 @@ const char* zkmsm_last_error(const zkmsm_ctx* ctx);
 /* Override the window width c for later MSMs / precomputed loads (0 = automatic). */
 int zkmsm_set_window(zkmsm_ctx* ctx, unsigned c);
 
+/* Tuning / cross-check switches of this context.  The environment variables ZKMSM_<NAME> (upper case) are read ONCE,
+ * in zkmsm_create; this call overrides one of them afterwards.  Names: batch_rounds (-1 = automatic), batch_T,
+ * batch_g2, batch_blocks, L, K, no_wave_L, no_coop, ntt_no_fuse, quotient_schoolbook, no_graph, no_bucket_acc
+ * ("Tuning and cross-check switches"). */
+int zkmsm_set_option(zkmsm_ctx* ctx, const char* name, long value);
+
 /* Pinned host memory for scalars / points (optional; any host pointer is accepted). */
 int zkmsm_host_alloc(size_t bytes, void** out);
 int zkmsm_host_free(void* p);
@@ -135,11 +141,30 @@ int zkmsm_g1_msm_partial(zkmsm_ctx* ctx, const zkmsm_points* pts, const uint32_t
                          uint32_t out_partial[ZKMSM_G1_PARTIAL_WORDS]);
 int zkmsm_g2_msm_partial(zkmsm_ctx* ctx, const zkmsm_points* pts, const uint32_t* scalars, size_t n,
                          uint32_t out_partial[ZKMSM_G2_PARTIAL_WORDS]);
+/* Stream-ordered variants (scalars and the partial in device memory, no host synchronisation).  An out-of-range
+ * scalar cannot be reported by a call that does not wait: the partial is then exported poisoned and the combine
+ * call that meets it returns ZKMSM_ERR_SCALAR_RANGE. */
 int zkmsm_g1_msm_partial_device(zkmsm_ctx* ctx, const zkmsm_points* pts, const uint32_t* scalars_device, size_t n,
                                 uint32_t* out_partial_device);
+int zkmsm_g2_msm_partial_device(zkmsm_ctx* ctx, const zkmsm_points* pts, const uint32_t* scalars_device, size_t n,
+                                uint32_t* out_partial_device);
+/* The other way to split one MSM over `world` devices (a power of two): every device holds the WHOLE precomputed
+ * point set and sees all n scalars, but owns only 1/world of the bucket range, so that sorted pairs AND buckets
+ * (the latency-bound reduction) shrink by `world`.  The partials of ranks 0..world-1 add up to the MSM exactly as
+ * above.  Needs a ZKMSM_PRECOMPUTE set; world = 1 is the plain partial. */
+int zkmsm_g1_msm_partial_range(zkmsm_ctx* ctx, const zkmsm_points* pts, const uint32_t* scalars, size_t n, unsigned rank,
+                               unsigned world, uint32_t out_partial[ZKMSM_G1_PARTIAL_WORDS]);
+int zkmsm_g2_msm_partial_range(zkmsm_ctx* ctx, const zkmsm_points* pts, const uint32_t* scalars, size_t n, unsigned rank,
+                               unsigned world, uint32_t out_partial[ZKMSM_G2_PARTIAL_WORDS]);
+int zkmsm_g1_msm_partial_range_device(zkmsm_ctx* ctx, const zkmsm_points* pts, const uint32_t* scalars_device, size_t n,
+                                      unsigned rank, unsigned world, uint32_t* out_partial_device);
+int zkmsm_g2_msm_partial_range_device(zkmsm_ctx* ctx, const zkmsm_points* pts, const uint32_t* scalars_device, size_t n,
+                                      unsigned rank, unsigned world, uint32_t* out_partial_device);
 int zkmsm_g1_combine(zkmsm_ctx* ctx, const uint32_t* partials, size_t k, uint32_t out_xy[24], int* out_is_inf);
 int zkmsm_g2_combine(zkmsm_ctx* ctx, const uint32_t* partials, size_t k, uint32_t out_xy[48], int* out_is_inf);
 int zkmsm_g1_combine_device(zkmsm_ctx* ctx, const uint32_t* partials_device, size_t k, uint32_t out_xy[24],
+                            int* out_is_inf);
+int zkmsm_g2_combine_device(zkmsm_ctx* ctx, const uint32_t* partials_device, size_t k, uint32_t out_xy[48],
                             int* out_is_inf);
 
 /* ---- vector scalar multiplication of one base point: `&G1Point * &Fq1`

@@ -20,6 +20,11 @@ struct HostExec {
     launches++;
   }
   void zero(void* p, size_t bytes) { memset(p, 0, bytes); }
+  template <class C> void accumulate_buckets(const MsmPlan& p, const uint32_t* offsets, const Entry* entries,
+                                             const Affine<typename C::F>* points, uint32_t direct,
+                                             XYZZ<typename C::F>* bucket_sums, uint32_t* big) {
+    launch<AccumulateBucketsRef<C>>(p.nb, p, offsets, entries, points, direct, bucket_sums, big);
+  }
   template <class C> uint32_t bucket_reduce(const MsmPlan& p, const uint32_t* offsets, const XYZZ<typename C::F>* buckets,
                                             XYZZ<typename C::F>* out) {
     launch<BucketReduce<C>>(p.nwin * (p.B / p.K), p, offsets, buckets, out);
@@ -48,10 +53,12 @@ struct HostExec {
   }
 };
 
+static uint32_t g_last_fallback = 0;   // 1 when the last emu_msm took the chunked fallback (a bucket over the cap)
+
 template <class C>
 static int emu_msm(const uint32_t* xy, const uint8_t* inf, const uint32_t* scalars, uint32_t n, uint32_t npts,
                    uint32_t c, int precomp, uint32_t L, uint32_t K, uint32_t* out_xy, uint32_t* out_inf,
-                   uint32_t* out_xyzz) {
+                   uint32_t* out_xyzz, uint32_t rank = 0, uint32_t world = 1) {
   typedef typename C::F F;
   HostExec ex;
   bool half = (precomp & 2) != 0;
@@ -62,10 +69,11 @@ static int emu_msm(const uint32_t* xy, const uint8_t* inf, const uint32_t* scala
   ex.launch<LoadPoints<C>>(npts, npts, xy, inf, pts.data());
   if (precomp) ex.launch<PrecomputeSlabs<C>>(npts, npts, npts, c, W, pts.data());
   if (n == 0) { *out_inf = 1; memset(out_xy, 0, 4 * C::AFF_LIMBS); return 0; }
-  MsmPlan p = msm_plan(n, c, precomp != 0, npts, half);
+  const MsmTuning tune = MsmTuning::from_env();   // test infrastructure: the switches are read per call here
+  MsmPlan p = msm_plan(n, c, precomp != 0, npts, half, false, 0, tune, rank, world);
   if (L) { p.L = L; p.acc_threads = (p.max_entries + L - 1) / L; }
   if (K) p.K = K;
-  std::vector<uint32_t> hist(p.nb), offsets(p.nb + 1), segsum((p.nb + SCAN_SEG - 1) / SCAN_SEG + 1), err(1);
+  std::vector<uint32_t> hist(p.nb), offsets(p.nb + 1), segsum((p.nb + SCAN_SEG - 1) / SCAN_SEG + 1), err(1), big(1);
   std::vector<Entry> entries(p.max_entries + 1);
   std::vector<XYZZ<F>> buckets(p.nb), partials(msm_partial_slots(p)), reduced(msm_reduced_slots(p));
   std::vector<uint32_t> pkeys(msm_partial_slots(p), 0x12345678u);
@@ -81,11 +89,15 @@ static int emu_msm(const uint32_t* xy, const uint8_t* inf, const uint32_t* scala
   b.pre_pts[0] = pre_a.data(); b.pre_pts[1] = pre_b.data(); b.pre_prefix = pre_prefix.data();
   b.pre_off[0] = pre_off_a.data(); b.pre_off[1] = pre_off_b.data(); b.pre_cnt = pre_cnt.data(); b.pre_entries = pre_entries.data();
   b.hist_cursor = hist.data(); b.offsets = offsets.data(); b.segsum = segsum.data(); b.entries = entries.data();
-  b.bucket_sums = buckets.data(); b.partials = partials.data(); b.reduced = reduced.data(); b.err = err.data(); b.partial_keys = pkeys.data();
+  b.bucket_sums = buckets.data(); b.partials = partials.data(); b.reduced = reduced.data(); b.err = err.data(); b.big = big.data(); b.partial_keys = pkeys.data();
   XYZZ<F> xyzz;
-  msm_launch<C>(ex, p, b, (const Affine<F>*)pts.data(), scalars, out_xyzz ? &xyzz : (XYZZ<F>*)nullptr,
+  msm_launch<C>(ex, p, tune, b, (const Affine<F>*)pts.data(), scalars, out_xyzz ? &xyzz : (XYZZ<F>*)nullptr,
                 out_xyzz ? (uint32_t*)nullptr : out_xy, out_xyzz ? (uint32_t*)nullptr : out_inf);
-  if (out_xyzz) memcpy(out_xyzz, &xyzz, sizeof(xyzz));
+  if (out_xyzz) {
+    if (err[0]) ex.launch<PoisonPartial<C>>(1u, (const uint32_t*)err.data(), &xyzz);
+    memcpy(out_xyzz, &xyzz, sizeof(xyzz));
+  }
+  g_last_fallback = big[0];
   return err[0] ? -3 : 0;
 }
 
@@ -111,9 +123,25 @@ int emu_g1_msm_sharded(const uint32_t* xy, const uint32_t* scalars, uint32_t n, 
     if (rc) return rc;
   }
   HostExec ex;
-  ex.launch<CombinePartials<G1>>(1u, k, (const XYZZ<Fp>*)parts.data(), out_xy, out_inf);
-  return 0;
+  uint32_t err = 0;
+  ex.launch<CombinePartials<G1>>(1u, k, (const XYZZ<Fp>*)parts.data(), out_xy, out_inf, &err);
+  return err ? -3 : 0;
 }
+// bucket-range split: `world` ranks each see all n scalars and the whole precomputed set, own 1/world of the buckets
+int emu_g1_msm_range(const uint32_t* xy, const uint32_t* scalars, uint32_t n, uint32_t world, uint32_t c, int half, uint32_t* out_xy,
+                     uint32_t* out_inf) {
+  std::vector<XYZZ<Fp>> parts(world);
+  for (uint32_t r = 0; r < world; r++) {
+    uint32_t dummy[24], dinf;
+    int rc = emu_msm<G1>(xy, nullptr, scalars, n, n, c, 1 | (half ? 2 : 0), 0, 0, dummy, &dinf, (uint32_t*)&parts[r], r, world);
+    if (rc) return rc;
+  }
+  HostExec ex;
+  uint32_t err = 0;
+  ex.launch<CombinePartials<G1>>(1u, world, (const XYZZ<Fp>*)parts.data(), out_xy, out_inf, &err);
+  return err ? -3 : 0;
+}
+uint32_t emu_last_fallback() { return g_last_fallback; }
 // one rank's share: partial point as the opaque 48-word blob of the C ABI, and the combine step
 int emu_g1_msm_partial(const uint32_t* xy, const uint32_t* scalars, uint32_t n, uint32_t* out_partial) {
   if (n == 0) { memset(out_partial, 0, sizeof(XYZZ<Fp>)); return 0; }
@@ -122,8 +150,9 @@ int emu_g1_msm_partial(const uint32_t* xy, const uint32_t* scalars, uint32_t n, 
 }
 int emu_g1_combine(const uint32_t* partials, uint32_t k, uint32_t* out_xy, uint32_t* out_inf) {
   HostExec ex;
-  ex.launch<CombinePartials<G1>>(1u, k, (const XYZZ<Fp>*)partials, out_xy, out_inf);
-  return 0;
+  uint32_t err = 0;
+  ex.launch<CombinePartials<G1>>(1u, k, (const XYZZ<Fp>*)partials, out_xy, out_inf, &err);
+  return err ? -3 : 0;
 }
 // `base * k_i` for a vector of raw 256-bit scalars (FixedBaseMul path)
 int emu_g1_mul_base(const uint32_t* base_xy, const uint32_t* scalars, uint32_t n, uint32_t* out_xy, uint8_t* out_inf) {
@@ -187,12 +216,19 @@ int emu_fr_quotient_ntt(const uint32_t* u, const uint32_t* v, const uint32_t* w,
 // out = {c, L, default batched-affine rounds, additions per thread of the first round, its thread count, K, coop}
 void emu_policy(uint32_t n, uint32_t c, int precomp, int half, uint32_t acc_slots, uint32_t* out) {
   if (c == 0) c = msm_pick_c(n, precomp != 0, half != 0);
-  MsmPlan p = msm_plan(n, c, precomp != 0, n, half != 0, true, acc_slots);
+  const uint32_t world = out[7] ? out[7] : 1;   // in: ranks of a bucket-range split (0 / 1 = none)
+  MsmPlan p = msm_plan(n, c, precomp != 0, n, half != 0, true, acc_slots, MsmTuning(), 0, world);
   uint32_t rounds = msm_default_batch_rounds(p);
-  uint64_t items = ((uint64_t)p.max_entries + 1) / 2 + p.nb;
+  uint64_t items = (msm_expected_entries(p) + 1) / 2 + p.nb / 2;
   uint32_t T = msm_batch_T(p, items);
+  uint64_t left = msm_expected_entries(p);
+  for (uint32_t r = 0; r < rounds; r++) left = (left + 1) / 2 + p.nb / 2;
+  msm_pick_bucket_acc(p, left, MsmTuning());
   out[0] = c; out[1] = p.L; out[2] = rounds; out[3] = T; out[4] = (uint32_t)((items + T - 1) / T); out[5] = p.K; out[6] = p.coop;
+  out[7] = p.acc_G; out[8] = p.acc_cap; out[9] = p.nb;
 }
+// n * windows must stay below 2^32 sorted pairs (the kernels' positions are 32-bit): the product rejects the rest
+int emu_fits(uint64_t n, uint32_t c, int half) { return msm_fits(n, c, half != 0) ? 1 : 0; }
 void emu_plan(uint32_t n, uint32_t c, int precomp, uint32_t* out) {
   if (c == 0) c = msm_pick_c(n, precomp != 0);
   MsmPlan p = msm_plan(n, c, precomp != 0, n);

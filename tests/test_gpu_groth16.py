@@ -131,9 +131,9 @@ def test_fr_quotient_transforms_vs_schoolbook_and_identity(z, monkeypatch):
         u, v, w = ([rnd.randrange(O.R) for _ in range(n)] for _ in range(3))
         arrs = [z.scalars_to_array(x) for x in (u, v, w)]
         h1, exact1 = ctx.fr_quotient(*arrs)
-        monkeypatch.setenv("ZKMSM_QUOTIENT_SCHOOLBOOK", "1")
+        ctx.set_option("quotient_schoolbook", 1)
         h2, exact2 = ctx.fr_quotient(*arrs)
-        monkeypatch.delenv("ZKMSM_QUOTIENT_SCHOOLBOOK")
+        ctx.set_option("quotient_schoolbook", 0)
         assert h1.tolist() == h2.tolist() and exact1 == exact2 == False   # random w: Euclidean quotient + remainder
     n = 1024
     t = O.qap_build_t(n).coeffs

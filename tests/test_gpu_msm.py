@@ -282,11 +282,11 @@ def test_begin_result_and_points_info(z, ctx):
     ctx.msm(pts.set, arr)
     names = [nm for nm, _, _ in ctx.profile_read()]
     ctx.profile(False)
-    assert "accumulate" in names and "bucket_reduce" in names and "finish" in names
+    assert "accumulate_buckets" in names and "bucket_reduce" in names and "finish" in names
 
 
-def test_batched_affine_prereduction_option(z, ctx, monkeypatch):
-    """batched-affine pre-reduction rounds forced on small inputs (ZKMSM_BATCH_ROUNDS / ZKMSM_BATCH_T): identical
+def test_batched_affine_prereduction_option(z, ctx):
+    """batched-affine pre-reduction rounds forced on small inputs (options batch_rounds / batch_T): identical
     results, including P + P (tangent), P + (-P), AtInfinity operands and odd leftovers inside the rounds"""
     n = 6000
     rnd = random.Random(31)
@@ -296,13 +296,24 @@ def test_batched_affine_prereduction_option(z, ctx, monkeypatch):
     for pre in (False, True):
         pts = z.G1Points.generator_multiples(dlogs, precompute=pre)
         for rounds, T in ((1, 128), (3, 7), (4, 64)):
-            monkeypatch.setenv("ZKMSM_BATCH_ROUNDS", str(rounds))
-            monkeypatch.setenv("ZKMSM_BATCH_T", str(T))
-            out, inf = ctx.msm(pts.set, z.scalars_to_array(sc))
-            assert U.g1_from_array(out, inf) == exp
-        monkeypatch.delenv("ZKMSM_BATCH_ROUNDS")
-    monkeypatch.setenv("ZKMSM_BATCH_ROUNDS", "2")
-    monkeypatch.setenv("ZKMSM_BATCH_T", "5")
+            ctx.set_option("batch_rounds", rounds)
+            ctx.set_option("batch_T", T)
+            for no_bucket_acc in (0, 1):                 # bucket sums in one launch / chunked accumulation + fix-up tree
+                ctx.set_option("no_bucket_acc", no_bucket_acc)
+                out, inf = ctx.msm(pts.set, z.scalars_to_array(sc))
+                assert U.g1_from_array(out, inf) == exp
+            ctx.set_option("no_bucket_acc", 0)
+        ctx.set_option("batch_rounds", -1)
+    try:
+        _rare_cases_inside_rounds(z, ctx)
+    finally:
+        ctx.set_option("batch_rounds", -1)
+        ctx.set_option("batch_T", 0)
+
+
+def _rare_cases_inside_rounds(z, ctx):
+    ctx.set_option("batch_rounds", 2)
+    ctx.set_option("batch_T", 5)
     g = z.G1Point.g()
     dup = z.G1Points([g * 7] * 40)
     out, inf = ctx.msm(dup.set, z.scalars_to_array([5] * 40))
@@ -329,7 +340,7 @@ def test_default_batched_path_at_2p19(z, ctx):
     out, inf = ctx.msm(pts.set, z.scalars_to_array(sc))
     names = [name for name, _, _ in ctx.profile_read()]
     ctx.profile(False)
-    assert "batched_add_first" in names and "batched_add" in names and "accumulate" in names
+    assert "batched_add_first" in names and "batched_add" in names and "accumulate_buckets" in names
     assert U.g1_from_array(out, inf) == U.expected_from_dlogs(O.G1_GEN, dlogs, sc)
     same = [12345] * n                                   # every term lands in the same buckets: long runs of pairs
     out, inf = ctx.msm(pts.set, z.scalars_to_array(same))
@@ -342,3 +353,102 @@ def test_default_batched_path_at_2p19(z, ctx):
     sc2 = U.rand_scalars(rnd, n)
     out, inf = ctx.msm(pts2.set, z.scalars_to_array(sc2))
     assert U.g1_from_array(out, inf) == U.expected_from_dlogs(O.G1_GEN, dl2, sc2)
+
+
+def test_bucket_range_split_partials(z, ctx):
+    """zkmsm_g1_msm_partial_range: `world` ranks each take the whole precomputed set and all scalars but 1/world of the
+    bucket range; the partials combine to the MSM.  Host and stream-ordered device variants."""
+    import torch
+    n = 5000
+    rnd = random.Random(808)
+    dlogs = [rnd.randrange(1, O.R) for _ in range(n)]
+    sc = U.rand_scalars(rnd, n)
+    sc[0], sc[1], sc[2] = 0, O.R - 1, (O.R - 1) // 2
+    exp = U.expected_from_dlogs(O.G1_GEN, dlogs, sc)
+    pts = z.G1Points.generator_multiples(dlogs, precompute=True)
+    arr = z.scalars_to_array(sc)
+    for world in (1, 2, 8):
+        parts = [ctx.msm_partial_range(pts.set, arr, r, world) for r in range(world)]
+        assert U.g1_from_array(*ctx.combine(1, np.stack(parts))) == exp
+    d_sc = torch.from_numpy(arr.view(np.int32)).cuda()
+    d_parts = torch.zeros(4, 48, dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    for r in range(4):
+        ctx.msm_partial_range_device(pts.set, d_sc.data_ptr(), n, r, 4, d_parts[r].data_ptr())
+    assert U.g1_from_array(*ctx.combine_device(d_parts.data_ptr(), 4)) == exp
+    plain = z.G1Points.generator_multiples(dlogs[:16])
+    with pytest.raises(z.ZkmsmError):                      # needs the precomputed slabs
+        ctx.msm_partial_range(plain.set, arr[:16], 0, 2)
+    with pytest.raises(z.ZkmsmError):                      # world must be a power of two
+        ctx.msm_partial_range(pts.set, arr, 0, 3)
+    # G2 twin
+    dl2 = dlogs[:300]
+    pts2 = z.G2Points.generator_multiples(dl2, precompute=True)
+    parts = [ctx.msm_partial_range(pts2.set, arr[:300], r, 2) for r in range(2)]
+    assert U.g2_from_array(*ctx.combine(2, np.stack(parts))) == U.expected_from_dlogs(O.G2_GEN, dl2, sc[:300])
+
+
+def test_partial_device_reports_bad_scalar_through_combine(z, ctx):
+    """the stream-ordered partial cannot return ZKMSM_ERR_SCALAR_RANGE itself: the blob is poisoned and the combine
+    call that meets it fails (previously the bad scalar was silently dropped)"""
+    import torch
+    n = 64
+    dlogs = list(range(1, n + 1))
+    pts = z.G1Points.generator_multiples(dlogs)
+    good = z.scalars_to_array([3] * n)
+    bad = good.copy()
+    bad[5, 7] = 0x80000000                                  # bit 255 set
+    d_good, d_bad = (torch.from_numpy(a.view(np.int32)).cuda() for a in (good, bad))
+    d_parts = torch.zeros(2, 48, dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    ctx.msm_partial_device(pts.set, d_good.data_ptr(), n, d_parts[0].data_ptr())
+    ctx.msm_partial_device(pts.set, d_bad.data_ptr(), n, d_parts[1].data_ptr())
+    with pytest.raises(z.ZkmsmError) as e:
+        ctx.combine_device(d_parts.data_ptr(), 2)
+    assert e.value.code == -3
+    ctx.msm_partial_device(pts.set, d_good.data_ptr(), n, d_parts[1].data_ptr())
+    assert U.g1_from_array(*ctx.combine_device(d_parts.data_ptr(), 2)) == O.scalar_mul(O.G1_GEN, 2 * 3 * n * (n + 1) // 2)
+
+
+def test_graph_replay_matches_plain_launches(z, ctx):
+    """the launch sequence is captured once into a CUDA graph and replayed while point set, size and buffers recur;
+    no_graph launches kernel by kernel.  Same points; new scalars in the same buffer are picked up by the replay."""
+    n = 3000
+    rnd = random.Random(4242)
+    dlogs = [rnd.randrange(1, O.R) for _ in range(n)]
+    pts = z.G1Points.generator_multiples(dlogs, precompute=True)
+    for trial in range(3):
+        sc = U.rand_scalars(rnd, n)
+        exp = U.expected_from_dlogs(O.G1_GEN, dlogs, sc)
+        assert U.g1_from_array(*ctx.msm(pts.set, z.scalars_to_array(sc))) == exp      # capture, then replays
+    ctx.set_option("no_graph", 1)
+    try:
+        assert U.g1_from_array(*ctx.msm(pts.set, z.scalars_to_array(sc))) == exp
+    finally:
+        ctx.set_option("no_graph", 0)
+    # an out-of-range scalar is still reported on a replay
+    bad = z.scalars_to_array(sc)
+    bad[7, 7] |= 0x80000000
+    with pytest.raises(z.ZkmsmError):
+        ctx.msm(pts.set, bad)
+    assert U.g1_from_array(*ctx.msm(pts.set, z.scalars_to_array(sc))) == exp
+
+
+def test_msm_2p20_default_path_vs_oracle_closed_form(z, ctx):
+    """BASELINE configs[2] size on the default path (precomputed CRS tables, batched rounds, bucket accumulation,
+    CUDA-graph replay), compared with the ORACLE's scalar multiplication of the closed form (sum s_i k_i) g"""
+    n = 1 << 20
+    rnd = random.Random(2020)
+    dlogs = [rnd.randrange(1, O.R) for _ in range(n)]
+    sc = U.rand_scalars(rnd, n)
+    pts = z.G1Points.generator_multiples(dlogs, precompute=True)
+    # the generated points themselves are spot-checked against the oracle's double-and-add
+    for i in (0, 1, n // 2, n - 1):
+        assert to_o1(pts[i]) == O.scalar_mul(O.G1_GEN, dlogs[i])
+    want = O.scalar_mul(O.G1_GEN, sum(k * s for k, s in zip(dlogs, sc)) % O.R)
+    arr = z.scalars_to_array(sc)
+    assert U.g1_from_array(*ctx.msm(pts.set, arr)) == want
+    assert U.g1_from_array(*ctx.msm(pts.set, arr)) == want             # replayed graph
+    # the same through the two multi-GPU splits, all ranks on this device
+    parts = [ctx.msm_partial_range(pts.set, arr, r, 8) for r in range(8)]
+    assert U.g1_from_array(*ctx.combine(1, np.stack(parts))) == want

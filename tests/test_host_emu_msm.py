@@ -137,6 +137,68 @@ def test_emu_g1_sharded_partials_match_single(lib, g1_set):
         assert U.g1_from_array(out, oinf.value) == exp
 
 
+def test_emu_g1_bucket_range_split(lib, g1_set):
+    """the other multi-GPU split: every rank sees all scalars and the whole precomputed set but owns 1/world of the
+    bucket range (zkmsm_g1_msm_partial_range); the partials add up to the same point"""
+    dlogs, pts = g1_set
+    rnd = random.Random(77)
+    sc = U.rand_scalars(rnd, len(pts))
+    sc[3], sc[4], sc[5] = 0, O.R - 1, 1
+    xy, _ = U.g1_points_to_array(pts)
+    s = U.scalars_to_array(sc)
+    exp = U.expected_from_dlogs(O.G1_GEN, dlogs, sc)
+    for world, c, half in ((1, 6, 1), (2, 6, 1), (4, 5, 0), (8, 7, 1), (16, 5, 1)):
+        out = np.zeros(24, dtype=np.uint32)
+        oinf = ctypes.c_uint32(0)
+        assert lib.emu_g1_msm_range(ptr(xy), ptr(s), len(pts), world, c, half, ptr(out), ctypes.byref(oinf)) == 0
+        assert U.g1_from_array(out, oinf.value) == exp, (world, c, half)
+    # an out-of-range scalar poisons that rank's partial and the combine reports it
+    bad = U.scalars_to_array([O.R] + sc[1:])
+    out = np.zeros(24, dtype=np.uint32)
+    assert lib.emu_g1_msm_range(ptr(xy), ptr(bad), len(pts), 4, 5, 1, ptr(out), ctypes.byref(oinf)) == -3
+
+
+def test_emu_poisoned_partial_is_reported_by_combine(lib, g1_set):
+    """zkmsm_g1_msm_partial_device cannot return the scalar-range error (no host sync): the blob carries it"""
+    dlogs, pts = g1_set
+    xy, _ = U.g1_points_to_array(pts[:4])
+    good = np.zeros(48, dtype=np.uint32)
+    assert lib.emu_g1_msm_partial(ptr(xy), ptr(U.scalars_to_array([1, 2, 3, 4])), 4, ptr(good)) == 0
+    bad = np.zeros(48, dtype=np.uint32)
+    assert lib.emu_g1_msm_partial(ptr(xy), ptr(U.scalars_to_array([1, 1 << 255, 3, 4])), 4, ptr(bad)) == -3
+    assert bad[36:48].tolist() == [0xFFFFFFFF] * 12 and not bad[24:36].any()      # ZZ = 0, ZZZ = all ones
+    out = np.zeros(24, dtype=np.uint32)
+    oinf = ctypes.c_uint32(0)
+    parts = np.concatenate([good, bad, good])
+    assert lib.emu_g1_combine(ptr(parts), 3, ptr(out), ctypes.byref(oinf)) == -3
+    assert lib.emu_g1_combine(ptr(np.concatenate([good, good])), 2, ptr(out), ctypes.byref(oinf)) == 0
+    assert U.g1_from_array(out, oinf.value) == O.scalar_mul(O.msm(pts[:4], [1, 2, 3, 4]), 2)
+
+
+def test_emu_bucket_accumulation_and_its_fallback(lib, g1_set, monkeypatch):
+    """AccumulateBuckets (G lanes per bucket, one launch) is the default; a bucket over the cap raises the flag and the
+    gated chunked accumulation + fix-up tree redo the buckets; ZKMSM_NO_BUCKET_ACC forces the chunked path.  All three
+    give the reference's point."""
+    dlogs, pts = g1_set
+    rnd = random.Random(99)
+    sc = U.rand_scalars(rnd, len(pts))
+    exp = U.expected_from_dlogs(O.G1_GEN, dlogs, sc)
+    lib.emu_last_fallback.restype = ctypes.c_uint32
+    assert emu_g1(lib, pts, sc, c=5, precomp=1) == (0, exp)
+    assert lib.emu_last_fallback() == 0
+    # all-equal scalars: every window's digit falls into one bucket -> far over the cap -> fallback, same point
+    n = 48
+    eq = [0x0123456789ABCDEF0123456789ABCDEF0123456789ABCDEF0123456789ABCDEF % O.R] * n
+    big_pts = pts[:n]
+    # many copies so that one bucket is well over 4 x average + 32
+    many_pts, many_sc, many_d = big_pts * 6, eq * 6, dlogs[:n] * 6
+    assert emu_g1(lib, many_pts, many_sc, c=8, precomp=0) == (0, U.expected_from_dlogs(O.G1_GEN, many_d, many_sc))
+    assert lib.emu_last_fallback() == 1
+    monkeypatch.setenv("ZKMSM_NO_BUCKET_ACC", "1")
+    assert emu_g1(lib, pts, sc, c=5, precomp=1) == (0, exp)
+    assert lib.emu_last_fallback() == 0
+
+
 def test_emu_g1_mul_base_matches_reference_scalar_mul(lib):
     # `g * k` (macros.rs:2-32) incl. raw scalars >= r and the g1_point.rs:352-371 multiples
     ks = [0, 1, 2, 3, 12345, 1234567, 1234567890123456789, 123456789012345678901234567890,
@@ -292,21 +354,27 @@ def test_launch_plan_policies(lib):
     batched-affine pre-reduction (msm_default_batch_rounds) and the additions per thread of a round (msm_batch_T)"""
     slots = 148 * 256
 
-    def policy(logn, c=0, precomp=1, half=1, s=slots):
-        out = (ctypes.c_uint32 * 7)()
+    def policy(logn, c=0, precomp=1, half=1, s=slots, world=1):
+        out = (ctypes.c_uint32 * 10)()
+        out[7] = world
         lib.emu_policy(1 << logn, c, precomp, half, s, out)
-        return dict(zip(("c", "L", "rounds", "T", "threads", "K", "coop"), out))
+        return dict(zip(("c", "L", "rounds", "T", "threads", "K", "coop", "G", "cap", "nb"), out))
 
-    assert policy(17)["rounds"] == 0 and policy(16)["rounds"] == 0          # small sets: XYZZ accumulation only
+    assert policy(16)["rounds"] == 0                                        # small sets: bucket accumulation only
     assert policy(20, precomp=0)["rounds"] == 0                             # plain point sets: per-window buckets
     assert policy(20, s=0)["rounds"] == 0                                   # unknown device (CPU emulation)
     p20 = policy(20)
     assert p20["c"] == 17 and p20["rounds"] == 4 and p20["coop"] == 1 and p20["K"] == 16
-    assert policy(19)["rounds"] == 3 and policy(22)["rounds"] == 3 and policy(21)["rounds"] == 2
-    assert policy(18, c=16)["rounds"] == 2 and policy(18, c=17)["rounds"] == 0
+    assert p20["G"] == 1 and p20["cap"] >= 64                               # ~15 items per bucket left: one lane each
+    # rounds continue while a round keeps every resident thread at >= 8 additions and >= 12 items per bucket remain
+    assert policy(19)["rounds"] == 3 and policy(22)["rounds"] >= 3
+    assert policy(18, c=16)["rounds"] == 3 and policy(18, c=17)["rounds"] == 2
+    # bucket-range split over 8 devices: an eighth of the buckets and of the expected pairs, several lanes per bucket
+    p8 = policy(20, world=8)
+    assert p8["nb"] == (1 << 16) // 8 and p8["rounds"] in (2, 3) and p8["G"] >= 4
     for logn in (19, 20, 21, 22, 24):
         p = policy(logn)
-        assert 32 <= p["T"] <= 128
+        assert 8 <= p["T"] <= 128
         waves = p["threads"] / (slots * 3 // 2)                             # 3 blocks of 128 per SM
         assert waves <= round(waves) + 1e-9 or waves - int(waves) > 0.85     # whole waves (or nearly)
     # the chunk length of Accumulate fills whole waves of 2 x 128 threads per SM at small n
@@ -315,3 +383,12 @@ def test_launch_plan_policies(lib):
         entries = (1 << logn) * (254 // p["c"] + 1)
         threads = -(-entries // p["L"])
         assert threads / slots - int(threads / slots) > 0.8 or threads % slots == 0
+
+
+def test_sorted_pair_count_must_fit_32_bits(lib):
+    """a forced narrow window on a large set would wrap the 32-bit pair count (c = 4: 64 windows, n = 2^26 gives exactly
+    2^32): msm_fits is what zkmsm_*_msm checks before planning"""
+    lib.emu_fits.argtypes = [ctypes.c_uint64, ctypes.c_uint32, ctypes.c_int]
+    assert lib.emu_fits(1 << 26, 17, 1) == 1 and lib.emu_fits(1 << 26, 5, 0) == 1      # 52 windows
+    assert lib.emu_fits(1 << 26, 4, 0) == 0 and lib.emu_fits(1 << 26, 3, 0) == 0
+    assert lib.emu_fits((1 << 26) - 1, 4, 0) == 1 and lib.emu_fits(50_000_000, 3, 0) == 0

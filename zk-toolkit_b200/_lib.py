@@ -28,14 +28,17 @@ class ZkmsmError(RuntimeError):
 # every symbol include/zkmsm.h declares (checked by tests/test_abi.py)
 SYMBOLS = [
     "zkmsm_version", "zkmsm_create", "zkmsm_destroy", "zkmsm_set_stream", "zkmsm_last_error", "zkmsm_set_window",
+    "zkmsm_set_option",
     "zkmsm_host_alloc", "zkmsm_host_free",
     "zkmsm_g1_load_points", "zkmsm_g2_load_points", "zkmsm_points_free", "zkmsm_points_len", "zkmsm_points_info", "zkmsm_points_read",
     "zkmsm_g1_msm", "zkmsm_g2_msm", "zkmsm_g1_msm_device", "zkmsm_g2_msm_device",
     "zkmsm_g1_msm_oneshot", "zkmsm_g2_msm_oneshot",
     "zkmsm_g1_msm_enqueue", "zkmsm_g2_msm_enqueue", "zkmsm_g1_msm_begin", "zkmsm_g2_msm_begin", "zkmsm_g1_msm_result", "zkmsm_g2_msm_result",
     "zkmsm_last_launch_count", "zkmsm_profile", "zkmsm_profile_read",
-    "zkmsm_g1_msm_partial", "zkmsm_g2_msm_partial", "zkmsm_g1_msm_partial_device",
-    "zkmsm_g1_combine", "zkmsm_g2_combine", "zkmsm_g1_combine_device",
+    "zkmsm_g1_msm_partial", "zkmsm_g2_msm_partial", "zkmsm_g1_msm_partial_device", "zkmsm_g2_msm_partial_device",
+    "zkmsm_g1_msm_partial_range", "zkmsm_g2_msm_partial_range",
+    "zkmsm_g1_msm_partial_range_device", "zkmsm_g2_msm_partial_range_device",
+    "zkmsm_g1_combine", "zkmsm_g2_combine", "zkmsm_g1_combine_device", "zkmsm_g2_combine_device",
     "zkmsm_g1_mul_base", "zkmsm_g2_mul_base", "zkmsm_g1_points_from_scalars", "zkmsm_g2_points_from_scalars",
     "zkmsm_fr_aggregate", "zkmsm_fr_quotient", "zkmsm_bench_imad",
 ]
@@ -64,6 +67,7 @@ def load():
         "zkmsm_set_stream": (ci, [vp, vp]),
         "zkmsm_last_error": (ctypes.c_char_p, [vp]),
         "zkmsm_set_window": (ci, [vp, cu]),
+        "zkmsm_set_option": (ci, [vp, ctypes.c_char_p, ctypes.c_long]),
         "zkmsm_host_alloc": (ci, [sz, vpp]),
         "zkmsm_host_free": (ci, [vp]),
         "zkmsm_g1_load_points": (ci, [vp, vp, vp, sz, cu, vpp]),
@@ -90,9 +94,15 @@ def load():
         "zkmsm_g1_msm_partial": (ci, [vp, vp, vp, sz, vp]),
         "zkmsm_g2_msm_partial": (ci, [vp, vp, vp, sz, vp]),
         "zkmsm_g1_msm_partial_device": (ci, [vp, vp, vp, sz, vp]),
+        "zkmsm_g2_msm_partial_device": (ci, [vp, vp, vp, sz, vp]),
+        "zkmsm_g1_msm_partial_range": (ci, [vp, vp, vp, sz, cu, cu, vp]),
+        "zkmsm_g2_msm_partial_range": (ci, [vp, vp, vp, sz, cu, cu, vp]),
+        "zkmsm_g1_msm_partial_range_device": (ci, [vp, vp, vp, sz, cu, cu, vp]),
+        "zkmsm_g2_msm_partial_range_device": (ci, [vp, vp, vp, sz, cu, cu, vp]),
         "zkmsm_g1_combine": (ci, [vp, vp, sz, vp, ip]),
         "zkmsm_g2_combine": (ci, [vp, vp, sz, vp, ip]),
         "zkmsm_g1_combine_device": (ci, [vp, vp, sz, vp, ip]),
+        "zkmsm_g2_combine_device": (ci, [vp, vp, sz, vp, ip]),
         "zkmsm_g1_mul_base": (ci, [vp, vp, vp, sz, vp, vp]),
         "zkmsm_g2_mul_base": (ci, [vp, vp, vp, sz, vp, vp]),
         "zkmsm_g1_points_from_scalars": (ci, [vp, vp, vp, sz, cu, vpp]),

@@ -91,6 +91,10 @@ class Context:
     def set_window(self, c):
         self._check(self.lib.zkmsm_set_window(self.h, c))
 
+    def set_option(self, name, value):
+        """tuning / cross-check switch of this context (zkmsm_set_option; the ZKMSM_* environment is read once, at creation)"""
+        self._check(self.lib.zkmsm_set_option(self.h, name.encode(), int(value)))
+
     # ---- point sets
     def _words(self, group):
         return L.G1_WORDS if group == 1 else L.G2_WORDS
@@ -220,9 +224,22 @@ class Context:
         return out
 
     def msm_partial_device(self, pts: PointSet, scalars_dev_ptr, n, out_dev_ptr):
-        assert pts.group == 1
-        self._check(self.lib.zkmsm_g1_msm_partial_device(self.h, pts.handle, ctypes.c_void_p(scalars_dev_ptr), n,
-                                                         ctypes.c_void_p(out_dev_ptr)))
+        fn = self.lib.zkmsm_g1_msm_partial_device if pts.group == 1 else self.lib.zkmsm_g2_msm_partial_device
+        self._check(fn(self.h, pts.handle, ctypes.c_void_p(scalars_dev_ptr), n, ctypes.c_void_p(out_dev_ptr)))
+
+    def msm_partial_range(self, pts: PointSet, scalars, rank, world, n=None):
+        """this rank's share of the MSM under the bucket-range split (whole precomputed set on every device)"""
+        sc = L.as_u32(scalars, 8).reshape(-1, 8) if len(scalars) else np.zeros((0, 8), dtype=np.uint32)
+        n = sc.shape[0] if n is None else n
+        words = L.G1_PARTIAL_WORDS if pts.group == 1 else L.G2_PARTIAL_WORDS
+        out = np.zeros(words, dtype=np.uint32)
+        fn = self.lib.zkmsm_g1_msm_partial_range if pts.group == 1 else self.lib.zkmsm_g2_msm_partial_range
+        self._check(fn(self.h, pts.handle, L.dptr(sc), n, rank, world, L.dptr(out)))
+        return out
+
+    def msm_partial_range_device(self, pts: PointSet, scalars_dev_ptr, n, rank, world, out_dev_ptr):
+        fn = self.lib.zkmsm_g1_msm_partial_range_device if pts.group == 1 else self.lib.zkmsm_g2_msm_partial_range_device
+        self._check(fn(self.h, pts.handle, ctypes.c_void_p(scalars_dev_ptr), n, rank, world, ctypes.c_void_p(out_dev_ptr)))
 
     def combine(self, group, partials):
         words = L.G1_PARTIAL_WORDS if group == 1 else L.G2_PARTIAL_WORDS
@@ -233,11 +250,11 @@ class Context:
         self._check(fn(self.h, L.dptr(parts), parts.shape[0], L.dptr(out), ctypes.byref(inf)))
         return out, bool(inf.value)
 
-    def combine_device(self, partials_dev_ptr, k):
-        out = np.zeros(L.G1_WORDS, dtype=np.uint32)
+    def combine_device(self, partials_dev_ptr, k, group=1):
+        out = np.zeros(self._words(group), dtype=np.uint32)
         inf = ctypes.c_int(0)
-        self._check(self.lib.zkmsm_g1_combine_device(self.h, ctypes.c_void_p(partials_dev_ptr), k, L.dptr(out),
-                                                     ctypes.byref(inf)))
+        fn = self.lib.zkmsm_g1_combine_device if group == 1 else self.lib.zkmsm_g2_combine_device
+        self._check(fn(self.h, ctypes.c_void_p(partials_dev_ptr), k, L.dptr(out), ctypes.byref(inf)))
         return out, bool(inf.value)
 
     def fr_aggregate(self, polys, wires):

@@ -210,7 +210,7 @@ template <class F> __device__ __forceinline__ void lane_tree(const Slots<F>& S, 
 
 template <class F> constexpr size_t smem_bytes() { return (size_t)S_TOTAL * (sizeof(F) / 4) * 32 * 4 + sizeof(Flags); }
 
-// 32 chains per block; chain (win, k): out = sum_{i<K} (k K + i + 1) * bucket[win*B + k*K + i]   (as BucketReduce)
+// 32 chains per block; chain (win, k): out = sum_{i<K} (b_lo + k K + i + 1) * bucket[win*B + k*K + i]   (as BucketReduce)
 template <class C>
 __global__ void __launch_bounds__(kThreads) bucket_reduce_kernel(MsmPlan p, const uint32_t* offsets,
                                                                  const XYZZ<typename C::F>* bucket_sums,
@@ -235,9 +235,10 @@ __global__ void __launch_bounds__(kThreads) bucket_reduce_kernel(MsmPlan p, cons
     point_add(S, fl, S_RUN, S_Q, S_TMP, false);
     point_add(S, fl, S_ACC, S_RUN, S_TMP, false);
   }
-  // run = (k K) * run, MSB first over the bit length of the largest multiplier (uniform for the grid)
-  const uint32_t s = k * p.K;
-  int nbits = 32 - __clz((chunks - 1) * p.K | 1u);
+  // run = (b_lo + k K) * run, MSB first over the bit length of the largest multiplier (uniform for the grid);
+  // b_lo (bucket-range split) is a multiple of B, hence of K
+  const uint32_t s = p.b_lo + k * p.K;
+  int nbits = 32 - __clz((p.b_lo + (chunks - 1) * p.K) | 1u);
   point_copy(S, S_BASE, S_RUN);
   __syncthreads();
   point_set_inf(S, S_RUN);
@@ -320,13 +321,18 @@ __global__ void __launch_bounds__(kThreads) finish_kernel(uint32_t nwin, uint32_
 // sum of k <= 32 partial points (multi-GPU combine): lane i holds partial i, 5-level tree across lanes
 template <class C>
 __global__ void __launch_bounds__(kThreads) combine_kernel(uint32_t k, const XYZZ<typename C::F>* parts,
-                                                           uint32_t* out_affine, uint32_t* out_inf) {
+                                                           uint32_t* out_affine, uint32_t* out_inf, uint32_t* err) {
   typedef typename C::F F;
   extern __shared__ __align__(16) uint32_t smem[];
   Slots<F> S{smem};
   Flags* fl = reinterpret_cast<Flags*>(smem + (size_t)S_TOTAL * Slots<F>::NL * 32);
   const int l = threadIdx.x & 31;
-  point_load_global(S, S_ACC, parts + l, (uint32_t)l < k);
+  bool present = (uint32_t)l < k;
+  if (present && is_poisoned(parts[l])) {   // a rank saw an out-of-range scalar (PoisonPartial, msm.cuh)
+    if (threadIdx.x < 32) atomicOr(err, ERR_SCALAR_RANGE);
+    present = false;
+  }
+  point_load_global(S, S_ACC, parts + l, present);
   __syncthreads();
   lane_tree(S, fl, k);
   if (threadIdx.x == 0) {

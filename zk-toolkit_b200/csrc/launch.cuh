@@ -58,9 +58,20 @@ cudaError_t zk_coop_row_sum_g1(cudaStream_t st, uint32_t nwin, uint32_t pitch_in
 cudaError_t zk_coop_finish_g1(cudaStream_t st, uint32_t nwin, uint32_t pitch, uint32_t c, const XYZZ<Mont<FqCfg>>* arr,
                               XYZZ<Mont<FqCfg>>* out_xyzz, uint32_t* out_affine, uint32_t* out_inf);
 cudaError_t zk_coop_combine_g1(cudaStream_t st, uint32_t k, const XYZZ<Mont<FqCfg>>* parts, uint32_t* out_affine,
-                               uint32_t* out_inf);
+                               uint32_t* out_inf, uint32_t* err);
 template <class C> struct Finish;
 struct Fp2;
+struct Entry;
+template <class F> struct Affine;
+cudaError_t zk_bucket_acc_g1(cudaStream_t st, const MsmPlan& p, const uint32_t* offsets, const Entry* entries,
+                             const Affine<Mont<FqCfg>>* points, uint32_t direct, XYZZ<Mont<FqCfg>>* bucket_sums, uint32_t* big);
+cudaError_t zk_bucket_acc_g2(cudaStream_t st, const MsmPlan& p, const uint32_t* offsets, const Entry* entries,
+                             const Affine<Fp2>* points, uint32_t direct, XYZZ<Fp2>* bucket_sums, uint32_t* big);
+// per-device opt-in to > 48 KB of dynamic shared memory for every kernel that needs it (once per device, before the
+// first launch there; zkmsm_create calls it for the context's device)
+cudaError_t zk_opt_in_shared_memory_coop_g1();
+cudaError_t zk_opt_in_shared_memory_coop_g2();
+cudaError_t zk_opt_in_shared_memory_ntt();
 cudaError_t zk_coop_bucket_reduce_g2(cudaStream_t st, const MsmPlan& p, const uint32_t* offsets, const XYZZ<Fp2>* buckets,
                                      XYZZ<Fp2>* out, int tree);
 cudaError_t zk_coop_row_sum_g2(cudaStream_t st, uint32_t nwin, uint32_t pitch_in, uint32_t m, uint32_t per_block,
@@ -90,7 +101,9 @@ struct CudaExec {
   int launches;
   cudaError_t err;
   LaunchProfile* prof;
-  explicit CudaExec(cudaStream_t s, LaunchProfile* p = nullptr) : st(s), launches(0), err(cudaSuccess), prof(p) {}
+  bool no_coop, ntt_no_fuse;   // cross-check switches (MsmTuning), fixed per context
+  explicit CudaExec(cudaStream_t s, LaunchProfile* p = nullptr, bool no_coop_ = false, bool ntt_no_fuse_ = false)
+      : st(s), launches(0), err(cudaSuccess), prof(p), no_coop(no_coop_), ntt_no_fuse(ntt_no_fuse_) {}
   template <class Body, class... Args>
   void launch(uint32_t nthreads, Args... args) {
     if (nthreads == 0 || err != cudaSuccess) return;
@@ -121,6 +134,16 @@ struct CudaExec {
     launches += nlaunch;
     if (e != cudaSuccess) err = e;
   }
+  // bucket sums with acc_G lanes per bucket meeting in a shuffle tree (tu_g{1,2}_bacc.cu)
+  template <class C, class P, class E, class A, class Pt>
+  void accumulate_buckets(const P& p, const uint32_t* offsets, const E* entries, const A* points, uint32_t direct, Pt* bucket_sums,
+                          uint32_t* big) {
+    const uint32_t threads = p.nb * p.acc_G;
+    if (std::is_same<C, G1>::value)
+      timed("accumulate_buckets", threads, 1, [&] { return zk_bucket_acc_g1(st, p, offsets, entries, (const Affine<Mont<FqCfg>>*)points, direct, (XYZZ<Mont<FqCfg>>*)bucket_sums, big); });
+    else
+      timed("accumulate_buckets", threads, 1, [&] { return zk_bucket_acc_g2(st, p, offsets, entries, (const Affine<Fp2>*)points, direct, (XYZZ<Fp2>*)bucket_sums, big); });
+  }
   // stages 6 / 7 of the MSM: block-cooperative kernels (coop.cuh), per-thread bodies as the wide / fallback path.
   // bucket_reduce returns the row length it left per window (row pitch stays B / K): the cooperative kernel also
   // sums the 32 chains of each block when they share a window.
@@ -145,7 +168,7 @@ struct CudaExec {
   // levels alternating between arr and scratch (nwin * (pitch / 32 + 1) points).
   template <class C, class Pt>
   RowRef<Pt> window_tree(uint32_t nwin, uint32_t pitch, uint32_t m, Pt* arr, Pt* scratch) {
-    const bool coop_ok = !getenv("ZKMSM_NO_COOP");
+    const bool coop_ok = !no_coop;
     while (m > 1 && (!coop_ok || (uint64_t)nwin * m > 16384)) {
       uint32_t half = (m + 1) / 2;
       launch<PairSum<C>>(nwin * half, nwin, pitch, m, half, arr);
@@ -169,7 +192,7 @@ struct CudaExec {
   // stage 8: Horner over the windows runs cooperatively for G1 when there is more than one window
   template <class C, class Pt>
   void finish(uint32_t nwin, uint32_t pitch, uint32_t c, const Pt* arr, Pt* out_xyzz, uint32_t* out_affine, uint32_t* out_inf) {
-    if (std::is_same<C, G1>::value && nwin > 1 && !getenv("ZKMSM_NO_COOP"))
+    if (std::is_same<C, G1>::value && nwin > 1 && !no_coop)
       timed("finish", 1, 1, [&] { return zk_coop_finish_g1(st, nwin, pitch, c, (const XYZZ<Mont<FqCfg>>*)arr, (XYZZ<Mont<FqCfg>>*)out_xyzz, out_affine, out_inf); });
     else
       launch<Finish<C>>(1u, nwin, pitch, c, arr, out_xyzz, out_affine, out_inf);
@@ -177,7 +200,7 @@ struct CudaExec {
   // several transform stages in one shared-memory pass (tu_fr_ntt.cu); false = shape not supported, launch the stages
   bool ntt_fused(bool inverse, Mont<FrCfg>* a, uint32_t total, uint32_t L0, uint32_t k, const Mont<FrCfg>* tw, uint32_t m) {
     if (err != cudaSuccess) return true;
-    if (getenv("ZKMSM_NTT_NO_FUSE")) return false;
+    if (ntt_no_fuse) return false;
     int slot = -1;
     if (prof && prof->n < LaunchProfile::MAX) {
       slot = prof->n;

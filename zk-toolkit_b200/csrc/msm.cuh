@@ -82,6 +82,11 @@ struct MsmPlan {
   uint32_t acc_slots;     // accumulate threads the device keeps resident at 2 blocks of 128 per SM (0 = unknown)
   uint32_t half;          // 1: point set is in the prime-order subgroup; scalars s > (r-1)/2 become r - s with
                           //    the point negated, so 254 bits are recoded and no carry-only top window exists
+  uint32_t b_lo;          // bucket-range split (precomputed sets): this plan owns the global buckets [b_lo, b_lo + B)
+                          //    of the 2^(c-1) and keeps only the digits that fall there; 0 with B = 2^(c-1) otherwise
+  uint32_t acc_G;         // > 0: bucket sums by AccumulateBuckets with acc_G lanes per bucket (no fix-up tree unless
+                          //    a bucket holds more than acc_cap items); 0: chunked Accumulate + fix-up tree
+  uint32_t acc_cap;       //    items per bucket above which the chunked fallback takes over
 };
 
 // ---------------------------------------------------------------- signed-digit recoding
@@ -144,7 +149,8 @@ struct RecodeCount {
     for (uint32_t w = 0; w < p.W; w++) {
       int32_t d = dg.next(w);
       if (d == 0) continue;
-      uint32_t mag = (uint32_t)(d < 0 ? -d : d) - 1;
+      uint32_t mag = (uint32_t)(d < 0 ? -d : d) - 1 - p.b_lo;   // wraps below the range
+      if (mag >= p.B) continue;                                 // another rank's bucket (range split)
       zk_atomic_add(&hist[(p.precomp ? 0 : w * p.B) + mag], 1u);
     }
   }
@@ -195,7 +201,8 @@ struct Scatter {
     for (uint32_t w = 0; w < p.W; w++) {
       int32_t d = dg.next(w);
       if (d == 0) continue;
-      uint32_t neg = d < 0, mag = (uint32_t)(neg ? -d : d) - 1;
+      uint32_t neg = d < 0, mag = (uint32_t)(neg ? -d : d) - 1 - p.b_lo;
+      if (mag >= p.B) continue;
       neg ^= negate ? 1u : 0u;
       uint32_t key = (p.precomp ? 0 : w * p.B) + mag;
       uint32_t idx = p.precomp ? w * p.stride + tid : tid;
@@ -216,8 +223,11 @@ inline uint32_t fix_fan(uint32_t level) { return level == 0 ? 4u : (level <= 2 ?
 template <class C> struct Accumulate {
   typedef typename C::F F;
   static const char* name() { return "accumulate"; }
+  // gate (nullable): the launch is the fallback of AccumulateBuckets and does nothing unless *gate != 0
   static ZK_HD void run(uint32_t tid, MsmPlan p, const uint32_t* offsets, const Entry* entries,
-                        const Affine<F>* points, XYZZ<F>* bucket_sums, XYZZ<F>* partials, uint32_t* partial_keys) {
+                        const Affine<F>* points, XYZZ<F>* bucket_sums, XYZZ<F>* partials, uint32_t* partial_keys,
+                        const uint32_t* gate) {
+    if (gate && *gate == 0) return;
     uint32_t total = offsets[p.nb];
     uint64_t beg64 = (uint64_t)tid * p.L;
     if (beg64 >= total) { partial_keys[tid] = NO_KEY; return; }
@@ -265,6 +275,59 @@ template <class C> struct Accumulate {
   }
 };
 
+// Bucket sums with G lanes per bucket (G a power of two <= 32, chosen so that the launch fills the device): lane g
+// adds the items s + g, s + g + G, .. of its bucket with mixed additions; the G partial sums then meet in a
+// log2(G)-level tree (register shuffles on the device, BucketAccTree on the CPU emulation).  Every bucket is
+// complete after this one launch -- no partial sums, no fix-up tree -- which is what the batched-affine rounds
+// leave behind (8..24 items per bucket) and what small shards look like.  A bucket with more than p.acc_cap items
+// (skewed scalars) raises *big and is left alone: the chunked Accumulate + FixupLevel launches that follow are
+// gated on that flag and then redo all buckets, balanced for any distribution.
+//   direct != 0: item i is points[i] (output of a batched round); else item i is entries[i] -> (index, sign).
+template <class C> struct BucketAccLane {
+  typedef typename C::F F;
+  static ZK_HD Affine<F> item(uint32_t i, const Entry* entries, const Affine<F>* points, uint32_t direct) {
+    if (direct) return points[i];
+    Entry e = entries[i];
+    Affine<F> q = points[e.val & 0x7fffffffu];
+    affine_cneg(q, (e.val >> 31) != 0);
+    return q;
+  }
+  // returns false when the bucket is over the cap (acc is infinity then)
+  static ZK_HD bool run(XYZZ<F>& acc, uint32_t s, uint32_t e, uint32_t g, uint32_t G, uint32_t cap, const Entry* entries,
+                        const Affine<F>* points, uint32_t direct) {
+    set_inf(acc);
+    if (e - s > cap) return false;
+    uint32_t i = s + g;
+    if (i >= e) return true;
+    Affine<F> qn = item(i, entries, points, direct);
+    for (; i < e; i += G) {
+      Affine<F> q = qn;
+      if (i + G < e) qn = item(i + G, entries, points, direct);   // next item rides under this mixed add
+      xyzz_madd(acc, q);
+    }
+    return true;
+  }
+};
+// the emulation's form of the launch: one logical thread per bucket runs the G lanes one after the other and
+// folds them in the order of the device's shuffle tree
+template <class C> struct AccumulateBucketsRef {
+  typedef typename C::F F;
+  static const char* name() { return "accumulate_buckets"; }
+  static ZK_HD void run(uint32_t tid, MsmPlan p, const uint32_t* offsets, const Entry* entries, const Affine<F>* points,
+                        uint32_t direct, XYZZ<F>* bucket_sums, uint32_t* big) {
+    if (tid >= p.nb) return;
+    const uint32_t s = offsets[tid], e = offsets[tid + 1], G = p.acc_G;
+    if (s == e) return;
+    XYZZ<F> lane[32];
+    bool ok = true;
+    for (uint32_t g = 0; g < G; g++) ok = BucketAccLane<C>::run(lane[g], s, e, g, G, p.acc_cap, entries, points, direct) && ok;
+    if (!ok) { zk_atomic_or(big, 1u); return; }
+    for (uint32_t d = G / 2; d >= 1; d >>= 1)
+      for (uint32_t g = 0; g < d; g++) xyzz_add(lane[g], lane[g + d]);
+    bucket_sums[tid] = lane[0];
+  }
+};
+
 // One level of the fix-up tree.  Input: `count` partial sums in bucket order, keys_in[t] = bucket the
 // partial continues (NO_KEY = none).  Thread u folds `fan` consecutive partials: a run of equal keys
 // that STARTS inside the thread's range is added to its bucket sum (exactly one thread per bucket and
@@ -274,7 +337,8 @@ template <class C> struct FixupLevel {
   typedef typename C::F F;
   static const char* name() { return "fixup_level"; }
   static ZK_HD void run(uint32_t tid, uint32_t count, uint32_t fan, const uint32_t* keys_in, const XYZZ<F>* parts_in,
-                        uint32_t* keys_out, XYZZ<F>* parts_out, XYZZ<F>* bucket_sums) {
+                        uint32_t* keys_out, XYZZ<F>* parts_out, XYZZ<F>* bucket_sums, const uint32_t* gate) {
+    if (gate && *gate == 0) return;
     uint32_t beg = tid * fan;
     if (beg >= count) return;
     uint32_t end = beg + fan < count ? beg + fan : count;
@@ -505,7 +569,7 @@ template <class F> ZK_HD void xyzz_mul_small(XYZZ<F>& p, uint32_t s) {
   }
 }
 
-// thread (win, k): out = sum_{i<K} (k K + i + 1) * bucket[win*B + k*K + i]; empty buckets were never written
+// thread (win, k): out = sum_{i<K} (b_lo + k K + i + 1) * bucket[win*B + k*K + i]; empty buckets were never written
 template <class C> struct BucketReduce {
   typedef typename C::F F;
   static const char* name() { return "bucket_reduce"; }
@@ -521,7 +585,7 @@ template <class C> struct BucketReduce {
       if (offsets[base + i] != offsets[base + i + 1]) { XYZZ<F> q = bucket_sums[base + i]; xyzz_add_ilp(run, q); }
       xyzz_add_ilp(acc, run);
     }
-    xyzz_mul_small(run, k * p.K);
+    xyzz_mul_small(run, p.b_lo + k * p.K);
     xyzz_add_ilp(acc, run);
     out[tid] = acc;
   }
@@ -581,15 +645,41 @@ template <class C> struct Finish {
   }
 };
 
-// sum of k XYZZ partial results (multi-GPU combine) -> canonical affine
+// A partial whose MSM saw an out-of-range scalar is exported POISONED (ZZ = 0, ZZZ = all ones: not a field
+// element), so that the error travels with the blob through any gather and the combine step reports it.
+template <class F> ZK_HD void poison_partial(XYZZ<F>& q) {
+  uint32_t* w = reinterpret_cast<uint32_t*>(&q);
+  constexpr int NL = sizeof(F) / 4;
+  for (int i = 0; i < NL; i++) { w[2 * NL + i] = 0; w[3 * NL + i] = 0xffffffffu; }
+}
+template <class F> ZK_HD bool is_poisoned(const XYZZ<F>& q) {
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(&q);
+  constexpr int NL = sizeof(F) / 4;
+  uint32_t all = 0xffffffffu, zz = 0;
+  for (int i = 0; i < NL; i++) { all &= w[3 * NL + i]; zz |= w[2 * NL + i]; }
+  return all == 0xffffffffu && zz == 0;
+}
+template <class C> struct PoisonPartial {   // after Finish, when the partial leaves the context without a status read
+  typedef typename C::F F;
+  static const char* name() { return "poison_partial"; }
+  static ZK_HD void run(uint32_t tid, const uint32_t* err, XYZZ<F>* out) {
+    if (tid == 0 && *err) poison_partial(*out);
+  }
+};
+
+// sum of k XYZZ partial results (multi-GPU combine) -> canonical affine; *err |= ERR_SCALAR_RANGE for a poisoned partial
 template <class C> struct CombinePartials {
   typedef typename C::F F;
   static const char* name() { return "combine_partials"; }
-  static ZK_HD void run(uint32_t tid, uint32_t k, const XYZZ<F>* parts, uint32_t* out_affine, uint32_t* out_inf) {
+  static ZK_HD void run(uint32_t tid, uint32_t k, const XYZZ<F>* parts, uint32_t* out_affine, uint32_t* out_inf, uint32_t* err) {
     if (tid != 0) return;
     XYZZ<F> acc;
     set_inf(acc);
-    for (uint32_t i = 0; i < k; i++) { XYZZ<F> q = parts[i]; xyzz_add_ilp(acc, q); }
+    for (uint32_t i = 0; i < k; i++) {
+      XYZZ<F> q = parts[i];
+      if (is_poisoned(q)) { zk_atomic_or(err, ERR_SCALAR_RANGE); continue; }
+      xyzz_add_ilp(acc, q);
+    }
     Affine<F> a;
     xyzz_to_affine(a, acc);
     store_canonical<F>(out_affine, a);
@@ -688,6 +778,40 @@ template <class C> struct StorePoints {
 };
 
 // ---------------------------------------------------------------- planning
+// Tuning / cross-check switches.  The product reads the environment ONCE per context (zkmsm_create) and lets
+// zkmsm_set_option override single fields; the CPU emulation reads it per call.  -1 / 0 = automatic.
+struct MsmTuning {
+  int batch_rounds = -1;   // ZKMSM_BATCH_ROUNDS: force the number of batched-affine rounds (0 = off)
+  int batch_T = 0;         // ZKMSM_BATCH_T: additions sharing one inversion (2..128)
+  int batch_g2 = 0;        // ZKMSM_BATCH_G2: forced rounds also apply to G2
+  int batch_blocks = 0;    // ZKMSM_BATCH_BLOCKS: resident blocks per SM assumed for the batched kernel (A/B builds)
+  int L = 0;               // ZKMSM_L: sorted pairs per accumulate thread
+  int K = 0;               // ZKMSM_K: buckets per reduction chain (power of two)
+  int no_wave_L = 0;       // ZKMSM_NO_WAVE_L
+  int no_coop = 0;         // ZKMSM_NO_COOP: per-thread tail kernels
+  int ntt_no_fuse = 0;     // ZKMSM_NTT_NO_FUSE
+  int quotient_schoolbook = 0;   // ZKMSM_QUOTIENT_SCHOOLBOOK
+  int no_graph = 0;        // ZKMSM_NO_GRAPH: launch kernel by kernel instead of replaying a captured CUDA graph
+  int no_bucket_acc = 0;   // ZKMSM_NO_BUCKET_ACC: always the chunked accumulation + fix-up tree
+  static int env_int(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; }
+  static MsmTuning from_env() {
+    MsmTuning t;
+    t.batch_rounds = env_int("ZKMSM_BATCH_ROUNDS", -1);
+    t.batch_T = env_int("ZKMSM_BATCH_T", 0);
+    t.batch_g2 = getenv("ZKMSM_BATCH_G2") ? 1 : 0;
+    t.batch_blocks = env_int("ZKMSM_BATCH_BLOCKS", 0);
+    t.L = env_int("ZKMSM_L", 0);
+    t.K = env_int("ZKMSM_K", 0);
+    t.no_wave_L = getenv("ZKMSM_NO_WAVE_L") ? 1 : 0;
+    t.no_coop = getenv("ZKMSM_NO_COOP") ? 1 : 0;
+    t.ntt_no_fuse = getenv("ZKMSM_NTT_NO_FUSE") ? 1 : 0;
+    t.quotient_schoolbook = getenv("ZKMSM_QUOTIENT_SCHOOLBOOK") ? 1 : 0;
+    t.no_graph = getenv("ZKMSM_NO_GRAPH") ? 1 : 0;
+    t.no_bucket_acc = getenv("ZKMSM_NO_BUCKET_ACC") ? 1 : 0;
+    return t;
+  }
+};
+
 // windows needed for 255-bit scalars (254-bit after the half-range fold): the last one absorbs the recoding carry
 inline uint32_t msm_windows(uint32_t c, bool half = false) { return (half ? 254u : 255u) / c + 1; }
 
@@ -712,23 +836,36 @@ inline uint32_t msm_pick_c(uint32_t n, bool precomp, bool half = false) {
   return best;
 }
 
+// true when the sorted-pair count of an MSM of n terms at window c fits the 32-bit positions the kernels use
+inline bool msm_fits(uint64_t n, uint32_t c, bool half = false) { return n * msm_windows(c, half) < (1ull << 32); }
+
 // acc_slots: accumulate threads the device keeps resident (SMs x 256 at 2 blocks of 128 per SM), 0 = unknown.
+// (rank, world): bucket-range split of a precomputed set over `world` devices (a power of two <= 2^(c-1)); the plan
+// then owns 2^(c-1) / world buckets and expects 1 / world of the sorted pairs (the buffers stay sized for all of them).
 inline MsmPlan msm_plan(uint32_t n, uint32_t c, bool precomp, uint32_t stride, bool half = false, bool coop_tail = false,
-                        uint32_t acc_slots = 0) {
+                        uint32_t acc_slots = 0, const MsmTuning& tune = MsmTuning(), uint32_t rank = 0, uint32_t world = 1) {
   MsmPlan p;
   p.n = n;
   p.c = c;
   p.half = half ? 1 : 0;
   p.W = msm_windows(c, half);
   p.B = 1u << (c - 1);
+  p.b_lo = 0;
   p.precomp = precomp ? 1 : 0;
+  if (precomp && world > 1 && (world & (world - 1)) == 0 && world <= p.B && rank < world) {
+    p.B /= world;
+    p.b_lo = rank * p.B;
+  }
   p.nwin = precomp ? 1 : p.W;
   p.nb = p.nwin * p.B;
   p.stride = stride;
-  p.max_entries = n * p.W;
+  const uint64_t entries64 = (uint64_t)n * p.W;
+  p.max_entries = entries64 < (1ull << 32) ? (uint32_t)entries64 : 0xffffffffu;   // callers reject the latter (msm_fits)
   p.acc_slots = acc_slots;
+  p.acc_G = 0;
+  p.acc_cap = 0;
   p.L = p.max_entries >= (1u << 23) ? 32 : (p.max_entries >= (1u << 21) ? 16 : 8);
-  if (acc_slots && !getenv("ZKMSM_NO_WAVE_L")) {
+  if (acc_slots && !tune.no_wave_L) {
     // Wave quantisation: every resident slot runs ceil(threads / slots) threads of L mixed additions one after the
     // other, so with few waves (small n) the last, partly filled wave costs a whole one.  Take the L near the
     // default that minimises waves x L (ties: the larger L, fewer partial sums for the fix-up tree).
@@ -745,22 +882,45 @@ inline MsmPlan msm_plan(uint32_t n, uint32_t c, bool precomp, uint32_t stride, b
   if (p.K > p.B) p.K = p.B;
   p.batch_rounds = 0;                        // see msm_default_batch_rounds()
   p.batch_T = 128;
-  if (const char* e = getenv("ZKMSM_BATCH_ROUNDS")) { uint32_t v = (uint32_t)atoi(e); if (v <= 8) p.batch_rounds = v; }
-  if (const char* e = getenv("ZKMSM_BATCH_T")) { uint32_t v = (uint32_t)atoi(e); if (v >= 2 && v <= 128) p.batch_T = v; }   // <= 128: one flag bit per output in two words
+  if (tune.batch_rounds >= 0 && tune.batch_rounds <= 8) p.batch_rounds = (uint32_t)tune.batch_rounds;
+  if (tune.batch_T >= 2 && tune.batch_T <= 128) p.batch_T = (uint32_t)tune.batch_T;   // <= 128: one flag bit per output in two words
   p.coop = 0;
-  if (coop_tail) {
-    // cooperative reduction: 32 chains per 4-warp block, aim at <= ~one block per SM (148 x 32 = 4736 chains) so
-    // every chain runs at single-block latency; give up (per-thread kernel) when that needs K > 64
+  if (coop_tail && !tune.no_coop) {
+    // cooperative reduction: 32 chains per 4-warp block.  Up to ~one block per SM (148 x 32 = 4736 chains) every chain
+    // runs at single-block latency; give up (per-thread kernel) when that needs K > 64
     // (2^19 buckets at K = 64: 256 blocks, 0.9 ms against 1.8 ms for the per-thread kernel at K = 32)
     uint32_t k = 2;
     while (k < 64 && (uint64_t)p.nwin * (p.B / k) > 4736) k *= 2;
     if (k <= p.B && (uint64_t)p.nwin * (p.B / k) <= 2 * 4736) { p.K = k; p.coop = 1; }
   }
-  if (const char* e = getenv("ZKMSM_L")) { uint32_t v = (uint32_t)atoi(e); if (v >= 1 && v <= 4096) p.L = v; }   // tuning overrides
-  if (const char* e = getenv("ZKMSM_K")) { uint32_t v = (uint32_t)atoi(e); if (v >= 1 && v <= p.B && (v & (v - 1)) == 0) p.K = v; }
+  if (tune.L >= 1 && tune.L <= 4096) p.L = (uint32_t)tune.L;   // tuning overrides
+  if (tune.K >= 1 && (uint32_t)tune.K <= p.B && (tune.K & (tune.K - 1)) == 0) p.K = (uint32_t)tune.K;
   p.acc_threads = (p.max_entries + p.L - 1) / p.L;
   if (p.acc_threads == 0) p.acc_threads = 1;
   return p;
+}
+
+// sorted pairs this plan expects for uniformly random scalars (the buffers hold max_entries, the worst case)
+inline uint64_t msm_expected_entries(const MsmPlan& p) {
+  const uint64_t full = (uint64_t)1 << (p.c - 1);
+  return p.precomp ? (uint64_t)p.max_entries * p.B / full : p.max_entries;
+}
+
+// Lanes per bucket and item cap for AccumulateBuckets when about `left` items in total are expected in the plan's
+// buckets: enough lanes that the launch is about two waves of the device, never more lanes than half the items of
+// an average bucket, at most ~256 items per lane before the chunked fallback is the better kernel.
+inline void msm_pick_bucket_acc(MsmPlan& p, uint64_t left, const MsmTuning& tune) {
+  p.acc_G = 0;
+  p.acc_cap = 0;
+  if (tune.no_bucket_acc || p.nb == 0) return;
+  const uint64_t avg = left / p.nb + 1;
+  uint32_t G = 1;
+  const uint64_t slots = p.acc_slots ? p.acc_slots : 32768;
+  while (G < 32 && (uint64_t)p.nb * G * 2 <= 2 * slots && (uint64_t)G * 2 <= (avg + 1) / 2) G *= 2;
+  if (avg / G > 256) return;   // huge buckets without pre-reduction (narrow forced windows): chunks balance better
+  p.acc_G = G;
+  const uint64_t cap = 4 * avg + 32 * G;
+  p.acc_cap = cap > 0x7fffffffu ? 0x7fffffffu : (uint32_t)cap;
 }
 
 // slots needed for the partial sums of all fix-up levels
@@ -771,33 +931,39 @@ inline size_t msm_partial_slots(const MsmPlan& p) {
   return total + 1;
 }
 
-// Rounds of batched-affine pre-reduction for a G1 set with precomputed slabs on a real device (measured on B200,
-// profiles/r1_batched_affine.log): an affine addition sharing its inversion costs ~0.29 ns against 0.31 ns for
-// the XYZZ mixed addition, so the rounds pay once the buckets are large and the per-round fixed costs (pair
-// count, scan, launch) are amortised; below 2^18 terms they do not.  The scratch (~300 bytes per pair) is capped.
-inline uint32_t msm_default_batch_rounds(const MsmPlan& p) {
-  if (!p.precomp || !p.acc_slots || p.n < (1u << 18)) return 0;
-  if ((uint64_t)p.max_entries / 2 * 300 > (40ull << 30)) return 0;
-  const uint32_t per_bucket = p.max_entries / p.nb;
-  if (p.n < (1u << 19)) return per_bucket >= 100 ? 2 : 0;
-  if (per_bucket < 40) return 0;
+// threads the batched-affine kernel keeps resident: 3 blocks of 128 per SM (ZK_MIN_BLOCKS in tu_g1_batch.cu), i.e.
+// 1.5 x acc_slots; tune.batch_blocks overrides the 3 for A/B builds of that translation unit
+inline uint64_t msm_batch_slots(const MsmPlan& p, const MsmTuning& tune) {
+  const uint64_t blocks = tune.batch_blocks >= 1 && tune.batch_blocks <= 8 ? (uint64_t)tune.batch_blocks : 3;
+  return (uint64_t)p.acc_slots * blocks / 2;
+}
+
+// Rounds of batched-affine pre-reduction for a set with precomputed slabs on a real device (measured on B200,
+// profiles/): an affine addition sharing its inversion costs ~0.29 ns against 0.35 ns for the XYZZ mixed addition
+// while a round keeps every resident thread busy with >= 8 additions per inversion; a smaller round is bound by
+// the latency of its one inversion per thread (~40 us) and AccumulateBuckets is the better tool.  Rounds stop at
+// ~12 items per bucket.  The scratch (~250 bytes per pair) is capped.
+inline uint32_t msm_default_batch_rounds(const MsmPlan& p, const MsmTuning& tune = MsmTuning()) {
+  if (!p.precomp || !p.acc_slots) return 0;
+  if ((uint64_t)p.max_entries / 2 * 250 > (40ull << 30)) return 0;
+  const uint64_t expected = msm_expected_entries(p), per_bucket = expected / p.nb;
+  const uint64_t min_adds = 8 * msm_batch_slots(p, tune);
   uint32_t r = 0;
-  while ((12u << (r + 1)) <= per_bucket) r++;           // floor(log2(per_bucket / 12)): ~12-24 entries left
-  return r < 2 ? 2 : (r > 4 ? 4 : r);
+  while (r < 8 && (expected >> (r + 1)) >= min_adds && (per_bucket >> (r + 1)) >= 12) r++;
+  return r < 2 ? 0 : r;
 }
 
 // items a batched-affine round can leave (every bucket rounds up), and the prefix-product scratch: a block of
 // 128 threads owns 128 * T consecutive slots, so the last block may reach past the item count
 inline size_t msm_pre_slots(const MsmPlan& p) { return (size_t)(p.max_entries + 1) / 2 + p.nb + 1; }
 inline size_t msm_prefix_slots(const MsmPlan& p) { return msm_pre_slots(p) + (size_t)129 * p.batch_T; }
-// additions per thread in a round with about `items` outputs: whole waves of the resident threads (3 blocks of
-// 128 per SM, ZK_MIN_BLOCKS in tu_g1_batch.cu, i.e. 1.5 x acc_slots), at most p.batch_T and at least a quarter of it
-inline uint32_t msm_batch_T(const MsmPlan& p, uint64_t items) {
+// additions per thread in a round with about `items` outputs: whole waves of the resident threads, at most
+// p.batch_T; below one wave the round's time is one thread's chain (T additions + one inversion), so T shrinks with
+// the round (down to 8: the inversion is worth ~6 additions)
+inline uint32_t msm_batch_T(const MsmPlan& p, uint64_t items, const MsmTuning& tune = MsmTuning()) {
   if (!p.acc_slots) return p.batch_T;
-  uint64_t half_blocks = 3;   // resident blocks per SM of the batched kernel (override for A/B builds of that TU)
-  if (const char* e = getenv("ZKMSM_BATCH_BLOCKS")) { int v = atoi(e); if (v >= 1 && v <= 8) half_blocks = (uint64_t)v; }
-  const uint64_t slots = (uint64_t)p.acc_slots * half_blocks / 2;
-  uint32_t lo = p.batch_T / 4 ? p.batch_T / 4 : 1;
+  const uint64_t slots = msm_batch_slots(p, tune);
+  const uint32_t lo = p.batch_T < 8 ? p.batch_T : 8;
   for (uint64_t waves = 1;; waves++) {
     uint64_t t = (items + waves * slots - 1) / (waves * slots);
     if (t <= p.batch_T) return t < lo ? lo : (uint32_t)t;
@@ -828,35 +994,39 @@ template <class C> struct MsmBuffers {
   Entry* pre_entries;      // ceil(max_entries / 2) + nb
   XYZZ<F>* reduced;        // msm_reduced_slots(): nwin rows of B / K, then the window tree's scratch
   uint32_t* err;           // 1
+  uint32_t* big;           // 1: raised by AccumulateBuckets when a bucket is over the cap (gates the chunked fallback)
 };
 
 // The launch sequence.  Exec::launch<Body>(nthreads, args...) runs Body::run(tid, args...) for
 // tid in [0, nthreads); Exec::zero(ptr, bytes) clears device memory (both stream-ordered).
 template <class C, class Exec>
-void msm_launch(Exec& ex, const MsmPlan& p, const MsmBuffers<C>& b, const Affine<typename C::F>* points,
+void msm_launch(Exec& ex, const MsmPlan& p, const MsmTuning& tune, const MsmBuffers<C>& b, const Affine<typename C::F>* points,
                 const uint32_t* d_scalars, XYZZ<typename C::F>* out_xyzz, uint32_t* out_affine, uint32_t* out_inf) {
+  typedef typename C::F F;
   ex.zero(b.hist_cursor, sizeof(uint32_t) * p.nb);
   ex.zero(b.err, sizeof(uint32_t));
+  ex.zero(b.big, sizeof(uint32_t));
   ex.template launch<RecodeCount>(p.n, p, d_scalars, b.hist_cursor, b.err);
   // offsets[0..nb] = exclusive scan of the histogram; the histogram array becomes the scatter cursors
   ex.exclusive_scan(p.nb, b.hist_cursor, b.offsets, b.segsum);
   ex.template launch<Scatter>(p.n, p, d_scalars, b.hist_cursor, b.entries);
   const uint32_t* acc_offsets = b.offsets;
   const Entry* acc_entries = b.entries;
-  const Affine<typename C::F>* acc_points = points;
+  const Affine<F>* acc_points = points;
+  uint64_t bound = p.max_entries;               // worst-case items (sizes the launches)
+  uint64_t expected = msm_expected_entries(p);  // items for uniformly random scalars (tunes them)
   if (p.batch_rounds > 0) {
-    typedef typename C::F F;
-    uint64_t items = p.max_entries;
     const uint32_t* off_in = b.offsets;
     const Affine<F>* src = points;
     for (uint32_t r = 0; r < p.batch_rounds; r++) {
       uint32_t* off_out = b.pre_off[r & 1];
       Affine<F>* dst = b.pre_pts[r & 1];
       bool last = r + 1 == p.batch_rounds;
-      items = (items + 1) / 2 + p.nb;                 // upper bound of this round's outputs
+      bound = (bound + 1) / 2 + p.nb;                 // upper bound of this round's outputs
+      expected = (expected + 1) / 2 + p.nb / 2;
       MsmPlan pr = p;
-      pr.batch_T = msm_batch_T(p, items);
-      const uint32_t threads = (uint32_t)((items + pr.batch_T - 1) / pr.batch_T);
+      pr.batch_T = msm_batch_T(p, expected, tune);
+      const uint32_t threads = (uint32_t)((bound + pr.batch_T - 1) / pr.batch_T);
       ex.template launch<PairCount>(p.nb, p.nb, off_in, b.pre_cnt);
       ex.exclusive_scan(p.nb, b.pre_cnt, off_out, b.segsum);
       if (r == 0)
@@ -877,27 +1047,34 @@ void msm_launch(Exec& ex, const MsmPlan& p, const MsmBuffers<C>& b, const Affine
     pa.precomp = 0;   // the pre-reduced items are addressed directly
     // far fewer items are left: shorter chunks keep about two waves of threads busy (never more threads than
     // the partial-sum buffers were sized for)
-    uint64_t left = p.max_entries;
-    for (uint32_t r = 0; r < p.batch_rounds; r++) left = (left + 1) / 2 + p.nb;
-    uint64_t l = p.acc_slots ? left / (2ull * p.acc_slots) : p.L;
-    uint64_t lmin = (left * p.L + p.max_entries - 1) / p.max_entries;
+    uint64_t l = p.acc_slots ? bound / (2ull * p.acc_slots) : p.L;
+    uint64_t lmin = (bound * p.L + p.max_entries - 1) / p.max_entries;
     if (l < 4) l = 4;
     if (l < lmin) l = lmin;
     if (l > p.L) l = p.L;
     pa.L = (uint32_t)l;
-    pa.acc_threads = (uint32_t)((left + pa.L - 1) / pa.L);
+    pa.acc_threads = (uint32_t)((bound + pa.L - 1) / pa.L);
     if (pa.acc_threads > p.acc_threads) { pa.L = p.L; pa.acc_threads = p.acc_threads; }
   }
+  // bucket sums: one launch with acc_G lanes per bucket; the chunked accumulation and its fix-up tree stay as the
+  // distribution-independent fallback, gated on the flag a bucket over the cap raises (launches that return at once
+  // otherwise), or as the only path when no lane count fits
+  msm_pick_bucket_acc(pa, expected, tune);
+  const uint32_t* gate = nullptr;
+  if (pa.acc_G) {
+    ex.template accumulate_buckets<C>(pa, acc_offsets, acc_entries, acc_points, p.batch_rounds > 0 ? 1u : 0u, b.bucket_sums, b.big);
+    gate = b.big;
+  }
   ex.template launch<Accumulate<C>>(pa.acc_threads, pa, acc_offsets, acc_entries, acc_points, b.bucket_sums, b.partials,
-                                    b.partial_keys);
+                                    b.partial_keys, gate);
   {  // fix-up tree over the per-chunk partial sums: level l reads region l, writes region l+1
     uint32_t count = pa.acc_threads, level = 0;
-    XYZZ<typename C::F>* pin = b.partials;
+    XYZZ<F>* pin = b.partials;
     uint32_t* kin = b.partial_keys;
     while (count > 1) {
       uint32_t fan = fix_fan(level++), next = (count + fan - 1) / fan;
-      ex.template launch<FixupLevel<C>>(next, count, fan, (const uint32_t*)kin, (const XYZZ<typename C::F>*)pin,
-                                        kin + count, pin + count, b.bucket_sums);
+      ex.template launch<FixupLevel<C>>(next, count, fan, (const uint32_t*)kin, (const XYZZ<F>*)pin, kin + count, pin + count,
+                                        b.bucket_sums, gate);
       pin += count;
       kin += count;
       count = next;
@@ -906,7 +1083,7 @@ void msm_launch(Exec& ex, const MsmPlan& p, const MsmBuffers<C>& b, const Affine
   uint32_t chunks = p.B / p.K;
   // stages 6 and 7 go through the Exec policy: the CUDA build has block-cooperative versions (coop.cuh), the CPU
   // emulation runs the per-thread bodies BucketReduce / PairSum; both give the same points
-  uint32_t m = ex.template bucket_reduce<C>(p, (const uint32_t*)b.offsets, (const XYZZ<typename C::F>*)b.bucket_sums, b.reduced);
+  uint32_t m = ex.template bucket_reduce<C>(p, acc_offsets, (const XYZZ<F>*)b.bucket_sums, b.reduced);
   auto rows = ex.template window_tree<C>(p.nwin, chunks, m, b.reduced, b.reduced + (size_t)p.nwin * chunks);
   ex.template finish<C>(p.nwin, rows.pitch, p.c, rows.arr, out_xyzz, out_affine, out_inf);
 }

@@ -69,6 +69,13 @@ __global__ void __launch_bounds__(kNttThreads) fr_ntt_fused_kernel(Fr* a, uint32
   }
 }
 
+// per-device opt-in (zkmsm_create), see launch.cuh
+cudaError_t zk_opt_in_shared_memory_ntt() {
+  cudaError_t e = cudaFuncSetAttribute(fr_ntt_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(fr_ntt_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
+  return e;
+}
+
 // returns cudaErrorNotSupported when the shape does not fit (caller falls back to the per-stage bodies)
 cudaError_t zk_ntt_fused(cudaStream_t st, bool inverse, Fr* a, uint32_t total, uint32_t L0, uint32_t k, const Fr* tw,
                          uint32_t m) {
@@ -76,13 +83,6 @@ cudaError_t zk_ntt_fused(cudaStream_t st, bool inverse, Fr* a, uint32_t total, u
   if (k < 2 || k > 8 || (L0 >> k) << k != L0 || groups % G != 0 || !(sub == 1 || sub % G == 0) || total % L0 != 0)
     return cudaErrorNotSupported;
   const size_t smem = (size_t)(G << k) * sizeof(Fr);
-  static bool opted = false;   // one device per process
-  if (!opted) {
-    cudaError_t e = cudaFuncSetAttribute(fr_ntt_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(fr_ntt_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
-    if (e != cudaSuccess) return e;
-    opted = true;
-  }
   if (inverse) fr_ntt_fused_kernel<true><<<groups / G, kNttThreads, smem, st>>>(a, L0, k, G, m / L0, tw);
   else fr_ntt_fused_kernel<false><<<groups / G, kNttThreads, smem, st>>>(a, L0, k, G, m / L0, tw);
   return cudaGetLastError();

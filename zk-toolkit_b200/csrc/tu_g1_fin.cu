@@ -6,3 +6,4 @@
 #include "msm.cuh"
 ZK_INSTANTIATE_KERNEL(zk::Finish<zk::G1>);
 ZK_INSTANTIATE_KERNEL(zk::CombinePartials<zk::G1>);
+ZK_INSTANTIATE_KERNEL(zk::PoisonPartial<zk::G1>);

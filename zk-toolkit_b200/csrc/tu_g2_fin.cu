@@ -5,3 +5,4 @@
 #include "msm.cuh"
 ZK_INSTANTIATE_KERNEL(zk::Finish<zk::G2>);
 ZK_INSTANTIATE_KERNEL(zk::CombinePartials<zk::G2>);
+ZK_INSTANTIATE_KERNEL(zk::PoisonPartial<zk::G2>);

@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
 #include <new>
 
 #include "../../include/zkmsm.h"
@@ -27,7 +28,24 @@ struct alignas(16) ResultBlock {      // device + pinned host mirror
   uint32_t affine[48];
   uint32_t inf;
   uint32_t err;
+  uint32_t big;           // AccumulateBuckets' "a bucket is over the cap" flag (device side only)
 };
+
+// one captured MSM launch sequence (CUDA graph): replayed while the same point set, sizes, buffers and options recur
+struct GraphKey {
+  uint64_t ps_uid, ws_epoch, tune_epoch;
+  size_t n;
+  const void* scalars;
+  const void* out;
+  int mode;             // curve | want_affine << 4
+  uint32_t rank, world;
+  bool operator==(const GraphKey& o) const {
+    return ps_uid == o.ps_uid && ws_epoch == o.ws_epoch && tune_epoch == o.tune_epoch && n == o.n && scalars == o.scalars &&
+           out == o.out && mode == o.mode && rank == o.rank && world == o.world;
+  }
+};
+struct GraphSlot { GraphKey key; cudaGraphExec_t exec; int launches; uint64_t used; };
+static constexpr int kGraphSlots = 8;
 
 struct zkmsm_ctx {
   int device;
@@ -35,6 +53,9 @@ struct zkmsm_ctx {
   cudaStream_t own_stream, stream;
   char err[512];
   unsigned window_override;
+  MsmTuning tune;       // environment switches, read once in zkmsm_create; zkmsm_set_option overrides
+  uint64_t tune_epoch, ws_epoch, graph_clock;
+  GraphSlot graphs[kGraphSlots];
   void* ws[WS_COUNT];
   size_t ws_bytes[WS_COUNT];
   ResultBlock* d_res;
@@ -47,7 +68,10 @@ struct zkmsm_ctx {
   size_t ntt_n;
 };
 
+static std::atomic<uint64_t> g_next_ps_uid{1};
+
 struct zkmsm_points {
+  uint64_t uid;         // never reused (keys the cached launch graphs)
   int curve;            // 1 = G1, 2 = G2
   int device;
   size_t n;             // points per slab
@@ -72,9 +96,19 @@ static int fail(zkmsm_ctx* ctx, int code, const char* fmt, ...) {
     if (e__ != cudaSuccess) return fail(ctx, ZKMSM_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e__)); \
   } while (0)
 
+static void graphs_drop(zkmsm_ctx* ctx, uint64_t ps_uid /* 0 = all */) {
+  for (int i = 0; i < kGraphSlots; i++)
+    if (ctx->graphs[i].exec && (ps_uid == 0 || ctx->graphs[i].key.ps_uid == ps_uid)) {
+      cudaGraphExecDestroy(ctx->graphs[i].exec);
+      ctx->graphs[i].exec = nullptr;
+    }
+}
+
 static int ws_reserve(zkmsm_ctx* ctx, int slot, size_t bytes) {
   if (bytes == 0) bytes = 16;
   if (ctx->ws_bytes[slot] >= bytes) return ZKMSM_OK;
+  ctx->ws_epoch++;          // captured graphs hold the old pointers
+  graphs_drop(ctx, 0);
   if (ctx->ws[slot]) {
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     CU(ctx, cudaFree(ctx->ws[slot]));
@@ -117,6 +151,14 @@ extern "C" int zkmsm_create(int device, zkmsm_ctx** out) {
     return ZKMSM_ERR_CUDA;
   }
   ctx->stream = ctx->own_stream;
+  ctx->tune = MsmTuning::from_env();
+  // > 48 KB of dynamic shared memory is a per-device opt-in: done here for this context's device
+  if (zk_opt_in_shared_memory_coop_g1() != cudaSuccess || zk_opt_in_shared_memory_coop_g2() != cudaSuccess ||
+      zk_opt_in_shared_memory_ntt() != cudaSuccess) {
+    cudaGetLastError();
+    zkmsm_destroy(ctx);
+    return ZKMSM_ERR_CUDA;
+  }
   *out = ctx;
   return ZKMSM_OK;
 }
@@ -125,6 +167,7 @@ extern "C" int zkmsm_destroy(zkmsm_ctx* ctx) {
   if (!ctx) return ZKMSM_ERR_INVALID_ARG;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  graphs_drop(ctx, 0);
   for (int i = 0; i < WS_COUNT; i++)
     if (ctx->ws[i]) cudaFree(ctx->ws[i]);
   if (ctx->ntt_tables) cudaFree(ctx->ntt_tables);
@@ -150,6 +193,23 @@ extern "C" int zkmsm_set_window(zkmsm_ctx* ctx, unsigned c) {
   if (!ctx || (c != 0 && (c < 3 || c > 22))) return ZKMSM_ERR_INVALID_ARG;
   ctx->window_override = c;
   return ZKMSM_OK;
+}
+
+extern "C" int zkmsm_set_option(zkmsm_ctx* ctx, const char* name, long value) {
+  if (!ctx || !name) return ZKMSM_ERR_INVALID_ARG;
+  struct { const char* name; int MsmTuning::*field; } table[] = {
+      {"batch_rounds", &MsmTuning::batch_rounds}, {"batch_T", &MsmTuning::batch_T}, {"batch_g2", &MsmTuning::batch_g2},
+      {"batch_blocks", &MsmTuning::batch_blocks}, {"L", &MsmTuning::L}, {"K", &MsmTuning::K},
+      {"no_wave_L", &MsmTuning::no_wave_L}, {"no_coop", &MsmTuning::no_coop}, {"ntt_no_fuse", &MsmTuning::ntt_no_fuse},
+      {"quotient_schoolbook", &MsmTuning::quotient_schoolbook}, {"no_graph", &MsmTuning::no_graph},
+      {"no_bucket_acc", &MsmTuning::no_bucket_acc}};
+  for (auto& t : table)
+    if (strcmp(t.name, name) == 0) {
+      ctx->tune.*(t.field) = (int)value;
+      ctx->tune_epoch++;
+      return ZKMSM_OK;
+    }
+  return fail(ctx, ZKMSM_ERR_INVALID_ARG, "unknown option '%s'", name);
 }
 
 extern "C" int zkmsm_host_alloc(size_t bytes, void** out) {
@@ -213,6 +273,7 @@ static int alloc_point_set(zkmsm_ctx* ctx, size_t n, unsigned flags, int curve, 
   CU(ctx, cudaSetDevice(ctx->device));
   zkmsm_points* ps = new (std::nothrow) zkmsm_points();
   if (!ps) return fail(ctx, ZKMSM_ERR_NOMEM, "host allocation");
+  ps->uid = g_next_ps_uid++;
   ps->curve = curve;
   ps->device = ctx->device;
   ps->n = n;
@@ -265,7 +326,7 @@ extern "C" int zkmsm_g2_load_points(zkmsm_ctx* ctx, const uint32_t* xy, const ui
 extern "C" int zkmsm_points_free(zkmsm_ctx* ctx, zkmsm_points* ps) {
   if (!ps) return ZKMSM_ERR_INVALID_ARG;
   cudaSetDevice(ps->device);
-  if (ctx) cudaStreamSynchronize(ctx->stream);
+  if (ctx) { cudaStreamSynchronize(ctx->stream); graphs_drop(ctx, ps->uid); }
   if (ps->d_pts) cudaFree(ps->d_pts);
   delete ps;
   return ZKMSM_OK;
@@ -309,26 +370,36 @@ extern "C" int zkmsm_points_read(zkmsm_ctx* ctx, const zkmsm_points* ps, size_t 
 
 // ------------------------------------------------------------------------------------------------
 // MSM
+// rank/world: bucket-range split of a precomputed set (world = 1: the whole MSM)
 template <class C>
 static int msm_enqueue_impl(zkmsm_ctx* ctx, const zkmsm_points* ps, const uint32_t* d_scalars, size_t n, int curve,
-                            bool want_affine, uint32_t* d_partial_out) {
+                            bool want_affine, uint32_t* d_partial_out, uint32_t rank = 0, uint32_t world = 1) {
   typedef typename C::F F;
   if (!ctx || !ps) return fail(ctx, ZKMSM_ERR_INVALID_ARG, "null argument");
   if (ps->curve != curve) return fail(ctx, ZKMSM_ERR_INVALID_ARG, "point set is for the other group");
   if (ps->device != ctx->device) return fail(ctx, ZKMSM_ERR_INVALID_ARG, "point set lives on another device");
   if (n > ps->n) return fail(ctx, ZKMSM_ERR_TOO_FEW_POINTS, "%zu scalars but only %zu points", n, ps->n);
   if (n > 0 && !d_scalars) return fail(ctx, ZKMSM_ERR_INVALID_ARG, "null scalars");
+  if (world == 0 || rank >= world || (world & (world - 1)) != 0)
+    return fail(ctx, ZKMSM_ERR_INVALID_ARG, "bucket-range split: world must be a power of two and rank < world");
+  if (world > 1 && !ps->precomp) return fail(ctx, ZKMSM_ERR_INVALID_ARG, "bucket-range split needs a ZKMSM_PRECOMPUTE point set");
   CU(ctx, cudaSetDevice(ctx->device));
   ctx->pending_words = C::AFF_LIMBS;
   ctx->last_launches = 0;
+  XYZZ<F>* d_xyzz = d_partial_out ? (XYZZ<F>*)d_partial_out : (XYZZ<F>*)ctx->d_res->xyzz;
   if (n == 0) {  // empty sum = AtInfinity (polynomial.rs:276)
     ctx->pending = 2;
     if (d_partial_out) CU(ctx, cudaMemsetAsync(d_partial_out, 0, sizeof(XYZZ<F>), ctx->stream));
     return ZKMSM_OK;
   }
+  const MsmTuning& tune = ctx->tune;
   unsigned c = ps->precomp ? ps->c : (ctx->window_override ? ctx->window_override : msm_pick_c((uint32_t)n, false, ps->half));
-  MsmPlan p = msm_plan((uint32_t)n, c, ps->precomp, (uint32_t)ps->n, ps->half, !getenv("ZKMSM_NO_COOP"),
-                          (uint32_t)ctx->sms * 256u);
+  if (!msm_fits(n, c, ps->half))
+    return fail(ctx, ZKMSM_ERR_INVALID_ARG, "%zu terms at window %u exceed 2^32 sorted pairs; use a wider window", n, c);
+  if (world > 1 && world > (1u << (c - 1))) return fail(ctx, ZKMSM_ERR_INVALID_ARG, "bucket-range split: more ranks than buckets");
+  MsmPlan p = msm_plan((uint32_t)n, c, ps->precomp, (uint32_t)ps->n, ps->half, true, (uint32_t)ctx->sms * 256u, tune, rank, world);
+  if (curve != 1 && !tune.batch_g2) p.batch_rounds = 0;   // G2: off unless forced (the Fq2 kernel spills)
+  else if (tune.batch_rounds < 0) p.batch_rounds = msm_default_batch_rounds(p, tune);
   int rc;
   uint32_t nseg = (p.nb + SCAN_SEG - 1) / SCAN_SEG + 1;
   if ((rc = ws_reserve(ctx, WS_HIST, sizeof(uint32_t) * p.nb)) || (rc = ws_reserve(ctx, WS_OFFSETS, sizeof(uint32_t) * (p.nb + 1))) ||
@@ -340,16 +411,14 @@ static int msm_enqueue_impl(zkmsm_ctx* ctx, const zkmsm_points* ps, const uint32
     return rc;
   MsmBuffers<C> b;
   memset(&b, 0, sizeof(b));
-  if (curve != 1) { if (!getenv("ZKMSM_BATCH_G2")) p.batch_rounds = 0; }   // G2: off unless forced (the Fq2 kernel spills)
-  else if (!getenv("ZKMSM_BATCH_ROUNDS")) p.batch_rounds = msm_default_batch_rounds(p);
   if (p.batch_rounds > 0) {
     size_t pre_n = msm_pre_slots(p);
     if ((rc = ws_reserve(ctx, WS_PRE_A, sizeof(Affine<F>) * pre_n)) || (rc = ws_reserve(ctx, WS_PRE_B, sizeof(Affine<F>) * pre_n)) ||
         (rc = ws_reserve(ctx, WS_PRE_PREFIX, sizeof(F) * 2 * msm_prefix_slots(p))) || (rc = ws_reserve(ctx, WS_PRE_OFF, sizeof(uint32_t) * 3 * ((size_t)p.nb + 4))) ||
         (rc = ws_reserve(ctx, WS_PRE_ENTRIES, sizeof(Entry) * pre_n))) {
       // the rounds are an optimisation: without room for their scratch the MSM runs on the XYZZ accumulation alone
-      // (a forced ZKMSM_BATCH_ROUNDS still reports the failure)
-      if (rc != ZKMSM_ERR_NOMEM || getenv("ZKMSM_BATCH_ROUNDS")) return rc;
+      // (forced rounds still report the failure)
+      if (rc != ZKMSM_ERR_NOMEM || tune.batch_rounds >= 0) return rc;
       for (int slot : {WS_PRE_A, WS_PRE_B, WS_PRE_PREFIX, WS_PRE_ENTRIES})
         if (ctx->ws[slot]) { cudaFree(ctx->ws[slot]); ctx->ws[slot] = nullptr; ctx->ws_bytes[slot] = 0; }
       strcpy(ctx->err, "ok");
@@ -374,11 +443,56 @@ static int msm_enqueue_impl(zkmsm_ctx* ctx, const zkmsm_points* ps, const uint32
   b.partial_keys = (uint32_t*)ctx->ws[WS_PKEYS];
   b.reduced = (XYZZ<F>*)ctx->ws[WS_REDUCED];
   b.err = &ctx->d_res->err;
+  b.big = &ctx->d_res->big;
+  auto enqueue = [&](CudaExec& ex) {
+    msm_launch<C>(ex, p, tune, b, (const Affine<F>*)ps->d_pts, d_scalars, want_affine ? (XYZZ<F>*)nullptr : d_xyzz,
+                  want_affine ? ctx->d_res->affine : (uint32_t*)nullptr, want_affine ? &ctx->d_res->inf : (uint32_t*)nullptr);
+    // a partial that leaves the context without a status read carries its error flag inside the blob
+    if (d_partial_out) ex.template launch<PoisonPartial<C>>(1u, (const uint32_t*)b.err, d_xyzz);
+  };
+  // Replay a captured CUDA graph of the sequence when nothing it depends on changed (the ~30-40 launches then cost
+  // one submission and run back to back); per-launch profiling and ZKMSM_NO_GRAPH launch kernel by kernel.
+  if (!ctx->prof && !tune.no_graph) {
+    GraphKey key{ps->uid, ctx->ws_epoch, ctx->tune_epoch, n, d_scalars, d_partial_out, curve | (want_affine ? 16 : 0), rank, world};
+    GraphSlot* slot = nullptr;
+    GraphSlot* victim = &ctx->graphs[0];
+    for (int i = 0; i < kGraphSlots; i++) {
+      GraphSlot& g = ctx->graphs[i];
+      if (g.exec && g.key == key) { slot = &g; break; }
+      if (!g.exec || (victim->exec && g.used < victim->used)) victim = &g;
+    }
+    if (!slot && cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+      CudaExec ex(ctx->stream, nullptr, tune.no_coop != 0, tune.ntt_no_fuse != 0);
+      enqueue(ex);
+      cudaGraph_t graph = nullptr;
+      cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
+      if (ex.err != cudaSuccess || e != cudaSuccess) {
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        return fail(ctx, ZKMSM_ERR_CUDA, "msm capture: %s", cudaGetErrorString(ex.err != cudaSuccess ? ex.err : e));
+      }
+      if (victim->exec) cudaGraphExecDestroy(victim->exec);
+      victim->exec = nullptr;
+      e = cudaGraphInstantiate(&victim->exec, graph, 0);
+      cudaGraphDestroy(graph);
+      if (e != cudaSuccess) { victim->exec = nullptr; return fail(ctx, ZKMSM_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e)); }
+      victim->key = key;
+      victim->launches = ex.launches;
+      slot = victim;
+    } else if (!slot) {
+      cudaGetLastError();   // the stream cannot be captured (e.g. the legacy default stream): plain launches below
+    }
+    if (slot) {
+      slot->used = ++ctx->graph_clock;
+      CU(ctx, cudaGraphLaunch(slot->exec, ctx->stream));
+      ctx->last_launches = slot->launches;
+      ctx->pending = 1;
+      return ZKMSM_OK;
+    }
+  }
   if (ctx->prof) ctx->prof->n = 0;
-  CudaExec ex(ctx->stream, ctx->prof);
-  XYZZ<F>* d_xyzz = d_partial_out ? (XYZZ<F>*)d_partial_out : (XYZZ<F>*)ctx->d_res->xyzz;
-  msm_launch<C>(ex, p, b, (const Affine<F>*)ps->d_pts, d_scalars, want_affine ? (XYZZ<F>*)nullptr : d_xyzz,
-                want_affine ? ctx->d_res->affine : (uint32_t*)nullptr, want_affine ? &ctx->d_res->inf : (uint32_t*)nullptr);
+  CudaExec ex(ctx->stream, ctx->prof, tune.no_coop != 0, tune.ntt_no_fuse != 0);
+  enqueue(ex);
   ctx->last_launches = ex.launches;
   if (ex.err != cudaSuccess) return fail(ctx, ZKMSM_ERR_CUDA, "msm launch: %s", cudaGetErrorString(ex.err));
   ctx->pending = 1;
@@ -500,18 +614,30 @@ extern "C" int zkmsm_g2_msm_oneshot(zkmsm_ctx* ctx, const uint32_t* xy, const ui
 
 // ---- partials / combine
 template <class C>
-static int partial_impl(zkmsm_ctx* ctx, const zkmsm_points* ps, const uint32_t* scalars, size_t n, int curve, uint32_t* out) {
+static int partial_impl(zkmsm_ctx* ctx, const zkmsm_points* ps, const uint32_t* scalars, size_t n, int curve, uint32_t* out,
+                        uint32_t rank = 0, uint32_t world = 1) {
   typedef typename C::F F;
   if (!ctx || !ps || !out) return fail(ctx, ZKMSM_ERR_INVALID_ARG, "null argument");
   if (n > ps->n) return fail(ctx, ZKMSM_ERR_TOO_FEW_POINTS, "%zu scalars but only %zu points", n, ps->n);
   const uint32_t* d_s;
   int rc = upload_scalars(ctx, scalars, n, &d_s);
   if (rc) return rc;
-  rc = msm_enqueue_impl<C>(ctx, ps, d_s, n, curve, false, nullptr);
+  rc = msm_enqueue_impl<C>(ctx, ps, d_s, n, curve, false, nullptr, rank, world);
   if (rc) return rc;
   rc = msm_collect(ctx);
   if (rc) return rc;
   memcpy(out, ctx->h_res->xyzz, sizeof(XYZZ<F>));  // n == 0: zeros = infinity
+  return ZKMSM_OK;
+}
+// stream-ordered: the partial stays in the caller's device buffer; an out-of-range scalar poisons the blob and the
+// combine step reports ZKMSM_ERR_SCALAR_RANGE (PoisonPartial, msm.cuh)
+template <class C>
+static int partial_device_impl(zkmsm_ctx* ctx, const zkmsm_points* ps, const uint32_t* ds, size_t n, int curve, uint32_t* d_out,
+                               uint32_t rank = 0, uint32_t world = 1) {
+  if (!d_out) return fail(ctx, ZKMSM_ERR_INVALID_ARG, "null argument");
+  int rc = msm_enqueue_impl<C>(ctx, ps, ds, n, curve, false, d_out, rank, world);
+  if (rc) return rc;
+  ctx->pending = 0;  // result lives in the caller's buffer, stream-ordered
   return ZKMSM_OK;
 }
 extern "C" int zkmsm_g1_msm_partial(zkmsm_ctx* ctx, const zkmsm_points* ps, const uint32_t* s, size_t n, uint32_t* out) {
@@ -521,11 +647,26 @@ extern "C" int zkmsm_g2_msm_partial(zkmsm_ctx* ctx, const zkmsm_points* ps, cons
   return partial_impl<G2>(ctx, ps, s, n, 2, out);
 }
 extern "C" int zkmsm_g1_msm_partial_device(zkmsm_ctx* ctx, const zkmsm_points* ps, const uint32_t* ds, size_t n, uint32_t* d_out) {
-  if (!d_out) return fail(ctx, ZKMSM_ERR_INVALID_ARG, "null argument");
-  int rc = msm_enqueue_impl<G1>(ctx, ps, ds, n, 1, false, d_out);
-  if (rc) return rc;
-  ctx->pending = 0;  // result lives in the caller's buffer, stream-ordered
-  return ZKMSM_OK;
+  return partial_device_impl<G1>(ctx, ps, ds, n, 1, d_out);
+}
+extern "C" int zkmsm_g2_msm_partial_device(zkmsm_ctx* ctx, const zkmsm_points* ps, const uint32_t* ds, size_t n, uint32_t* d_out) {
+  return partial_device_impl<G2>(ctx, ps, ds, n, 2, d_out);
+}
+extern "C" int zkmsm_g1_msm_partial_range(zkmsm_ctx* ctx, const zkmsm_points* ps, const uint32_t* s, size_t n, unsigned rank,
+                                          unsigned world, uint32_t* out) {
+  return partial_impl<G1>(ctx, ps, s, n, 1, out, rank, world);
+}
+extern "C" int zkmsm_g2_msm_partial_range(zkmsm_ctx* ctx, const zkmsm_points* ps, const uint32_t* s, size_t n, unsigned rank,
+                                          unsigned world, uint32_t* out) {
+  return partial_impl<G2>(ctx, ps, s, n, 2, out, rank, world);
+}
+extern "C" int zkmsm_g1_msm_partial_range_device(zkmsm_ctx* ctx, const zkmsm_points* ps, const uint32_t* ds, size_t n,
+                                                 unsigned rank, unsigned world, uint32_t* d_out) {
+  return partial_device_impl<G1>(ctx, ps, ds, n, 1, d_out, rank, world);
+}
+extern "C" int zkmsm_g2_msm_partial_range_device(zkmsm_ctx* ctx, const zkmsm_points* ps, const uint32_t* ds, size_t n,
+                                                 unsigned rank, unsigned world, uint32_t* d_out) {
+  return partial_device_impl<G2>(ctx, ps, ds, n, 2, d_out, rank, world);
 }
 
 template <class C>
@@ -541,11 +682,11 @@ static int combine_impl(zkmsm_ctx* ctx, const uint32_t* parts, bool on_device, s
     d_parts = (const XYZZ<F>*)ctx->ws[WS_MISC];
   }
   CU(ctx, cudaMemsetAsync(&ctx->d_res->err, 0, sizeof(uint32_t), ctx->stream));
-  CudaExec ex(ctx->stream);
-  if (std::is_same<C, G1>::value && k > 2 && k <= 32 && !getenv("ZKMSM_NO_COOP"))
-    ex.timed("combine_partials", (uint32_t)k, 1, [&] { return zk_coop_combine_g1(ctx->stream, (uint32_t)k, (const XYZZ<Fp>*)d_parts, ctx->d_res->affine, &ctx->d_res->inf); });
+  CudaExec ex(ctx->stream, nullptr, ctx->tune.no_coop != 0);
+  if (std::is_same<C, G1>::value && k > 2 && k <= 32 && !ctx->tune.no_coop)
+    ex.timed("combine_partials", (uint32_t)k, 1, [&] { return zk_coop_combine_g1(ctx->stream, (uint32_t)k, (const XYZZ<Fp>*)d_parts, ctx->d_res->affine, &ctx->d_res->inf, &ctx->d_res->err); });
   else
-    ex.template launch<CombinePartials<C>>(1u, (uint32_t)k, d_parts, ctx->d_res->affine, &ctx->d_res->inf);
+    ex.template launch<CombinePartials<C>>(1u, (uint32_t)k, d_parts, ctx->d_res->affine, &ctx->d_res->inf, &ctx->d_res->err);
   if (ex.err != cudaSuccess) return fail(ctx, ZKMSM_ERR_CUDA, "combine: %s", cudaGetErrorString(ex.err));
   ctx->pending = 1;
   ctx->pending_words = C::AFF_LIMBS;
@@ -559,6 +700,9 @@ extern "C" int zkmsm_g2_combine(zkmsm_ctx* ctx, const uint32_t* parts, size_t k,
 }
 extern "C" int zkmsm_g1_combine_device(zkmsm_ctx* ctx, const uint32_t* parts, size_t k, uint32_t* out, int* inf) {
   return combine_impl<G1>(ctx, parts, true, k, out, inf);
+}
+extern "C" int zkmsm_g2_combine_device(zkmsm_ctx* ctx, const uint32_t* parts, size_t k, uint32_t* out, int* inf) {
+  return combine_impl<G2>(ctx, parts, true, k, out, inf);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -687,7 +831,7 @@ static int fr_quotient_ntt(zkmsm_ctx* ctx, const uint32_t* u, const uint32_t* v,
   uint32_t* d_flag = d_raw + 32 * n;
   Fr* scratch = (Fr*)(base + off_fr);
   if (ctx->prof) ctx->prof->n = 0;
-  CudaExec ex(ctx->stream, ctx->prof);
+  CudaExec ex(ctx->stream, ctx->prof, ctx->tune.no_coop != 0, ctx->tune.ntt_no_fuse != 0);
   FrNttTables tb;
   if (ctx->ntt_n != n) {
     if (ctx->ntt_tables) { CU(ctx, cudaStreamSynchronize(ctx->stream)); cudaFree(ctx->ntt_tables); ctx->ntt_tables = nullptr; }
@@ -727,7 +871,7 @@ extern "C" int zkmsm_fr_quotient(zkmsm_ctx* ctx, const uint32_t* u, const uint32
   CU(ctx, cudaSetDevice(ctx->device));
   // transforms from 32 coefficients on; below that (and on request, as the cross-check) the reference's schoolbook
   // multiplication and long division, one launch per step
-  const bool schoolbook = getenv("ZKMSM_QUOTIENT_SCHOOLBOOK") != nullptr;
+  const bool schoolbook = ctx->tune.quotient_schoolbook != 0;
   if (n >= 32 && !schoolbook) return fr_quotient_ntt(ctx, u, v, w, n, h_out, out_exact);
   if (n > (1u << 14)) return fail(ctx, ZKMSM_ERR_INVALID_ARG, "schoolbook quotient: n <= 2^14");
   const size_t in_bytes = sizeof(uint32_t) * 8 * n;
