@@ -111,6 +111,26 @@ def host_cores():
         return os.cpu_count() or 1
 
 
+# ------------------------------------------------------------------------------------------------ oracle checks
+def oracle_g1_multiple(k):
+    """(k mod r) * g by the ORACLE's restatement of the reference's double-and-add (macros.rs:2-32): the checker of
+    every result this script reports (one ~255-step affine scalar multiplication in Python, ~20 ms)"""
+    from oracle import zkt_oracle as O
+    p = O.scalar_mul(O.G1_GEN, k % R)
+    return None if p is O.INF else O.g1_to_limbs(p)
+
+
+def oracle_g2_multiple(k):
+    from oracle import zkt_oracle as O
+    p = O.scalar_mul(O.G2_GEN, k % R)
+    return None if p is O.INF else O.g2_to_limbs(p)
+
+
+def same_point(res, want):
+    xy, inf = res
+    return inf if want is None else ((not inf) and list(xy.tolist()) == list(want))
+
+
 # ------------------------------------------------------------------------------------------------ main
 def main():
     # stdout carries exactly ONE JSON line: anything a library prints there (e.g. NCCL's version banner)
@@ -126,8 +146,13 @@ def main():
     ap.add_argument("--logn", type=int, default=20)
     ap.add_argument("--seed", type=int, default=0x5EED0002)
     ap.add_argument("--no-precompute", action="store_true", help="plain point sets (per-window buckets + Horner)")
+    ap.add_argument("--split", default="range", choices=["range", "points"],
+                    help="N > 1: 'range' = every GPU holds the CRS tables and all scalars, owns 1/N of the bucket range; "
+                         "'points' = contiguous shards of the (point, scalar) vectors")
     ap.add_argument("--cpu-sample-per-core", type=int, default=64)
     ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--g2-logn", type=int, default=18, help="size of the G2 MSM block (0 = skip)")
+    ap.add_argument("--groth16-logn", type=int, default=18, help="constraints of the Groth16 block (0 = skip)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -154,8 +179,9 @@ def main():
     stream = torch.cuda.Stream()
     torch.cuda.synchronize()
     ctx.set_stream(stream.cuda_stream)
+    split = args.split if (world > 1 and not args.no_precompute and world & (world - 1) == 0) else "points"
 
-    lo, hi = sharding.shard_range(n_total, rank, world)
+    lo, hi = (0, n_total) if split == "range" and world > 1 else sharding.shard_range(n_total, rank, world)
     n = hi - lo
     t_setup = time.time()
     dlog_arr, dlogs = synth_scalars(n_total, args.seed + 1, lo, hi)
@@ -168,104 +194,147 @@ def main():
     sc_arr, scalars = synth_scalars(n_total, args.seed + 2, lo, hi)
     pts = ctx.points_from_scalars(1, z.G1Point.g().limbs(), dlog_arr, precompute=not args.no_precompute,
                                   in_subgroup=True)   # multiples of g have order r; scalars are < r
-    expected_k = sum(k * s for k, s in zip(dlogs, scalars)) % R     # this rank's share of sum s_i k_i
-    log(f"[rank {rank}] shard [{lo},{hi}) set up in {time.time() - t_setup:.1f}s")
+    expected_k = sum(k * s for k, s in zip(dlogs, scalars)) % R     # this rank's terms of sum s_i k_i
+    if split == "range" and world > 1:
+        expected_k = expected_k if rank == 0 else 0                 # every rank holds all terms: count them once
+    log(f"[rank {rank}] terms [{lo},{hi}) ({split} split) set up in {time.time() - t_setup:.1f}s")
 
     with torch.cuda.stream(stream):
         h_sc = torch.from_numpy(sc_arr.view(np.int32)).pin_memory()
         d_sc = h_sc.to("cuda", non_blocking=True)
-        flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
         d_partial = torch.zeros(48, dtype=torch.int32, device="cuda")
         stream.synchronize()
 
-        def device_step():
-            """one MSM with inputs resident in HBM; returns (xy, inf) on rank 0 / every rank"""
+        def enqueue_step():
+            """one MSM with inputs resident in HBM, stream-ordered (no host synchronisation); the canonical affine
+            result lands in the context's device result block and is fetched by fetch()"""
             if world == 1:
                 ctx.msm_enqueue(pts, d_sc.data_ptr(), n)
-                return None
-            ctx.msm_partial_device(pts, d_sc.data_ptr(), n, d_partial.data_ptr())
-            gathered = sharding.gather_partials(d_partial)
-            return gathered
+                return
+            if split == "range":
+                ctx.msm_partial_range_device(pts, d_sc.data_ptr(), n, rank, world, d_partial.data_ptr())
+            else:
+                ctx.msm_partial_device(pts, d_sc.data_ptr(), n, d_partial.data_ptr())
+            g = sharding.gather_partials(d_partial)
+            ctx.combine_enqueue(g.data_ptr(), world)
+            return g
 
-        def finish_step(g):
-            if world == 1:
-                return ctx.msm_result(1)
-            return ctx.combine_device(g.data_ptr(), world)
+        def fetch():
+            return ctx.msm_result(1)
 
         def e2e_step():
             """through the public call with HOST scalars: H2D copy + MSM + D2H of the result"""
             if world == 1:
                 return ctx.msm_host_ptr(pts, h_sc.data_ptr(), n)
             d_sc.copy_(h_sc, non_blocking=True)
-            return finish_step(device_step())
+            enqueue_step()
+            return fetch()
 
         # ---- warm-up (the clock sampler starts here so that nvidia-smi's start-up cost is not in the timed region)
         sampler = ClockSampler(local_rank) if rank == 0 else None
         for _ in range(W):
-            res = finish_step(device_step())
-        # ---- check the result once: sum_i s_i (k_i g) == (sum_i s_i k_i mod r) g, via the fixed-base kernel
+            enqueue_step()
+            res = fetch()
+        # ---- check the result: sum_i s_i (k_i g) == (sum_i s_i k_i mod r) g, the right-hand side by the ORACLE
         tot_k = expected_k
         if world > 1:
             ks = [None] * world
             dist.all_gather_object(ks, expected_k)
             tot_k = sum(ks) % R
-        exp_xy, exp_inf = ctx.mul_base(1, z.G1Point.g().limbs(), z.scalars_to_array([tot_k]))
-        ok = (bool(exp_inf[0]) == res[1]) and (res[1] or exp_xy[0].tolist() == res[0].tolist())
-        if not ok:
-            raise SystemExit(f"[rank {rank}] MSM result does not match (sum s_i k_i) * g")
+        want_xy = oracle_g1_multiple(tot_k)
+        if not same_point(res, want_xy):
+            raise SystemExit(f"[rank {rank}] MSM result does not match the oracle's (sum s_i k_i) * g")
+        # (the generated points themselves: a sample against the oracle's scalar multiplication)
+        if rank == 0:
+            for i in (0, n // 2, n - 1):
+                xy, inf = pts.read(i, 1)
+                if not same_point((xy[0], bool(inf[0])), oracle_g1_multiple(dlogs[i])):
+                    raise SystemExit("generated point differs from the oracle's k_i * g")
 
-        # ---- timed region: K steps, CUDA events on the launching stream, L2 flushed between steps
-        ctx.profile(True)
-        for _ in range(2):          # untimed: first use of the per-launch events
-            res = finish_step(device_step())
+        # ---- timed region: EXACTLY K steps back to back on the launching stream, one CUDA-event bracket, a barrier and
+        # a device synchronisation on both sides, max over ranks.  No L2 flush: every step gathers from the resident
+        # CRS tables (1.4 GB at 2^20, 11x the 126 MB L2) and rewrites > 300 MB of sorted pairs and partial sums.
         time.sleep(0.5)             # let the sampler's first queries finish
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         t_wall0 = time.time()
-        step_ms, acc_ms, launches, phase_ms, batch_rounds = [], [], 0, {}, 0
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        keep = []
         for _ in range(args.steps):
-            flush.zero_()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(stream)
-            if world > 1:
-                ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                ctx.msm_partial_device(pts, d_sc.data_ptr(), n, d_partial.data_ptr())
-                ea.record(stream)
-                g = sharding.gather_partials(d_partial)
-                eb.record(stream)
-                res = finish_step(g)
-                e1.record(stream)
-                e1.synchronize()
-                phase_ms = {"shard_msm": round(e0.elapsed_time(ea), 4), "all_gather": round(ea.elapsed_time(eb), 4),
-                            "combine": round(eb.elapsed_time(e1), 4)}
-            else:
-                g = device_step()
-                e1.record(stream)
-                res = finish_step(g)
-            e1.synchronize()
-            step_ms.append(e0.elapsed_time(e1))
-            prof = ctx.profile_read()
-            acc_ms.append(sum(ms for name, ms, _ in prof if name in ACC_STAGES))
-            batch_rounds = sum(1 for name, _, _ in prof if name in ("batched_add_first", "batched_add"))
-            launches += ctx.last_launch_count() + (1 if world > 1 else 0)
+            keep.append(enqueue_step())
+        e1.record(stream)
+        e1.synchronize()
+        res = fetch()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         t_wall1 = time.time()
         clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
-        stage_profile = {}
-        for name, ms, _ in ctx.profile_read():
-            stage_profile[name] = round(stage_profile.get(name, 0.0) + ms, 4)
-        ctx.profile(False)
-        total_ms = sum(step_ms)
-        log(f"[rank {rank}] step ms: {[round(x, 3) for x in step_ms]}")
+        total_ms = e0.elapsed_time(e1)
+        launches = args.steps * (ctx.last_launch_count() + (2 if world > 1 else 0))
+        if not same_point(res, want_xy):
+            raise SystemExit(f"[rank {rank}] result of the timed steps does not match the oracle's")
+        del keep
         if world > 1:
             t = torch.tensor([total_ms], device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             total_ms = float(t.item())
         ms_per_step = total_ms / args.steps
         value = n_total / (ms_per_step * 1e-3) / 1e6
+        log(f"[rank {rank}] {args.steps} steps in {total_ms:.3f} ms")
+
+        # ---- the same steps once more with a CUDA-event pair around every launch (zkmsm_profile; the launches then go
+        # out one by one instead of as a graph replay): stage split, duration of the dominant kernel group
+        ctx.profile(True)
+        enqueue_step(); fetch()      # first use of the per-launch events
+        acc_ms, batch_rounds, prof_step_ms, phase_ms = [], 0, [], {}
+        for _ in range(args.steps):
+            p0, pa, pb, p1 = (torch.cuda.Event(enable_timing=True) for _ in range(4))
+            p0.record(stream)
+            if world > 1:
+                if split == "range":
+                    ctx.msm_partial_range_device(pts, d_sc.data_ptr(), n, rank, world, d_partial.data_ptr())
+                else:
+                    ctx.msm_partial_device(pts, d_sc.data_ptr(), n, d_partial.data_ptr())
+                prof = None
+                pa.record(stream)
+                g = sharding.gather_partials(d_partial)
+                pb.record(stream)
+                ctx.combine_enqueue(g.data_ptr(), world)
+            else:
+                enqueue_step()
+            p1.record(stream)
+            p1.synchronize()
+            prof_step_ms.append(p0.elapsed_time(p1))
+            if world > 1:
+                phase_ms = {"shard_msm": round(p0.elapsed_time(pa), 4), "all_gather": round(pa.elapsed_time(pb), 4),
+                            "combine": round(pb.elapsed_time(p1), 4)}
+            fetch()
+            prof = ctx.profile_read()
+            if world == 1:
+                acc_ms.append(sum(ms for name, ms, _ in prof if name in ACC_STAGES))
+                batch_rounds = sum(1 for name, _, _ in prof if name in ("batched_add_first", "batched_add"))
+        stage_profile = {}
+        if world == 1:
+            for name, ms, _ in prof:
+                stage_profile[name] = round(stage_profile.get(name, 0.0) + ms, 4)
+        ctx.profile(False)
+        if world > 1:
+            # the combine's profile replaced the shard's: take the shard MSM's stages from one more run of it alone
+            ctx.profile(True)
+            for _ in range(2):
+                if split == "range":
+                    ctx.msm_partial_range_device(pts, d_sc.data_ptr(), n, rank, world, d_partial.data_ptr())
+                else:
+                    ctx.msm_partial_device(pts, d_sc.data_ptr(), n, d_partial.data_ptr())
+                prof = ctx.profile_read()
+                acc_ms.append(sum(ms for name, ms, _ in prof if name in ACC_STAGES))
+            batch_rounds = sum(1 for name, _, _ in prof if name in ("batched_add_first", "batched_add"))
+            for name, ms, _ in prof:
+                stage_profile[name] = round(stage_profile.get(name, 0.0) + ms, 4)
+            ctx.profile(False)
 
         # ---- end to end through the public API with host buffers
         for _ in range(2):
@@ -275,19 +344,22 @@ def main():
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            e2e_step()
+            e2e_res = e2e_step()
         torch.cuda.synchronize()
         e2e_s = (time.perf_counter() - t0) / args.steps
+        if not same_point(e2e_res, want_xy):
+            raise SystemExit("end-to-end result does not match the oracle's")
         if world > 1:
             t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             e2e_s = float(t.item())
         e2e = {"value": round(n_total / e2e_s / 1e6, 3), "unit": "Mpoints/s", "ms_per_step": round(e2e_s * 1e3, 4),
-               "h2d_bytes_per_step": n_total * 32, "d2h_bytes_per_step": 24 * 4 + 8,
-               "api": "zkmsm_g1_msm(ctx, resident CRS points, host scalars) -> host affine point"}
+               "h2d_bytes_per_step": n * 32, "d2h_bytes_per_step": 24 * 4 + 8,
+               "api": "zkmsm_g1_msm(ctx, resident CRS points, host scalars) -> host affine point" if world == 1 else
+                      "per rank: H2D of its scalars, zkmsm_g1_msm_partial_*_device, NCCL all-gather, zkmsm_g1_combine_enqueue + result"}
         if world == 1:
             # the same steps issued through the asynchronous pair of calls on two contexts, so that the copy of step
-            # k + 1 runs under the kernels of step k (what a prover with several MSMs per proof does, groth16.py);
+            # k + 1 runs under the kernels of step k (what a prover with several MSMs per proof does);
             # every step still copies its scalars from pinned host memory and reads its result back
             ctx_b = z.Context(local_rank)
             h_sc_b = h_sc.clone().pin_memory()
@@ -301,7 +373,7 @@ def main():
                 return lanes[(steps - 1) % 2][0].msm_result(1)
 
             out = pipelined(3)
-            if out[0].tolist() != res[0].tolist():
+            if not same_point(out, want_xy):
                 raise SystemExit("pipelined end-to-end result differs")
             torch.cuda.synchronize()
             t0 = time.perf_counter()
@@ -310,11 +382,13 @@ def main():
             pip_s = (time.perf_counter() - t0) / args.steps
             e2e["pipelined"] = {"value": round(n_total / pip_s / 1e6, 3), "ms_per_step": round(pip_s * 1e3, 4),
                                 "api": "zkmsm_g1_msm_begin / zkmsm_g1_msm_result alternating on two contexts"}
+            ctx_b.close()
 
     # ---- roofline of the dominant kernel (bucket accumulation), measured live above
     # Denominator: a limb product (32x32->64 multiply-accumulate) is one IMAD.WIDE, which issues at HALF the
     # rate of a 32-bit IMAD on sm_100 (measured: a 300-LP modmul takes 1237 cycles per warp per SMSP, see
-    # DESIGN.md); so LP peak = measured 32-bit IMAD rate / 2.  The carry-chain probe is reported beside it.
+    # DESIGN.md); the carry-chain probe (the Montgomery inner loop's instruction) is measured beside it and the
+    # LARGER of the two is the peak.
     lp_peak, probe = None, {}
     if rank == 0:
         for v, name in ((2, "imad32"), (1, "imad_wide_x_carry_chain"), (3, "imad_wide_x_dependent")):
@@ -324,16 +398,17 @@ def main():
             except Exception:
                 pass
         if "imad32" in probe:
-            lp_peak = probe["imad32"] * 1e12 / 2
+            lp_peak = max(probe["imad32"] / 2, probe.get("imad_wide_x_carry_chain", 0.0)) * 1e12
     acc_avg_ms = sum(acc_ms) / len(acc_ms)
-    achieved = n * LP_PER_G1_POINT / (acc_avg_ms * 1e-3) if acc_avg_ms > 0 else None
+    n_share = n_total / world        # terms' worth of accumulation work on this rank
+    achieved = n_share * LP_PER_G1_POINT / (acc_avg_ms * 1e-3) if acc_avg_ms > 0 else None
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
-    # DRAM bytes per launch of the dominant kernel: taken from the committed ncu --set full capture of the
-    # same command (profiles/*_accumulate_traffic.json, written by tools/summarize_profiles.py), never guessed
+    # DRAM bytes per launch of the dominant kernel group: from the committed ncu --set full capture of the
+    # same command (profiles/accumulate_traffic.json, written by tools/summarize_profiles.py), never guessed
     traffic = None
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "accumulate_traffic.json")))
@@ -341,43 +416,49 @@ def main():
             traffic = tr
     except Exception:
         pass
+    info = pts.info()
     roofline = {
         "bound": "int32 multiplier (IMAD.WIDE on the fma pipe); not hbm, not tensor",
-        "kernel": "bucket accumulation = BatchedAddRound<G1> x rounds (affine adds, shared inversion) + Accumulate<G1> "
+        "kernel": "bucket accumulation = BatchedAddRound<G1> x rounds (affine adds, shared inversion) + AccumulateBuckets<G1> "
                   "(XYZZ mixed adds); one 'launch' is this group, durations summed",
         "achieved": round(achieved / 1e12, 3) if achieved else None,
         "peak": round(lp_peak / 1e12, 3) if lp_peak else None,
         "unit": "T limb-products/s (32x32->64 multiply-accumulate)",
-        "frac": round(achieved / lp_peak, 4) if achieved and lp_peak else None,
-        "peak_source": "measured live: zkmsm_bench_imad 32-bit IMAD rate / 2 (IMAD.WIDE is half rate); MEASURED_PEAKS.json has no integer figure",
-        "frac_of_imad32_issue_rate": round(achieved / (2 * lp_peak), 4) if achieved and lp_peak else None,
+        "frac": None,
+        "canonical_frac": round(achieved / lp_peak, 4) if achieved and lp_peak else None,
+        "peak_source": "measured live: max(zkmsm_bench_imad 32-bit IMAD rate / 2, carry-chained IMAD.WIDE.X rate); MEASURED_PEAKS.json has no integer figure",
+        "frac_of_imad32_issue_rate": round(achieved / (2 * probe["imad32"] * 1e12), 4) if achieved and probe.get("imad32") else None,
         "probe_T_per_s": probe,
         "kernel_ms": round(acc_avg_ms, 4),
-        "kernel_share_of_step": round(acc_avg_ms / (sum(step_ms) / len(step_ms)), 4),
-        "step_frac": round(n_total * LP_PER_G1_POINT / (ms_per_step * 1e-3) / lp_peak, 4) if lp_peak else None,
+        "kernel_ms_source": "CUDA events around every launch of the group, second pass of the same K steps (zkmsm_profile)",
+        "kernel_share_of_step": round(acc_avg_ms / (sum(prof_step_ms) / len(prof_step_ms)), 4),
+        "step_frac_canonical": round(n_total * LP_PER_G1_POINT / (ms_per_step * 1e-3) / lp_peak / world, 4) if lp_peak else None,
         "traffic": traffic,
         "actual_lp_per_point": None,
         "hbm": {"achieved_GBps": round(n_total * BYTES_PER_G1_POINT / (ms_per_step * 1e-3) / 1e9, 2),
                 "peak_GBps": peaks.get("hbm_gbs"), "note": "algorithmic 128 B/point; the path is multiplier-bound"},
-        "stages_ms_last_step": stage_profile,
+        "stages_ms_profiled_step": stage_profile,
+        "profiled_step_ms": round(sum(prof_step_ms) / len(prof_step_ms), 4),
     }
-
-    info = pts.info()
     if info["precomputed"]:
         # what the kernels really multiply (fewer windows than the canonical 16 with precomputed tables; a batched
         # affine addition is 6 modmul, an XYZZ mixed addition 10, 300 LP each): after R halving rounds a fraction
-        # 2^-R of the entries is left for the mixed additions.  multiplier-pipe utilisation ~ frac * actual / canonical
+        # 2^-R of the entries is left for the mixed additions.
         left = 0.5 ** batch_rounds
         roofline["actual_lp_per_point"] = round(info["windows"] * ((1 - left) * 1800 + left * 3000))
         roofline["batched_affine_rounds"] = batch_rounds
-        if achieved and lp_peak:
-            # frac above counts the CANONICAL 48 000 LP per point and can exceed 1 once the
-            # algorithm executes fewer products than that; this is what the multiplier pipe really does
-            ex = achieved * roofline["actual_lp_per_point"] / LP_PER_G1_POINT
-            roofline["executed"] = {"T_lp_per_s": round(ex / 1e12, 3), "frac_of_peak": round(ex / lp_peak, 4),
-                                    "note": "limb products actually issued by the accumulation group / its time; "
-                                            "ncu sm__pipe_fmaheavy_cycles_active of the same kernels is in profiles/"}
         roofline["window_bits"] = info["c"]
+        if achieved and lp_peak:
+            # `frac` = limb products the group really ISSUES / its time / peak (the multiplier-pipe utilisation ncu
+            # reports as sm__pipe_fmaheavy_cycles_active, profiles/); `canonical_frac` counts SURVEY.md 8(d)'s
+            # 48 000 LP per point whatever the algorithm executes and so can exceed 1
+            ex = achieved * roofline["actual_lp_per_point"] / LP_PER_G1_POINT
+            roofline["achieved_executed"] = round(ex / 1e12, 3)
+            roofline["frac"] = round(ex / lp_peak, 4)
+            roofline["frac_note"] = ("frac = executed limb products / kernel time / peak; canonical_frac uses the fixed 48 000 LP per "
+                                     "point of SURVEY.md 8(d) (precomputed tables + batched-affine additions execute fewer)")
+    elif achieved and lp_peak:
+        roofline["frac"] = roofline["canonical_frac"]
 
     # ---- CPU baseline beside it (rank 0, N = 1 only): the reference algorithm on a bounded sample
     cpu_baseline = None
@@ -391,8 +472,16 @@ def main():
         if cpu_inf != gpu_inf or (not cpu_inf and cpu_xy.tolist() != gpu_xy.tolist()):
             raise SystemExit("GPU and CPU-reference MSM differ on the baseline sample")
         cpu_baseline = {"value": round(m / dt / 1e6, 9), "unit": "Mpoints/s", "cores": cores, "kind": "port",
-                        "sample": f"first {m} (point, scalar) pairs of the workload, {dt:.2f} s; result bit-identical to the GPU's",
+                        "sample": f"first {m} (point, scalar) pairs of the workload, {dt:.2f} s; result bit-identical to the GPU's; "
+                                  "the reference's cost is linear in n, so the figure extrapolates to 2^20",
                         "points_per_s": round(m / dt, 2)}
+
+    # ---- the metric's other halves: G2 MSM throughput and Groth16 prove ms (extra keys; `value` stays the G1 MSM)
+    pts.free()
+    del d_sc
+    torch.cuda.empty_cache()
+    g2_block = g2_bench(args, ctx, stream, rank, world, lp_peak) if args.g2_logn else None
+    groth16_block = groth16_bench(args, ctx, rank, world) if args.groth16_logn else None
 
     if rank == 0:
         line = {
@@ -401,18 +490,138 @@ def main():
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "u32x12 (381-bit Montgomery integers, exact)", "data": "synthetic",
             "config": {"workload": workload, "n": n_total, "per_gpu": n, "precomputed_crs_tables": not args.no_precompute,
-                       "l2": "flushed: 256 MB written between timed steps; working set per step also exceeds the 126 MB L2",
-                       "result_check": "sum s_i*(k_i g) == (sum s_i k_i mod r) g, verified before timing"},
+                       "multi_gpu_split": ("bucket range: every GPU holds the CRS tables and all scalars, owns 1/N of the buckets"
+                                           if split == "range" and world > 1 else "contiguous shards of the (point, scalar) vectors")
+                                          if world > 1 else None,
+                       "l2": "not flushed: inputs exceed the 126 MB L2 (each step gathers from 1.4 GB of resident CRS tables and "
+                             "rewrites > 300 MB of sorted pairs / partial sums); steps run back to back on one stream",
+                       "result_check": "sum s_i*(k_i g) == (sum s_i k_i mod r) g with the right-hand side computed by the ORACLE "
+                                       "(oracle/zkt_oracle.py scalar_mul), before timing and again on the timed steps' result"},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,
             "gpu_launches": launches, "clocks": clocks,
+            "g2": g2_block, "groth16": groth16_block,
         }
         if world > 1:
             line["multi_gpu"] = {"exchange": "one all-gather of 48 words per rank (NCCL), rank-order sum + affine on every rank",
-                                 "phase_ms_last_step": phase_ms}
+                                 "phase_ms_profiled_step": phase_ms}
         print(json.dumps(line), file=_real_stdout, flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def g2_bench(args, ctx, stream, rank, world, lp_peak):
+    """G2 MSM (Polynomial::eval_with_g2_hidings, polynomial.rs:284-293) at 2^g2_logn, same protocol as the headline:
+    K steps back to back, inputs resident, oracle-checked; N > 1 splits the bucket range."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import zk_toolkit_b200 as z
+    from importlib import import_module
+    sharding = import_module("zk-toolkit_b200.sharding")
+    n = 1 << args.g2_logn
+    dlog_arr, dlogs = synth_scalars(n, args.seed + 11, 0, n)
+    sc_arr, scalars = synth_scalars(n, args.seed + 12, 0, n)
+    use_range = world > 1 and world & (world - 1) == 0
+    if world > 1 and not use_range:
+        return None
+    with torch.cuda.stream(stream):
+        pts = ctx.points_from_scalars(2, z.G2Point.g().limbs(), dlog_arr, precompute=True, in_subgroup=True)
+        d_sc = torch.from_numpy(sc_arr.view(np.int32)).cuda()
+        d_partial = torch.zeros(96, dtype=torch.int32, device="cuda")
+        stream.synchronize()
+
+        def enqueue():
+            if world == 1:
+                ctx.msm_enqueue(pts, d_sc.data_ptr(), n)
+                return None
+            ctx.msm_partial_range_device(pts, d_sc.data_ptr(), n, rank, world, d_partial.data_ptr())
+            g = sharding.gather_partials(d_partial)
+            ctx.combine_enqueue(g.data_ptr(), world, group=2)
+            return g
+
+        for _ in range(3):
+            enqueue()
+            res = ctx.msm_result(2)
+        want = oracle_g2_multiple(sum(k * s for k, s in zip(dlogs, scalars)))
+        if not same_point(res, want):
+            raise SystemExit("G2 MSM result does not match the oracle's (sum s_i k_i) * g2")
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        keep = [enqueue() for _ in range(args.steps)]
+        e1.record(stream)
+        e1.synchronize()
+        res = ctx.msm_result(2)
+        ms = e0.elapsed_time(e1) / args.steps
+        if world > 1:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        if not same_point(res, want):
+            raise SystemExit("G2 MSM timed result does not match the oracle's")
+        info = pts.info()
+        pts.free()
+    lp = 134400   # SURVEY.md 8(d): 16 windows x 28 Fq modmul x 300 limb products per G2 point
+    return {"metric": "bls12_381_g2_msm_mpoints_per_s", "n": n, "value": round(n / (ms * 1e-3) / 1e6, 3), "unit": "Mpoints/s",
+            "ms_per_step": round(ms, 4), "window_bits": info["c"],
+            "roofline": {"bound": "int32 multiplier", "achieved": round(n * lp / (ms * 1e-3) / 1e12, 3),
+                         "peak": round(lp_peak / 1e12, 3) if lp_peak else None, "unit": "T limb-products/s",
+                         "canonical_step_frac": round(n * lp / (ms * 1e-3) / lp_peak, 4) if lp_peak else None,
+                         "note": "whole step over the canonical 134 400 LP per G2 point"},
+            "result_check": "oracle closed form (sum s_i k_i) * g2"}
+
+
+def groth16_bench(args, ctx, rank, world):
+    """Groth16 prove (Prover::prove, prover.rs:96-147) on the synthetic instance of BASELINE.json configs[4]
+    (n constraints, n witness wires), end to end through the API: the coefficient vectors come
+    from pinned HOST memory every proof and the proof is read back.  N > 1: ONE proof over the N GPUs."""
+    import torch
+    import torch.distributed as dist
+    from importlib import import_module
+    S = import_module("zk-toolkit_b200.synthetic")
+    G = import_module("zk-toolkit_b200.groth16")
+    n = 1 << args.groth16_logn
+    use_dist = world > 1 and world & (world - 1) == 0
+    if world > 1 and not use_dist:
+        return None
+    t0 = time.time()
+    inst = S.build(n, n, ctx=ctx)
+    setup_s = time.time() - t0
+    r, s = 0x1234567 % R, 0x7654321 % R
+    prove = (lambda: G.prove_distributed(inst["prover"], inst["crs"], r, s)) if use_dist else (lambda: inst["prover"].prove(inst["crs"], r, s))
+    for _ in range(3):
+        proof = prove()
+    a, b, c = S.expected_dlogs(inst, r, s)
+    ok = (same_point((proof.A.limbs(), proof.A.is_zero()), oracle_g1_multiple(a)) and
+          same_point((proof.B.limbs(), proof.B.is_zero()), oracle_g2_multiple(b)) and
+          same_point((proof.C.limbs(), proof.C.is_zero()), oracle_g1_multiple(c)))
+    if not ok:
+        raise SystemExit("Groth16 proof does not match its closed form (oracle scalar multiplications)")
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    times = []
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        p2 = prove()
+        times.append((time.perf_counter() - t0) * 1e3)
+    if (p2.A, p2.B, p2.C) != (proof.A, proof.B, proof.C):
+        raise SystemExit("Groth16 proofs differ between runs")
+    ms = sum(times) / len(times)
+    if world > 1:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    inst["crs"].free()
+    return {"metric": "groth16_prove_ms", "n_constraints": n, "n_witness": n, "prove_ms": round(ms, 3), "min_ms": round(min(times), 3),
+            "unit": "ms", "higher_is_better": False, "n_gpus": world, "setup_s": round(setup_s, 1),
+            "msms": "A: G1 n+2 | B: G2 n+2 | C: G1 3n+3 (s A + r B_g1 - r s delta folded into C's scalars), three streams",
+            "h2d_bytes_per_proof": 4 * n * 32, "d2h_bytes_per_proof": 96 * 4,
+            "api": "zkmsm_groth16_prove" if not use_dist else "zkmsm_groth16_prove_partial per rank + NCCL all-gather + zkmsm_groth16_combine",
+            "result_check": "A, B, C equal their closed-form discrete logs times the generators, right-hand sides by the ORACLE"}
 
 
 def reference_arm(args, rank, world, n_total, workload, W):

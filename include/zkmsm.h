@@ -166,6 +166,9 @@ int zkmsm_g1_combine_device(zkmsm_ctx* ctx, const uint32_t* partials_device, siz
                             int* out_is_inf);
 int zkmsm_g2_combine_device(zkmsm_ctx* ctx, const uint32_t* partials_device, size_t k, uint32_t out_xy[48],
                             int* out_is_inf);
+/* Stream-ordered form: enqueue the sum of k device-resident partials; zkmsm_g{1,2}_msm_result fetches it. */
+int zkmsm_g1_combine_enqueue(zkmsm_ctx* ctx, const uint32_t* partials_device, size_t k);
+int zkmsm_g2_combine_enqueue(zkmsm_ctx* ctx, const uint32_t* partials_device, size_t k);
 
 /* ---- vector scalar multiplication of one base point: `&G1Point * &Fq1`
  * (impl_scalar_mul_point!, curves/macros.rs:2-32) for n scalars at once, as CRS::new does
@@ -197,6 +200,56 @@ int zkmsm_fr_aggregate(zkmsm_ctx* ctx, const uint32_t* polys, size_t n_wires, si
  * the reference's schoolbook product and long division, which remain the path below 32 and the cross-check. */
 int zkmsm_fr_quotient(zkmsm_ctx* ctx, const uint32_t* u, const uint32_t* v, const uint32_t* w, size_t n,
                       uint32_t* h_out, int* out_exact);
+
+/* ---- Groth16 proof generation: Prover::prove (groth16/zktoolkit_based/prover.rs:96-147) in one call.
+ * zkmsm_crs_load uploads the CRS of crs.rs:17-43 once (what the prover reads of it) and keeps it resident;
+ * zkmsm_groth16_prove takes the prover's aggregated coefficient vectors
+ *   u_j = sum_i a_i u_{i,j},  v_j = sum_i a_i v_{i,j}   (the per-wire loop of prover.rs:108-117 collapsed,
+ *                                                         zkmsm_fr_aggregate),
+ *   h = (u v - w) / t  (prover.rs:64-71, zkmsm_fr_quotient), the witness wires a_{l+1..m}, and the blinding
+ * scalars r, s (the reference draws them itself, prover.rs:100-101; here the caller does, so that proofs are
+ * reproducible), and returns Proof{A, B, C} (proof.rs:7-11) as canonical limbs A (24) | B (48) | C (24) with one
+ * AtInfinity flag each.  A, B and C are three MSMs running concurrently on three streams; C uses the identity
+ *   s A + r B_g1 - r s delta = sum_j (s u_j + r v_j) [x^j]_1 + s alpha + r beta + r s delta
+ * so that B_g1 (prover.rs:120) and the two scalar multiplications of prover.rs:137-138 are folded into its MSM.
+ * All vectors: 8 words per element, canonical, < r.  flags as for zkmsm_*_load_points (a CRS is made of multiples
+ * of the generators: ZKMSM_PRECOMPUTE | ZKMSM_SUBGROUP is the intended use).  `inf` arrays are optional
+ * AtInfinity flags (NULL = none).  n_xt <= n. */
+typedef struct zkmsm_crs zkmsm_crs;
+typedef struct zkmsm_crs_desc {
+  const uint32_t* g1_alpha;        /* crs.g1.alpha, 24 words */
+  const uint32_t* g1_beta;         /* crs.g1.beta */
+  const uint32_t* g1_delta;        /* crs.g1.delta */
+  const uint32_t* g1_xi;           /* crs.g1.xi, n x 24 (crs.rs:88-102) */
+  const uint8_t* g1_xi_inf;
+  size_t n;
+  const uint32_t* g1_uvw_wit;      /* crs.g1.uvw_wit, n_wit x 24 (crs.rs:65-86) */
+  const uint8_t* g1_uvw_wit_inf;
+  size_t n_wit;
+  const uint32_t* g1_xt_by_delta;  /* crs.g1.xt_by_delta, n_xt x 24 (crs.rs:104-116) */
+  const uint8_t* g1_xt_by_delta_inf;
+  size_t n_xt;
+  const uint32_t* g2_beta;         /* crs.g2.beta, 48 words */
+  const uint32_t* g2_delta;        /* crs.g2.delta */
+  const uint32_t* g2_xi;           /* crs.g2.xi, n x 48 */
+  const uint8_t* g2_xi_inf;
+} zkmsm_crs_desc;
+int zkmsm_crs_load(zkmsm_ctx* ctx, const zkmsm_crs_desc* desc, unsigned flags, zkmsm_crs** out);
+int zkmsm_crs_free(zkmsm_ctx* ctx, zkmsm_crs* crs);
+int zkmsm_crs_sizes(const zkmsm_crs* crs, size_t* n, size_t* n_wit, size_t* n_xt);
+int zkmsm_groth16_prove(zkmsm_ctx* ctx, zkmsm_crs* crs, const uint32_t* u, const uint32_t* v, const uint32_t* h,
+                        const uint32_t* witness, const uint32_t r[8], const uint32_t s[8], uint32_t proof_out[96],
+                        int out_is_inf[3]);
+/* The same proof over `world` devices (configs[4]): every device loads the CRS and runs its 1/world share of the
+ * three MSMs (bucket-range split, zkmsm_g1_msm_partial_range); the shares (one blob of
+ * ZKMSM_GROTH16_PARTIAL_WORDS per rank, rank order, gathered by the caller -- NCCL, MPI or memcpy) are added by
+ * zkmsm_groth16_combine on any one device.  Bit-identical to zkmsm_groth16_prove. */
+#define ZKMSM_GROTH16_PARTIAL_WORDS 192 /* A (48) | B (96) | C (48) */
+int zkmsm_groth16_prove_partial(zkmsm_ctx* ctx, zkmsm_crs* crs, const uint32_t* u, const uint32_t* v, const uint32_t* h,
+                                const uint32_t* witness, const uint32_t r[8], const uint32_t s[8], unsigned rank,
+                                unsigned world, uint32_t out_partials[ZKMSM_GROTH16_PARTIAL_WORDS]);
+int zkmsm_groth16_combine(zkmsm_ctx* ctx, const uint32_t* partials, size_t world, uint32_t proof_out[96],
+                          int out_is_inf[3]);
 
 /* ---- diagnostics: integer-multiply throughput of this device (roofline denominator).
  * variant 0: independent mad.wide.u32; 1: carry-chained IMAD.WIDE.U32.X (mad.lo.cc/madc.hi.cc

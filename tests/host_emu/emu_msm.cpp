@@ -19,6 +19,7 @@ struct HostExec {
     for (uint32_t t = 0; t < nthreads; t++) Body::run(t, args...);
     launches++;
   }
+  template <class Body, class... Args> void launch_capped(uint32_t, uint32_t nthreads, Args... args) { launch<Body>(nthreads, args...); }
   void zero(void* p, size_t bytes) { memset(p, 0, bytes); }
   template <class C> void accumulate_buckets(const MsmPlan& p, const uint32_t* offsets, const Entry* entries,
                                              const Affine<typename C::F>* points, uint32_t direct,

@@ -27,18 +27,29 @@ def write_kats(path):
         f.write("\n".join(lines) + "\n")
 
 
-def build(tmp):
-    exe = os.path.join(tmp, "test_seam")
+def build(tmp, name="test_seam"):
+    exe = os.path.join(tmp, name)
     libdir = os.path.join(ROOT, "zk-toolkit_b200")
     subprocess.check_call(["g++", "-O2", "-std=c++17", "-I", os.path.join(ROOT, "include"),
-                           os.path.join(ROOT, "tests", "cpp", "test_seam.cpp"), "-o", exe,
+                           os.path.join(ROOT, "tests", "cpp", name + ".cpp"), "-o", exe,
                            "-L", libdir, "-lzkmsm", f"-Wl,-rpath,{libdir}", "-Wl,--allow-shlib-undefined"])
     return exe
 
 
 def test_cpp_host_mirror_compiles(tmp_path):
-    """no GPU needed: the header and the test link against the C ABI"""
+    """no GPU needed: the header and the tests link against the C ABI"""
     build(str(tmp_path))
+    build(str(tmp_path), "test_multi_device")
+
+
+@pytest.mark.gpu
+def test_two_contexts_in_one_process_partials_and_combine(tmp_path):
+    """single-process host with one context per device (two devices when the box has them): point-split and
+    bucket-range-split partials, combined on either device, against the fixed-base closed form"""
+    exe = build(str(tmp_path), "test_multi_device")
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "OK: 0 failure(s)" in out.stdout
 
 
 @pytest.mark.gpu

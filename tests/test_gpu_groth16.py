@@ -58,6 +58,26 @@ def test_config1_proof_identical_to_oracle_and_verifies(z, precompute):
     got = (g1_to_o(proof.A), g2_to_o(proof.B), g1_to_o(proof.C))
     assert got == want                                      # identical canonical affine coordinates
     assert O.verify(got, crs, op.statement())               # and the reference verifier equation holds
+    # the proof split over 1, 2 and 4 "devices" (zkmsm_groth16_prove_partial / _combine, all on this GPU here)
+    if precompute:
+        for world in (1, 2, 4):
+            parts = [gp.prove_partial(dcrs, r, s, k, world) for k in range(world)]
+            pd = G.combine_partials(parts)
+            assert (pd.A, pd.B, pd.C) == (proof.A, proof.B, proof.C)
+    # r, s are field elements: anything else is rejected, not reduced silently on the device
+    import numpy as np
+    ctx = dcrs.ctx
+    u, v, h, wit = gp._arrays(dcrs)
+    bad_r = z.scalars_to_array([O.R])
+    ok_s = z.scalars_to_array([5])
+    out = np.zeros(96, dtype=np.uint32)
+    import ctypes
+    inf = (ctypes.c_int * 3)()
+    from zk_toolkit_b200 import ZkmsmError  # noqa: F401
+    L = import_module("zk-toolkit_b200._lib")
+    rc = ctx.lib.zkmsm_groth16_prove(ctx.h, dcrs.handle, L.dptr(u), L.dptr(v), L.dptr(h), L.dptr(wit), L.dptr(bad_r), L.dptr(ok_s),
+                                     L.dptr(out), inf)
+    assert rc == -3
 
 
 def test_synthetic_instance_closed_form_and_verifier(z):

@@ -17,6 +17,17 @@ PRECOMPUTE = 1
 SUBGROUP = 2
 G1_WORDS, G2_WORDS = 24, 48
 G1_PARTIAL_WORDS, G2_PARTIAL_WORDS = 48, 96
+GROTH16_PARTIAL_WORDS = 192
+
+
+class CrsDesc(ctypes.Structure):
+    """zkmsm_crs_desc (include/zkmsm.h)"""
+    _fields_ = [("g1_alpha", ctypes.c_void_p), ("g1_beta", ctypes.c_void_p), ("g1_delta", ctypes.c_void_p),
+                ("g1_xi", ctypes.c_void_p), ("g1_xi_inf", ctypes.c_void_p), ("n", ctypes.c_size_t),
+                ("g1_uvw_wit", ctypes.c_void_p), ("g1_uvw_wit_inf", ctypes.c_void_p), ("n_wit", ctypes.c_size_t),
+                ("g1_xt_by_delta", ctypes.c_void_p), ("g1_xt_by_delta_inf", ctypes.c_void_p), ("n_xt", ctypes.c_size_t),
+                ("g2_beta", ctypes.c_void_p), ("g2_delta", ctypes.c_void_p), ("g2_xi", ctypes.c_void_p),
+                ("g2_xi_inf", ctypes.c_void_p)]
 
 
 class ZkmsmError(RuntimeError):
@@ -39,8 +50,11 @@ SYMBOLS = [
     "zkmsm_g1_msm_partial_range", "zkmsm_g2_msm_partial_range",
     "zkmsm_g1_msm_partial_range_device", "zkmsm_g2_msm_partial_range_device",
     "zkmsm_g1_combine", "zkmsm_g2_combine", "zkmsm_g1_combine_device", "zkmsm_g2_combine_device",
+    "zkmsm_g1_combine_enqueue", "zkmsm_g2_combine_enqueue",
     "zkmsm_g1_mul_base", "zkmsm_g2_mul_base", "zkmsm_g1_points_from_scalars", "zkmsm_g2_points_from_scalars",
     "zkmsm_fr_aggregate", "zkmsm_fr_quotient", "zkmsm_bench_imad",
+    "zkmsm_crs_load", "zkmsm_crs_free", "zkmsm_crs_sizes", "zkmsm_groth16_prove", "zkmsm_groth16_prove_partial",
+    "zkmsm_groth16_combine",
 ]
 
 _lib = None
@@ -103,6 +117,8 @@ def load():
         "zkmsm_g2_combine": (ci, [vp, vp, sz, vp, ip]),
         "zkmsm_g1_combine_device": (ci, [vp, vp, sz, vp, ip]),
         "zkmsm_g2_combine_device": (ci, [vp, vp, sz, vp, ip]),
+        "zkmsm_g1_combine_enqueue": (ci, [vp, vp, sz]),
+        "zkmsm_g2_combine_enqueue": (ci, [vp, vp, sz]),
         "zkmsm_g1_mul_base": (ci, [vp, vp, vp, sz, vp, vp]),
         "zkmsm_g2_mul_base": (ci, [vp, vp, vp, sz, vp, vp]),
         "zkmsm_g1_points_from_scalars": (ci, [vp, vp, vp, sz, cu, vpp]),
@@ -110,6 +126,12 @@ def load():
         "zkmsm_fr_aggregate": (ci, [vp, vp, sz, sz, vp, vp]),
         "zkmsm_fr_quotient": (ci, [vp, vp, vp, vp, sz, vp, ip]),
         "zkmsm_bench_imad": (ci, [vp, ci, ci, dp, dp]),
+        "zkmsm_crs_load": (ci, [vp, ctypes.POINTER(CrsDesc), cu, vpp]),
+        "zkmsm_crs_free": (ci, [vp, vp]),
+        "zkmsm_crs_sizes": (ci, [vp, ctypes.POINTER(sz), ctypes.POINTER(sz), ctypes.POINTER(sz)]),
+        "zkmsm_groth16_prove": (ci, [vp, vp, vp, vp, vp, vp, vp, vp, vp, ip]),
+        "zkmsm_groth16_prove_partial": (ci, [vp, vp, vp, vp, vp, vp, vp, vp, cu, cu, vp]),
+        "zkmsm_groth16_combine": (ci, [vp, vp, sz, vp, ip]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

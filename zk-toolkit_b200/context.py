@@ -257,6 +257,11 @@ class Context:
         self._check(fn(self.h, ctypes.c_void_p(partials_dev_ptr), k, L.dptr(out), ctypes.byref(inf)))
         return out, bool(inf.value)
 
+    def combine_enqueue(self, partials_dev_ptr, k, group=1):
+        """stream-ordered combine of k device-resident partials; fetch with msm_result(group)"""
+        fn = self.lib.zkmsm_g1_combine_enqueue if group == 1 else self.lib.zkmsm_g2_combine_enqueue
+        self._check(fn(self.h, ctypes.c_void_p(partials_dev_ptr), k))
+
     def fr_aggregate(self, polys, wires):
         """out[j] = sum_i wires[i] * polys[i][j] mod r; polys (n_wires, n, 8) uint32, wires (n_wires, 8) -> (n, 8)"""
         polys = L.as_u32(polys, 8)

@@ -50,6 +50,62 @@ struct FrAggregate {
   }
 };
 
+// ---------------------------------------------------------------- scalar vectors of one Groth16 proof
+// Prover::prove (groth16/zktoolkit_based/prover.rs:96-147) as three MSMs (zkmsm_groth16_prove):
+//   A = alpha + sum_j u_j [x^j]_1 + r delta                        scalars  u ++ [1, r]
+//   B = beta_2 + sum_j v_j [x^j]_2 + s delta_2                     scalars  v ++ [1, s]
+//   C = sum a_i uvw_wit_i + sum h_j [x^j t/delta]_1 + s A + r B_g1 - r s delta       (:128-145)
+//     = sum a_i uvw_wit_i + sum h_j [x^j t/delta]_1 + sum_j (s u_j + r v_j) [x^j]_1 + s alpha + r beta + (r s) delta
+// (expand A and B_g1 = beta + sum v_j [x^j]_1 + s delta): one MSM with scalars wit ++ h ++ (s u + r v) ++ [s, r, r s],
+// so B_g1 and the two 255-bit scalar multiplications s A, r B_g1 of the reference are never formed.
+// This body fills what is not a plain copy of the caller's vectors: thread j < n writes (s u_j + r v_j) mod r,
+// thread n the trailing slots.  rs = r | s (canonical, < r, else *err |= 1).
+struct Groth16Scalars {
+  static const char* name() { return "groth16_scalars"; }
+  static ZK_HD bool below_r(const uint32_t* a) {
+    uint32_t t = ptx::sub_cc(a[0], FR_P[0]);
+#pragma unroll
+    for (int i = 1; i < 8; i++) t = ptx::subc_cc(a[i], FR_P[i]);
+    (void)t;
+    return ptx::subc(0, 0) != 0;   // borrow: a < r
+  }
+  static ZK_HD void run(uint32_t tid, uint32_t n, const uint32_t* rs, uint32_t* su, uint32_t* sv, uint32_t* sc3, uint32_t* err) {
+    if (tid > n) return;
+    uint32_t rc[8], sc[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { rc[i] = rs[i]; sc[i] = rs[8 + i]; }
+    Fr rm, sm;
+    fto_mont(rm, rc);
+    fto_mont(sm, sc);
+    if (tid < n) {
+      Fr u, v, a, b;
+#pragma unroll
+      for (int i = 0; i < 8; i++) { u.v[i] = su[(size_t)tid * 8 + i]; v.v[i] = sv[(size_t)tid * 8 + i]; }
+      fmul(a, sm, u);   // (s R) u / R = s u, fully reduced
+      fmul(b, rm, v);
+      fadd(a, a, b);
+#pragma unroll
+      for (int i = 0; i < 8; i++) sc3[(size_t)tid * 8 + i] = a.v[i];
+      return;
+    }
+    if (!below_r(rc) || !below_r(sc)) zk_atomic_or_u32(err, 1u);
+    Fr prod, sone;
+    fset_zero(sone);
+    sone.v[0] = 1;
+    fmul(prod, rm, sm);          // r s R
+    fmul(prod, prod, sone);      // r s (canonical)
+    uint32_t* a_tail = su + (size_t)n * 8;
+    uint32_t* b_tail = sv + (size_t)n * 8;
+    uint32_t* c_tail = sc3 + (size_t)n * 8;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      a_tail[i] = i == 0 ? 1u : 0u; a_tail[8 + i] = rc[i];
+      b_tail[i] = i == 0 ? 1u : 0u; b_tail[8 + i] = sc[i];
+      c_tail[i] = sc[i]; c_tail[8 + i] = rc[i]; c_tail[16 + i] = prod.v[i];
+    }
+  }
+};
+
 // ---------------------------------------------------------------- quotient polynomial h = (u v - w) / t
 // Reference: Prover::new (groth16/zktoolkit_based/prover.rs:64-71): p = qap.build_p(witness) = u*v - w
 // (qap.rs:99-112, Polynomial::multiply_by polynomial.rs:173-190), t = prod_{k=1..n} (x - k) (QAP::build_t,

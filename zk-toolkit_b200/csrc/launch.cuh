@@ -26,6 +26,13 @@ __global__ void __launch_bounds__(kBlock, ZK_MIN_BLOCKS) body_kernel(uint32_t nt
   if (tid < nthreads) Body::run(tid, a...);
 }
 
+// same, on a grid of at most max_blocks blocks that strides over the logical threads: what the gated fallback
+// launches use (a launch that returns at its gate then costs ~300 blocks instead of thousands)
+template <class Body, class... A>
+__global__ void __launch_bounds__(kBlock, ZK_MIN_BLOCKS) body_kernel_strided(uint32_t nthreads, A... a) {
+  for (uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x; tid < nthreads; tid += gridDim.x * blockDim.x) Body::run(tid, a...);
+}
+
 template <class Body, class Sig> struct LaunchBase;
 template <class Body, class... A> struct LaunchBase<Body, void(uint32_t, A...)> {
   static cudaError_t go(cudaStream_t st, uint32_t nthreads, A... a)
@@ -38,9 +45,25 @@ template <class Body, class... A> struct LaunchBase<Body, void(uint32_t, A...)> 
       ;
 #endif
 };
+// the strided form is its own launcher so that only the bodies that use it (ZK_INSTANTIATE_KERNEL_STRIDED) compile it
+template <class Body, class Sig> struct LaunchStridedBase;
+template <class Body, class... A> struct LaunchStridedBase<Body, void(uint32_t, A...)> {
+  static cudaError_t go(cudaStream_t st, uint32_t max_blocks, uint32_t nthreads, A... a)
+#ifdef ZK_DEFINE_LAUNCH
+  {
+    uint32_t blocks = (nthreads + kBlock - 1) / kBlock;
+    body_kernel_strided<Body, A...><<<blocks < max_blocks ? blocks : max_blocks, kBlock, 0, st>>>(nthreads, a...);
+    return cudaGetLastError();
+  }
+#else
+      ;
+#endif
+};
+template <class Body> struct LaunchStrided : LaunchStridedBase<Body, decltype(Body::run)> {};
 template <class Body> struct Launch : LaunchBase<Body, decltype(Body::run)> {};
 
 #define ZK_INSTANTIATE_KERNEL(...) template struct zk::LaunchBase<__VA_ARGS__, decltype(__VA_ARGS__::run)>
+#define ZK_INSTANTIATE_KERNEL_STRIDED(...) template struct zk::LaunchStridedBase<__VA_ARGS__, decltype(__VA_ARGS__::run)>
 
 // Exec policy for msm_launch (msm.cuh): stream-ordered CUDA launches
 // block-cooperative exclusive scan (tu_sort.cu): offsets[0..n] = scan(hist), hist <- offsets (cursors)
@@ -118,6 +141,12 @@ struct CudaExec {
     if (slot >= 0) cudaEventRecord(prof->end[slot], st);
     launches++;
     if (e != cudaSuccess) err = e;
+  }
+  // Body launch on a capped, striding grid (see body_kernel_strided)
+  template <class Body, class... Args>
+  void launch_capped(uint32_t max_blocks, uint32_t nthreads, Args... args) {
+    if (nthreads == 0) return;
+    timed(Body::name(), nthreads, 1, [&] { return LaunchStrided<Body>::go(st, max_blocks, nthreads, args...); });
   }
   // profiling bracket around a non-Body launch
   template <class Fn> void timed(const char* name, uint32_t threads, int nlaunch, Fn fn) {

@@ -793,6 +793,7 @@ struct MsmTuning {
   int quotient_schoolbook = 0;   // ZKMSM_QUOTIENT_SCHOOLBOOK
   int no_graph = 0;        // ZKMSM_NO_GRAPH: launch kernel by kernel instead of replaying a captured CUDA graph
   int no_bucket_acc = 0;   // ZKMSM_NO_BUCKET_ACC: always the chunked accumulation + fix-up tree
+  int acc_G = 0;           // ZKMSM_ACC_G: lanes per bucket of AccumulateBuckets (power of two <= 32)
   static int env_int(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; }
   static MsmTuning from_env() {
     MsmTuning t;
@@ -808,6 +809,7 @@ struct MsmTuning {
     t.quotient_schoolbook = getenv("ZKMSM_QUOTIENT_SCHOOLBOOK") ? 1 : 0;
     t.no_graph = getenv("ZKMSM_NO_GRAPH") ? 1 : 0;
     t.no_bucket_acc = getenv("ZKMSM_NO_BUCKET_ACC") ? 1 : 0;
+    t.acc_G = env_int("ZKMSM_ACC_G", 0);
     return t;
   }
 };
@@ -907,8 +909,9 @@ inline uint64_t msm_expected_entries(const MsmPlan& p) {
 }
 
 // Lanes per bucket and item cap for AccumulateBuckets when about `left` items in total are expected in the plan's
-// buckets: enough lanes that the launch is about two waves of the device, never more lanes than half the items of
-// an average bucket, at most ~256 items per lane before the chunked fallback is the better kernel.
+// buckets: as many lanes as still fit ONE wave of the device (a second wave costs as much as the first: measured
+// 0.31 ms with 4 lanes against 0.35 ms with 8 for 8192 buckets of 60 items), never more lanes than half the items
+// of an average bucket, at most ~256 items per lane before the chunked fallback is the better kernel.
 inline void msm_pick_bucket_acc(MsmPlan& p, uint64_t left, const MsmTuning& tune) {
   p.acc_G = 0;
   p.acc_cap = 0;
@@ -916,7 +919,8 @@ inline void msm_pick_bucket_acc(MsmPlan& p, uint64_t left, const MsmTuning& tune
   const uint64_t avg = left / p.nb + 1;
   uint32_t G = 1;
   const uint64_t slots = p.acc_slots ? p.acc_slots : 32768;
-  while (G < 32 && (uint64_t)p.nb * G * 2 <= 2 * slots && (uint64_t)G * 2 <= (avg + 1) / 2) G *= 2;
+  while (G < 32 && (uint64_t)p.nb * G * 2 <= slots && (uint64_t)G * 2 <= (avg + 1) / 2) G *= 2;
+  if (tune.acc_G >= 1 && tune.acc_G <= 32 && (tune.acc_G & (tune.acc_G - 1)) == 0) G = (uint32_t)tune.acc_G;
   if (avg / G > 256) return;   // huge buckets without pre-reduction (narrow forced windows): chunks balance better
   p.acc_G = G;
   const uint64_t cap = 4 * avg + 32 * G;
@@ -1065,16 +1069,18 @@ void msm_launch(Exec& ex, const MsmPlan& p, const MsmTuning& tune, const MsmBuff
     ex.template accumulate_buckets<C>(pa, acc_offsets, acc_entries, acc_points, p.batch_rounds > 0 ? 1u : 0u, b.bucket_sums, b.big);
     gate = b.big;
   }
-  ex.template launch<Accumulate<C>>(pa.acc_threads, pa, acc_offsets, acc_entries, acc_points, b.bucket_sums, b.partials,
-                                    b.partial_keys, gate);
+  // (as a gated fallback on a capped grid: the launches that find the gate closed cost a few hundred blocks each)
+  const uint32_t cap_blocks = gate ? (p.acc_slots ? p.acc_slots / 128 : 296) : 0xffffffffu;
+  ex.template launch_capped<Accumulate<C>>(cap_blocks, pa.acc_threads, pa, acc_offsets, acc_entries, acc_points, b.bucket_sums,
+                                           b.partials, b.partial_keys, gate);
   {  // fix-up tree over the per-chunk partial sums: level l reads region l, writes region l+1
     uint32_t count = pa.acc_threads, level = 0;
     XYZZ<F>* pin = b.partials;
     uint32_t* kin = b.partial_keys;
     while (count > 1) {
       uint32_t fan = fix_fan(level++), next = (count + fan - 1) / fan;
-      ex.template launch<FixupLevel<C>>(next, count, fan, (const uint32_t*)kin, (const XYZZ<F>*)pin, kin + count, pin + count,
-                                        b.bucket_sums, gate);
+      ex.template launch_capped<FixupLevel<C>>(cap_blocks, next, count, fan, (const uint32_t*)kin, (const XYZZ<F>*)pin, kin + count,
+                                               pin + count, b.bucket_sums, gate);
       pin += count;
       kin += count;
       count = next;

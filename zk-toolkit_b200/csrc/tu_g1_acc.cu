@@ -7,4 +7,4 @@
 #define ZK_ACC_DOUBLE_BUFFER   // next point held in registers under the current mixed add (208 registers, -2.7 %)
 #include "launch.cuh"
 #include "msm.cuh"
-ZK_INSTANTIATE_KERNEL(zk::Accumulate<zk::G1>);
+ZK_INSTANTIATE_KERNEL_STRIDED(zk::Accumulate<zk::G1>);   // launched on a capped grid (gated fallback of AccumulateBuckets)

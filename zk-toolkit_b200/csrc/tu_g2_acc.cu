@@ -3,4 +3,4 @@
 
 #include "launch.cuh"
 #include "msm.cuh"
-ZK_INSTANTIATE_KERNEL(zk::Accumulate<zk::G2>);
+ZK_INSTANTIATE_KERNEL_STRIDED(zk::Accumulate<zk::G2>);   // launched on a capped grid (gated fallback of AccumulateBuckets)

@@ -2,4 +2,4 @@
 #define ZK_DEFINE_LAUNCH
 #include "launch.cuh"
 #include "msm.cuh"
-ZK_INSTANTIATE_KERNEL(zk::FixupLevel<zk::G2>);
+ZK_INSTANTIATE_KERNEL_STRIDED(zk::FixupLevel<zk::G2>);   // launched on a capped grid (gated fallback of AccumulateBuckets)

@@ -29,6 +29,7 @@ struct alignas(16) ResultBlock {      // device + pinned host mirror
   uint32_t inf;
   uint32_t err;
   uint32_t big;           // AccumulateBuckets' "a bucket is over the cap" flag (device side only)
+  uint32_t aux_err;       // zkmsm_groth16_prove: r or s out of range
 };
 
 // one captured MSM launch sequence (CUDA graph): replayed while the same point set, sizes, buffers and options recur
@@ -202,7 +203,7 @@ extern "C" int zkmsm_set_option(zkmsm_ctx* ctx, const char* name, long value) {
       {"batch_blocks", &MsmTuning::batch_blocks}, {"L", &MsmTuning::L}, {"K", &MsmTuning::K},
       {"no_wave_L", &MsmTuning::no_wave_L}, {"no_coop", &MsmTuning::no_coop}, {"ntt_no_fuse", &MsmTuning::ntt_no_fuse},
       {"quotient_schoolbook", &MsmTuning::quotient_schoolbook}, {"no_graph", &MsmTuning::no_graph},
-      {"no_bucket_acc", &MsmTuning::no_bucket_acc}};
+      {"no_bucket_acc", &MsmTuning::no_bucket_acc}, {"acc_G", &MsmTuning::acc_G}};
   for (auto& t : table)
     if (strcmp(t.name, name) == 0) {
       ctx->tune.*(t.field) = (int)value;
@@ -669,10 +670,12 @@ extern "C" int zkmsm_g2_msm_partial_range_device(zkmsm_ctx* ctx, const zkmsm_poi
   return partial_device_impl<G2>(ctx, ps, ds, n, 2, d_out, rank, world);
 }
 
+// enqueue_only: stream-ordered, the result is fetched later with zkmsm_g{1,2}_msm_result
 template <class C>
-static int combine_impl(zkmsm_ctx* ctx, const uint32_t* parts, bool on_device, size_t k, uint32_t* out_xy, int* out_is_inf) {
+static int combine_impl(zkmsm_ctx* ctx, const uint32_t* parts, bool on_device, size_t k, uint32_t* out_xy, int* out_is_inf,
+                        bool enqueue_only = false) {
   typedef typename C::F F;
-  if (!ctx || (k && !parts) || !out_xy || !out_is_inf || k > 4096) return fail(ctx, ZKMSM_ERR_INVALID_ARG, "bad argument");
+  if (!ctx || (k && !parts) || (!enqueue_only && (!out_xy || !out_is_inf)) || k > 4096) return fail(ctx, ZKMSM_ERR_INVALID_ARG, "bad argument");
   CU(ctx, cudaSetDevice(ctx->device));
   const XYZZ<F>* d_parts = (const XYZZ<F>*)parts;
   if (!on_device && k) {
@@ -690,6 +693,7 @@ static int combine_impl(zkmsm_ctx* ctx, const uint32_t* parts, bool on_device, s
   if (ex.err != cudaSuccess) return fail(ctx, ZKMSM_ERR_CUDA, "combine: %s", cudaGetErrorString(ex.err));
   ctx->pending = 1;
   ctx->pending_words = C::AFF_LIMBS;
+  if (enqueue_only) return ZKMSM_OK;
   return msm_result_impl(ctx, C::AFF_LIMBS, out_xy, out_is_inf);
 }
 extern "C" int zkmsm_g1_combine(zkmsm_ctx* ctx, const uint32_t* parts, size_t k, uint32_t* out, int* inf) {
@@ -703,6 +707,12 @@ extern "C" int zkmsm_g1_combine_device(zkmsm_ctx* ctx, const uint32_t* parts, si
 }
 extern "C" int zkmsm_g2_combine_device(zkmsm_ctx* ctx, const uint32_t* parts, size_t k, uint32_t* out, int* inf) {
   return combine_impl<G2>(ctx, parts, true, k, out, inf);
+}
+extern "C" int zkmsm_g1_combine_enqueue(zkmsm_ctx* ctx, const uint32_t* parts_device, size_t k) {
+  return combine_impl<G1>(ctx, parts_device, true, k, nullptr, nullptr, true);
+}
+extern "C" int zkmsm_g2_combine_enqueue(zkmsm_ctx* ctx, const uint32_t* parts_device, size_t k) {
+  return combine_impl<G2>(ctx, parts_device, true, k, nullptr, nullptr, true);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -920,6 +930,220 @@ extern "C" int zkmsm_fr_quotient(zkmsm_ctx* ctx, const uint32_t* u, const uint32
   CU(ctx, cudaStreamSynchronize(ctx->stream));
   *out_exact = flag ? 0 : 1;
   return ZKMSM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Groth16: the resident CRS and Prover::prove as three concurrent MSMs (see Groth16Scalars in fr_ops.cuh)
+struct zkmsm_crs {
+  zkmsm_ctx* owner;
+  zkmsm_ctx* lane[2];      // two more contexts on the owner's device: stream + workspace for the B and C MSMs
+  zkmsm_points* set_A;     // g1.xi ++ [alpha, delta]
+  zkmsm_points* set_B;     // g2.xi ++ [beta_2, delta_2]
+  zkmsm_points* set_C;     // g1.uvw_wit ++ g1.xt_by_delta ++ g1.xi ++ [alpha, beta, delta]
+  size_t n, n_wit, n_xt;
+  uint32_t* d_scalars;     // su (n + 2) | sv (n + 2) | sc (n_wit + n_xt + n + 3) | r | s, 8 words each
+  uint32_t* h_rs;          // pinned staging for r | s
+  cudaEvent_t ready, done[2];
+};
+
+static void concat_points(uint32_t* dst, uint8_t* dinf, size_t& pos, int words, const uint32_t* src, const uint8_t* inf, size_t n) {
+  if (n) memcpy(dst + pos * words, src, sizeof(uint32_t) * words * n);
+  if (dinf) { if (inf) memcpy(dinf + pos, inf, n); else memset(dinf + pos, 0, n); }
+  pos += n;
+}
+
+extern "C" int zkmsm_crs_free(zkmsm_ctx* ctx, zkmsm_crs* crs) {
+  if (!crs) return ZKMSM_ERR_INVALID_ARG;
+  zkmsm_ctx* o = crs->owner ? crs->owner : ctx;
+  if (o) cudaSetDevice(o->device);
+  for (int i = 0; i < 2; i++)
+    if (crs->lane[i]) { cudaStreamSynchronize(crs->lane[i]->stream); }
+  if (crs->set_A) zkmsm_points_free(o, crs->set_A);
+  if (crs->set_B) { if (crs->lane[0]) graphs_drop(crs->lane[0], crs->set_B->uid); zkmsm_points_free(o, crs->set_B); }
+  if (crs->set_C) { if (crs->lane[1]) graphs_drop(crs->lane[1], crs->set_C->uid); zkmsm_points_free(o, crs->set_C); }
+  for (int i = 0; i < 2; i++)
+    if (crs->lane[i]) zkmsm_destroy(crs->lane[i]);
+  if (crs->d_scalars) cudaFree(crs->d_scalars);
+  if (crs->h_rs) cudaFreeHost(crs->h_rs);
+  if (crs->ready) cudaEventDestroy(crs->ready);
+  for (int i = 0; i < 2; i++)
+    if (crs->done[i]) cudaEventDestroy(crs->done[i]);
+  delete crs;
+  return ZKMSM_OK;
+}
+
+extern "C" int zkmsm_crs_load(zkmsm_ctx* ctx, const zkmsm_crs_desc* d, unsigned flags, zkmsm_crs** out) {
+  if (!ctx || !d || !out) return fail(ctx, ZKMSM_ERR_INVALID_ARG, "null argument");
+  *out = nullptr;
+  if (!d->g1_alpha || !d->g1_beta || !d->g1_delta || !d->g2_beta || !d->g2_delta || (d->n && (!d->g1_xi || !d->g2_xi)) ||
+      (d->n_wit && !d->g1_uvw_wit) || (d->n_xt && !d->g1_xt_by_delta))
+    return fail(ctx, ZKMSM_ERR_INVALID_ARG, "CRS descriptor: null vector");
+  if (d->n_xt > d->n) return fail(ctx, ZKMSM_ERR_INVALID_ARG, "CRS descriptor: xt_by_delta longer than xi");
+  CU(ctx, cudaSetDevice(ctx->device));
+  zkmsm_crs* crs = new (std::nothrow) zkmsm_crs();
+  if (!crs) return fail(ctx, ZKMSM_ERR_NOMEM, "host allocation");
+  memset(crs, 0, sizeof(*crs));
+  crs->owner = ctx;
+  crs->n = d->n; crs->n_wit = d->n_wit; crs->n_xt = d->n_xt;
+  int rc = ZKMSM_OK;
+  const size_t nA = d->n + 2, nC = d->n_wit + d->n_xt + d->n + 3;
+  const bool any_inf = d->g1_xi_inf || d->g1_uvw_wit_inf || d->g1_xt_by_delta_inf || d->g2_xi_inf;
+  uint32_t* buf = (uint32_t*)malloc(sizeof(uint32_t) * 48 * (nC > nA ? nC : nA));
+  uint8_t* binf = any_inf ? (uint8_t*)malloc(nC > nA ? nC : nA) : nullptr;
+  if (!buf || (any_inf && !binf)) rc = fail(ctx, ZKMSM_ERR_NOMEM, "host allocation");
+  size_t pos;
+  if (!rc) {
+    pos = 0;
+    concat_points(buf, binf, pos, 24, d->g1_xi, d->g1_xi_inf, d->n);
+    concat_points(buf, binf, pos, 24, d->g1_alpha, nullptr, 1);
+    concat_points(buf, binf, pos, 24, d->g1_delta, nullptr, 1);
+    rc = load_points_impl<G1>(ctx, buf, binf, nA, flags, 1, &crs->set_A);
+  }
+  if (!rc) {
+    pos = 0;
+    concat_points(buf, binf, pos, 48, d->g2_xi, d->g2_xi_inf, d->n);
+    concat_points(buf, binf, pos, 48, d->g2_beta, nullptr, 1);
+    concat_points(buf, binf, pos, 48, d->g2_delta, nullptr, 1);
+    rc = load_points_impl<G2>(ctx, buf, binf, nA, flags, 2, &crs->set_B);
+  }
+  if (!rc) {
+    pos = 0;
+    concat_points(buf, binf, pos, 24, d->g1_uvw_wit, d->g1_uvw_wit_inf, d->n_wit);
+    concat_points(buf, binf, pos, 24, d->g1_xt_by_delta, d->g1_xt_by_delta_inf, d->n_xt);
+    concat_points(buf, binf, pos, 24, d->g1_xi, d->g1_xi_inf, d->n);
+    concat_points(buf, binf, pos, 24, d->g1_alpha, nullptr, 1);
+    concat_points(buf, binf, pos, 24, d->g1_beta, nullptr, 1);
+    concat_points(buf, binf, pos, 24, d->g1_delta, nullptr, 1);
+    rc = load_points_impl<G1>(ctx, buf, binf, nC, flags, 1, &crs->set_C);
+  }
+  free(buf);
+  free(binf);
+  if (!rc && (zkmsm_create(ctx->device, &crs->lane[0]) || zkmsm_create(ctx->device, &crs->lane[1])))
+    rc = fail(ctx, ZKMSM_ERR_CUDA, "could not create the prover's extra streams");
+  if (!rc) {
+    cudaSetDevice(ctx->device);
+    const size_t words = 8 * (2 * nA + nC + 2);
+    if (cudaMalloc(&crs->d_scalars, sizeof(uint32_t) * words) != cudaSuccess || cudaMallocHost(&crs->h_rs, 64) != cudaSuccess ||
+        cudaEventCreateWithFlags(&crs->ready, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&crs->done[0], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&crs->done[1], cudaEventDisableTiming) != cudaSuccess) {
+      cudaGetLastError();
+      rc = fail(ctx, ZKMSM_ERR_NOMEM, "prover scalar buffers");
+    }
+  }
+  if (rc) { zkmsm_crs_free(ctx, crs); return rc; }
+  for (int i = 0; i < 2; i++) { crs->lane[i]->tune = ctx->tune; crs->lane[i]->window_override = ctx->window_override; }
+  *out = crs;
+  return ZKMSM_OK;
+}
+
+extern "C" int zkmsm_crs_sizes(const zkmsm_crs* crs, size_t* n, size_t* n_wit, size_t* n_xt) {
+  if (!crs) return ZKMSM_ERR_INVALID_ARG;
+  if (n) *n = crs->n;
+  if (n_wit) *n_wit = crs->n_wit;
+  if (n_xt) *n_xt = crs->n_xt;
+  return ZKMSM_OK;
+}
+
+// copies the four coefficient vectors into place, fills the derived scalars and enqueues the three MSMs on three
+// streams; rank/world as in zkmsm_g1_msm_partial_range.  The results stay in the three contexts' result blocks.
+static int groth16_enqueue(zkmsm_ctx* ctx, zkmsm_crs* crs, const uint32_t* u, const uint32_t* v, const uint32_t* h,
+                           const uint32_t* wit, const uint32_t* r, const uint32_t* s, bool want_affine, uint32_t rank, uint32_t world) {
+  if (!ctx || !crs || !r || !s || (crs->n && (!u || !v)) || (crs->n_xt && !h) || (crs->n_wit && !wit))
+    return fail(ctx, ZKMSM_ERR_INVALID_ARG, "null argument");
+  if (crs->owner != ctx) return fail(ctx, ZKMSM_ERR_INVALID_ARG, "the CRS belongs to another context");
+  CU(ctx, cudaSetDevice(ctx->device));
+  const size_t n = crs->n, nA = n + 2, nC = crs->n_wit + crs->n_xt + n + 3;
+  uint32_t* su = crs->d_scalars;
+  uint32_t* sv = su + 8 * nA;
+  uint32_t* sc = sv + 8 * nA;
+  uint32_t* d_rs = sc + 8 * nC;
+  cudaStream_t st = ctx->stream;
+  // the previous proof's B and C MSMs read sv / sc on their own streams: wait for them before overwriting
+  CU(ctx, cudaStreamWaitEvent(st, crs->done[0], 0));
+  CU(ctx, cudaStreamWaitEvent(st, crs->done[1], 0));
+  memcpy(crs->h_rs, r, 32);
+  memcpy(crs->h_rs + 8, s, 32);
+  const size_t row = sizeof(uint32_t) * 8;
+  if (n) {
+    CU(ctx, cudaMemcpyAsync(su, u, row * n, cudaMemcpyHostToDevice, st));
+    CU(ctx, cudaMemcpyAsync(sv, v, row * n, cudaMemcpyHostToDevice, st));
+  }
+  if (crs->n_wit) CU(ctx, cudaMemcpyAsync(sc, wit, row * crs->n_wit, cudaMemcpyHostToDevice, st));
+  if (crs->n_xt) CU(ctx, cudaMemcpyAsync(sc + 8 * crs->n_wit, h, row * crs->n_xt, cudaMemcpyHostToDevice, st));
+  CU(ctx, cudaMemcpyAsync(d_rs, crs->h_rs, 64, cudaMemcpyHostToDevice, st));
+  CU(ctx, cudaMemsetAsync(&ctx->d_res->aux_err, 0, sizeof(uint32_t), st));
+  CudaExec ex(st);
+  ex.template launch<Groth16Scalars>((uint32_t)n + 1, (uint32_t)n, (const uint32_t*)d_rs, su, sv, sc + 8 * (crs->n_wit + crs->n_xt),
+                                     &ctx->d_res->aux_err);
+  if (ex.err != cudaSuccess) return fail(ctx, ZKMSM_ERR_CUDA, "groth16 scalars: %s", cudaGetErrorString(ex.err));
+  CU(ctx, cudaEventRecord(crs->ready, st));
+  int rc;
+  zkmsm_ctx* cb = crs->lane[0];
+  zkmsm_ctx* cc = crs->lane[1];
+  CU(ctx, cudaStreamWaitEvent(cb->stream, crs->ready, 0));
+  CU(ctx, cudaStreamWaitEvent(cc->stream, crs->ready, 0));
+  // the G2 MSM is the longest: first in the queue
+  if ((rc = msm_enqueue_impl<G2>(cb, crs->set_B, sv, nA, 2, want_affine, nullptr, rank, world))) { strcpy(ctx->err, cb->err); return rc; }
+  CU(ctx, cudaEventRecord(crs->done[0], cb->stream));
+  if ((rc = msm_enqueue_impl<G1>(cc, crs->set_C, sc, nC, 1, want_affine, nullptr, rank, world))) { strcpy(ctx->err, cc->err); return rc; }
+  CU(ctx, cudaEventRecord(crs->done[1], cc->stream));
+  if ((rc = msm_enqueue_impl<G1>(ctx, crs->set_A, su, nA, 1, want_affine, nullptr, rank, world))) return rc;
+  return ZKMSM_OK;
+}
+
+// waits for the three MSMs; the result blocks are then in the three contexts' pinned mirrors
+static int groth16_collect(zkmsm_ctx* ctx, zkmsm_crs* crs) {
+  int rc = msm_collect(ctx);
+  int rb = msm_collect(crs->lane[0]), rcc = msm_collect(crs->lane[1]);
+  if (!rc && rb) { strcpy(ctx->err, crs->lane[0]->err); rc = rb; }
+  if (!rc && rcc) { strcpy(ctx->err, crs->lane[1]->err); rc = rcc; }
+  if (!rc && ctx->h_res->aux_err) rc = fail(ctx, ZKMSM_ERR_SCALAR_RANGE, "r or s is not a field element (>= r)");
+  return rc;
+}
+
+extern "C" int zkmsm_groth16_prove(zkmsm_ctx* ctx, zkmsm_crs* crs, const uint32_t* u, const uint32_t* v, const uint32_t* h,
+                                   const uint32_t* wit, const uint32_t* r, const uint32_t* s, uint32_t* proof_out, int* inf_out) {
+  if (!proof_out || !inf_out) return fail(ctx, ZKMSM_ERR_INVALID_ARG, "null output");
+  int rc = groth16_enqueue(ctx, crs, u, v, h, wit, r, s, true, 0, 1);
+  if (rc) return rc;
+  if ((rc = groth16_collect(ctx, crs))) return rc;
+  const ResultBlock* res[3] = {ctx->h_res, crs->lane[0]->h_res, crs->lane[1]->h_res};
+  const int words[3] = {24, 48, 24}, at[3] = {0, 24, 72};
+  for (int i = 0; i < 3; i++) {
+    inf_out[i] = res[i]->inf ? 1 : 0;
+    if (res[i]->inf) memset(proof_out + at[i], 0, sizeof(uint32_t) * words[i]);
+    else memcpy(proof_out + at[i], res[i]->affine, sizeof(uint32_t) * words[i]);
+  }
+  return ZKMSM_OK;
+}
+
+extern "C" int zkmsm_groth16_prove_partial(zkmsm_ctx* ctx, zkmsm_crs* crs, const uint32_t* u, const uint32_t* v, const uint32_t* h,
+                                           const uint32_t* wit, const uint32_t* r, const uint32_t* s, unsigned rank, unsigned world,
+                                           uint32_t* out_partials) {
+  if (!out_partials) return fail(ctx, ZKMSM_ERR_INVALID_ARG, "null output");
+  int rc = groth16_enqueue(ctx, crs, u, v, h, wit, r, s, false, rank, world);
+  if (rc) return rc;
+  if ((rc = groth16_collect(ctx, crs))) return rc;
+  memcpy(out_partials, ctx->h_res->xyzz, sizeof(uint32_t) * 48);
+  memcpy(out_partials + 48, crs->lane[0]->h_res->xyzz, sizeof(uint32_t) * 96);
+  memcpy(out_partials + 144, crs->lane[1]->h_res->xyzz, sizeof(uint32_t) * 48);
+  return ZKMSM_OK;
+}
+
+extern "C" int zkmsm_groth16_combine(zkmsm_ctx* ctx, const uint32_t* partials, size_t world, uint32_t* proof_out, int* inf_out) {
+  if (!ctx || !partials || !proof_out || !inf_out || world == 0 || world > 4096) return fail(ctx, ZKMSM_ERR_INVALID_ARG, "bad argument");
+  uint32_t* tmp = (uint32_t*)malloc(sizeof(uint32_t) * 96 * world);
+  if (!tmp) return fail(ctx, ZKMSM_ERR_NOMEM, "host allocation");
+  int rc = ZKMSM_OK;
+  const int words[3] = {48, 96, 48}, src[3] = {0, 48, 144}, at[3] = {0, 24, 72};
+  for (int i = 0; i < 3 && !rc; i++) {
+    for (size_t k = 0; k < world; k++) memcpy(tmp + k * words[i], partials + k * ZKMSM_GROTH16_PARTIAL_WORDS + src[i], sizeof(uint32_t) * words[i]);
+    rc = i == 1 ? combine_impl<G2>(ctx, tmp, false, world, proof_out + at[i], &inf_out[i])
+                : combine_impl<G1>(ctx, tmp, false, world, proof_out + at[i], &inf_out[i]);
+  }
+  free(tmp);
+  return rc;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -1,26 +1,27 @@
-"""Groth16 proof generation on the GPU: the five MSMs of `Prover::prove`
-(src/zk/w_trusted_setup/groth16/zktoolkit_based/prover.rs:96-147).
+"""Groth16 proof generation on the GPU: `Prover::prove`
+(src/zk/w_trusted_setup/groth16/zktoolkit_based/prover.rs:96-147) through zkmsm_groth16_prove.
 
 The reference evaluates, per wire i, `ui[i].eval_with_g1_hidings(xi) * a_i` and sums the results
 (prover.rs:108-117): (m+1) nested MSMs.  Because the group is commutative that equals ONE MSM with the
-aggregated coefficients  sum_i a_i * u_{i,j}  (the canonical affine result is
-identical).  The blinding terms are folded into the same MSMs by appending the single CRS points to
-the resident sets:
+aggregated coefficients  sum_i a_i * u_{i,j}  (the canonical affine result is identical).
+The library (csrc/zkmsm.cu, csrc/fr_ops.cuh Groth16Scalars) then runs three concurrent MSMs:
 
-    A    = alpha   + sum_j u_j [x^j]_1 + r delta        = MSM(xi_1 ++ [alpha_1, delta_1], u ++ [1, r])
-    B    = beta_2  + sum_j v_j [x^j]_2 + s delta_2      = MSM(xi_2 ++ [beta_2,  delta_2], v ++ [1, s])
-    B_g1 = beta_1  + sum_j v_j [x^j]_1 + s delta_1      = MSM(xi_1 ++ [beta_1,  delta_1], v ++ [1, s])
-    C    = sum_{i>l} a_i uvw_wit_i + sum_j h_j [x^j t/delta]_1 - (r s) delta_1   (one MSM)
-           + s A + r B_g1                                                          (one 2-term MSM)
+    A = alpha  + sum_j u_j [x^j]_1 + r delta           = MSM(xi_1 ++ [alpha_1, delta_1],  u ++ [1, r])
+    B = beta_2 + sum_j v_j [x^j]_2 + s delta_2         = MSM(xi_2 ++ [beta_2,  delta_2],  v ++ [1, s])
+    C = sum_{i>l} a_i uvw_wit_i + sum_j h_j [x^j t/delta]_1 + s A + r B_g1 - r s delta          (prover.rs:128-145)
+      = MSM(uvw_wit ++ xt_by_delta ++ xi_1 ++ [alpha_1, beta_1, delta_1],  wit ++ h ++ (s u + r v) ++ [s, r, r s])
 
-All scalar work here is exact integer arithmetic mod r on the host (the reference's Fr aggregation,
-qap.rs:99-109, is the next row of the scope table); every group operation runs in libzkmsm.so.
+(expand A and B_g1 = beta_1 + sum v_j [x^j]_1 + s delta_1), so B_g1 and the two 255-bit scalar multiplications
+s A, r B_g1 are never formed.  This module only marshals Python integers to the ABI's limb layout; every field
+and group operation runs in libzkmsm.so.
 """
+import ctypes
 from dataclasses import dataclass
 
 import numpy as np
 
-from .api import G1Point, G1Points, G2Point, G2Points, R, default_context, scalars_to_array
+from . import _lib as L
+from .api import G1Point, G2Point, R, default_context, scalars_to_array
 
 
 @dataclass
@@ -30,47 +31,74 @@ class Proof:  # proof.rs:7-11
     C: G1Point
 
 
+def _proof_from_limbs(out, inf):
+    return Proof(G1Point.from_limbs(out[:24], inf[0]), G2Point.from_limbs(out[24:72], inf[1]),
+                 G1Point.from_limbs(out[72:96], inf[2]))
+
+
 class DeviceCRS:
-    """CRS vectors of crs.rs:17-43 resident on one GPU, with the single points appended (see above)."""
+    """CRS vectors of crs.rs:17-43 resident on one GPU (zkmsm_crs_load).  in_subgroup=True asserts, unchecked, that
+    every CRS point has order r -- true for any CRS built as multiples of the generators (crs.rs:65-135); pass
+    False for points of unknown provenance (the device then assumes nothing, macros.rs:10-21)."""
 
     def __init__(self, g1_alpha, g1_beta, g1_delta, g1_xi, g1_uvw_wit, g1_xt_by_delta, g2_beta, g2_delta, g2_xi,
-                 precompute=True, ctx=None):
-        self.ctx = ctx or default_context()
-        self.n = len(g1_xi)
-        self.n_wit = len(g1_uvw_wit)
-        self.n_xt = len(g1_xt_by_delta)
-        self.g1_delta = g1_delta
-        mk1 = lambda pts: G1Points(pts, precompute=precompute, ctx=self.ctx, in_subgroup=True)  # CRS points have order r
-        self.set_A = mk1(list(g1_xi) + [g1_alpha, g1_delta])
-        self.set_Bg1 = mk1(list(g1_xi) + [g1_beta, g1_delta])
-        self.set_B = G2Points(list(g2_xi) + [g2_beta, g2_delta], precompute=precompute, ctx=self.ctx, in_subgroup=True)
-        self.set_C = mk1(list(g1_uvw_wit) + list(g1_xt_by_delta) + [g1_delta])
-
-    def contexts(self, k):
-        """k contexts on this CRS's device (the first is the CRS's own), created on first use"""
-        from .context import Context
-        pool = getattr(self, "_pool", None)
-        if pool is None:
-            pool = self._pool = [self.ctx]
-        while len(pool) < k:
-            pool.append(Context(self.ctx.device))
-        return pool[:k]
+                 precompute=True, ctx=None, in_subgroup=True):
+        p1 = lambda pts: G1Point.pack(list(pts))
+        xi, xi_inf = p1(g1_xi)
+        wit, wit_inf = p1(g1_uvw_wit)
+        xt, xt_inf = p1(g1_xt_by_delta)
+        xi2, xi2_inf = G2Point.pack(list(g2_xi))
+        for single in (g1_alpha, g1_beta, g1_delta, g2_beta, g2_delta):
+            if single.is_zero():
+                raise ValueError("alpha, beta, delta must not be AtInfinity")
+        self._load(dict(g1_alpha=g1_alpha.limbs(), g1_beta=g1_beta.limbs(), g1_delta=g1_delta.limbs(), g1_xi=xi,
+                        g1_uvw_wit=wit, g1_xt_by_delta=xt, g2_beta=g2_beta.limbs(), g2_delta=g2_delta.limbs(), g2_xi=xi2),
+                   dict(g1_xi=xi_inf, g1_uvw_wit=wit_inf, g1_xt_by_delta=xt_inf, g2_xi=xi2_inf), precompute, ctx, in_subgroup)
 
     @classmethod
-    def from_arrays(cls, arrs, precompute=True, ctx=None):
+    def from_arrays(cls, arrs, precompute=True, ctx=None, in_subgroup=True):
         """arrs: dict of canonical limb arrays (for large synthetic instances built on the device):
         g1_xi (n,24), g1_uvw_wit, g1_xt_by_delta, g2_xi (n,48), and single points g1_alpha, g1_beta,
         g1_delta (24,), g2_beta, g2_delta (48,)."""
         self = cls.__new__(cls)
-        self.ctx = ctx or default_context()
-        self.n, self.n_wit, self.n_xt = len(arrs["g1_xi"]), len(arrs["g1_uvw_wit"]), len(arrs["g1_xt_by_delta"])
-        self.g1_delta = G1Point.from_limbs(arrs["g1_delta"], False)
-        cat = lambda *a: np.concatenate([np.asarray(x, dtype=np.uint32).reshape(-1, np.asarray(a[0]).shape[-1]) for x in a])
-        self.set_A = G1Points.from_arrays(cat(arrs["g1_xi"], arrs["g1_alpha"], arrs["g1_delta"]), precompute=precompute, ctx=self.ctx, in_subgroup=True)
-        self.set_Bg1 = G1Points.from_arrays(cat(arrs["g1_xi"], arrs["g1_beta"], arrs["g1_delta"]), precompute=precompute, ctx=self.ctx, in_subgroup=True)
-        self.set_B = G2Points.from_arrays(cat(arrs["g2_xi"], arrs["g2_beta"], arrs["g2_delta"]), precompute=precompute, ctx=self.ctx, in_subgroup=True)
-        self.set_C = G1Points.from_arrays(cat(arrs["g1_uvw_wit"], arrs["g1_xt_by_delta"], arrs["g1_delta"]), precompute=precompute, ctx=self.ctx, in_subgroup=True)
+        self._load(arrs, {}, precompute, ctx, in_subgroup)
         return self
+
+    def _load(self, arrs, infs, precompute, ctx, in_subgroup):
+        self.ctx = ctx or default_context()
+        self.handle = None
+        keep = {}
+        d = L.CrsDesc()
+        for name, words in (("g1_alpha", 24), ("g1_beta", 24), ("g1_delta", 24), ("g1_xi", 24), ("g1_uvw_wit", 24),
+                            ("g1_xt_by_delta", 24), ("g2_beta", 48), ("g2_delta", 48), ("g2_xi", 48)):
+            a = np.ascontiguousarray(np.asarray(arrs[name], dtype=np.uint32).reshape(-1, words))
+            keep[name] = a
+            setattr(d, name, a.ctypes.data if a.size else None)
+        for name in ("g1_xi", "g1_uvw_wit", "g1_xt_by_delta", "g2_xi"):
+            f = infs.get(name)
+            if f is not None and np.any(f):
+                f = np.ascontiguousarray(f, dtype=np.uint8)
+                keep[name + "_inf"] = f
+                setattr(d, name + "_inf", f.ctypes.data)
+        self.n, self.n_wit, self.n_xt = len(keep["g1_xi"]), len(keep["g1_uvw_wit"]), len(keep["g1_xt_by_delta"])
+        assert len(keep["g2_xi"]) == self.n
+        d.n, d.n_wit, d.n_xt = self.n, self.n_wit, self.n_xt
+        self.g1_delta = G1Point.from_limbs(keep["g1_delta"][0], False)
+        flags = (L.PRECOMPUTE if precompute else 0) | (L.SUBGROUP if in_subgroup else 0)
+        h = ctypes.c_void_p()
+        self.ctx._check(self.ctx.lib.zkmsm_crs_load(self.ctx.h, ctypes.byref(d), flags, ctypes.byref(h)))
+        self.handle = h
+
+    def free(self):
+        if getattr(self, "handle", None) is not None and self.ctx.h:
+            self.ctx.lib.zkmsm_crs_free(self.ctx.h, self.handle)
+        self.handle = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
 
 
 def aggregate(polys, wires, ctx=None):
@@ -109,21 +137,22 @@ class Prover:
 
     def __init__(self, u_agg, v_agg, h, witness_wires):
         self.u, self.v, self.h, self.wit = u_agg, v_agg, h, witness_wires
-        self._limbs = {}   # scalar vectors marshalled once to the ABI layout (padding depends on the CRS)
+        self._limbs = {}   # (context id, CRS sizes) -> the four vectors marshalled once to the ABI layout, pinned
 
-    def _arr(self, ctx, name, parts, extra):
-        """scalar vector = concatenation of padded `parts` [(vec, n), ...] plus `extra` trailing slots that change
-        per proof; kept in pinned host memory so that only the trailing rows are rewritten for each proof"""
-        key = (name, tuple(n for _, n in parts), extra)
+    def _arrays(self, crs):
+        """u, v (n), h (n_xt), witness (n_wit) as canonical limb arrays in pinned host memory of the CRS's context
+        (keyed by that context: the memory is owned by it)"""
+        key = (id(crs.ctx), crs.n, crs.n_xt, crs.n_wit)
         if key not in self._limbs:
-            total = sum(n for _, n in parts) + extra
-            arr = ctx.pinned_array((total, 8))
-            pos = 0
-            for vec, n in parts:
-                arr[pos:pos + n] = scalars_to_array(_pad(vec, n))
-                pos += n
-            self._limbs[key] = arr
-        return self._limbs[key]
+            if len(self.wit) != crs.n_wit:
+                raise IndexError("witness length does not match crs.g1.uvw_wit")
+            out = []
+            for vec, n in ((self.u, crs.n), (self.v, crs.n), (self.h, crs.n_xt), (self.wit, crs.n_wit)):
+                arr = crs.ctx.pinned_array((max(n, 1), 8))
+                arr[:n] = scalars_to_array(_pad(vec, n))
+                out.append(arr)
+            self._limbs[key] = (crs.ctx, out)      # the context reference keeps the pinned memory alive
+        return self._limbs[key][1]
 
     @classmethod
     def from_per_wire(cls, ui, vi, h, wires, l):
@@ -139,29 +168,50 @@ class Prover:
         return cls(u, v, quotient(u, v, w, n, ctx), list(wires[l + 1:]))
 
     def prove(self, crs: DeviceCRS, r: int, s: int) -> Proof:
+        """Prover::prove (prover.rs:96-147) with the blinding scalars supplied by the caller"""
+        u, v, h, wit = self._arrays(crs)
+        rs = scalars_to_array([int(r) % R, int(s) % R])
+        out = np.zeros(96, dtype=np.uint32)
+        inf = (ctypes.c_int * 3)()
         ctx = crs.ctx
-        r, s = int(r) % R, int(s) % R
-        n = crs.n
-        su = self._arr(ctx, "u", [(self.u, n)], 2)
-        su[n:] = scalars_to_array([1, r])
-        sv = self._arr(ctx, "v", [(self.v, n)], 2)
-        sv[n:] = scalars_to_array([1, s])
-        if len(self.wit) != crs.n_wit:
-            raise IndexError("witness length does not match crs.g1.uvw_wit")
-        sc = self._arr(ctx, "c", [(self.wit, crs.n_wit), (self.h, crs.n_xt)], 1)
-        sc[crs.n_wit + crs.n_xt:] = scalars_to_array([(-(r * s)) % R])
-        # the four large MSMs are independent: one context (stream + workspace) each, all in flight at once, so
-        # the latency-bound reduction tail of one overlaps the accumulation of the others
-        cA, cB, cBg1, cC = crs.contexts(4)
-        cB.msm_begin(crs.set_B.set, sv)                                           # prover.rs:119 (G2, the longest)
-        cA.msm_begin(crs.set_A.set, su)                                           # :118
-        cBg1.msm_begin(crs.set_Bg1.set, sv)                                       # :120
-        cC.msm_begin(crs.set_C.set, sc)                                           # :128-133 and -(delta r) s
-        A = G1Point.from_limbs(*cA.msm_result(1))
-        B_g1 = G1Point.from_limbs(*cBg1.msm_result(1))
-        C_main = G1Point.from_limbs(*cC.msm_result(1))
-        B = G2Point.from_limbs(*cB.msm_result(2))
-        # s A + r B_g1 needs A and B_g1; it is a 2-term MSM, run once the device is idle again
-        xy, inf = G1Point.pack([A, B_g1])
-        C_blind = G1Point.from_limbs(*cA.msm_oneshot(1, xy, inf if inf.any() else None, scalars_to_array([s, r])))  # :137-138
-        return Proof(A, B, C_main + C_blind)
+        ctx._check(ctx.lib.zkmsm_groth16_prove(ctx.h, crs.handle, L.dptr(u), L.dptr(v), L.dptr(h), L.dptr(wit), L.dptr(rs[0:1]),
+                                               L.dptr(rs[1:2]), L.dptr(out), inf))
+        return _proof_from_limbs(out, inf)
+
+    def prove_partial(self, crs: DeviceCRS, r: int, s: int, rank: int, world: int):
+        """this device's 1/world share of the three MSMs (bucket-range split): a (192,) uint32 blob for
+        combine_partials (configs[4]: one proof over the GPUs of a box)"""
+        u, v, h, wit = self._arrays(crs)
+        rs = scalars_to_array([int(r) % R, int(s) % R])
+        out = np.zeros(L.GROTH16_PARTIAL_WORDS, dtype=np.uint32)
+        ctx = crs.ctx
+        ctx._check(ctx.lib.zkmsm_groth16_prove_partial(ctx.h, crs.handle, L.dptr(u), L.dptr(v), L.dptr(h), L.dptr(wit),
+                                                       L.dptr(rs[0:1]), L.dptr(rs[1:2]), rank, world, L.dptr(out)))
+        return out
+
+
+def combine_partials(partials, ctx=None) -> Proof:
+    """sum of the per-rank shares of prove_partial, in rank order (zkmsm_groth16_combine)"""
+    ctx = ctx or default_context()
+    parts = np.ascontiguousarray(np.asarray(partials, dtype=np.uint32).reshape(-1, L.GROTH16_PARTIAL_WORDS))
+    out = np.zeros(96, dtype=np.uint32)
+    inf = (ctypes.c_int * 3)()
+    ctx._check(ctx.lib.zkmsm_groth16_combine(ctx.h, L.dptr(parts), parts.shape[0], L.dptr(out), inf))
+    return _proof_from_limbs(out, inf)
+
+
+def prove_distributed(prover: Prover, crs: DeviceCRS, r: int, s: int) -> Proof:
+    """One proof over all ranks of the default torch.distributed group (one process per GPU, every rank holds the
+    CRS): each rank proves its share, ONE all-gather of 192 words per rank, every rank combines (rank order, so the
+    proof is identical everywhere and identical to Prover.prove on one GPU)."""
+    import torch
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(), dist.get_rank()
+    if world == 1:
+        return prover.prove(crs, r, s)
+    mine = prover.prove_partial(crs, r, s, rank, world)
+    dev = torch.device("cuda", crs.ctx.device) if dist.get_backend() == "nccl" else torch.device("cpu")
+    t = torch.from_numpy(mine.view(np.int32)).to(dev)
+    out = torch.empty(world * L.GROTH16_PARTIAL_WORDS, dtype=torch.int32, device=dev)
+    dist.all_gather_into_tensor(out, t)
+    return combine_partials(out.cpu().numpy().view(np.uint32), crs.ctx)
