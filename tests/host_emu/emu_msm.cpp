@@ -143,6 +143,12 @@ int emu_g1_msm_range(const uint32_t* xy, const uint32_t* scalars, uint32_t n, ui
   return err ? -3 : 0;
 }
 uint32_t emu_last_fallback() { return g_last_fallback; }
+// one rank's share under the bucket-range split, as the 48-word blob (zkmsm_g1_msm_partial_range)
+int emu_g1_msm_partial_range(const uint32_t* xy, const uint32_t* scalars, uint32_t n, uint32_t c, int half, uint32_t rank,
+                             uint32_t world, uint32_t* out_partial) {
+  uint32_t dummy[24], dinf;
+  return emu_msm<G1>(xy, nullptr, scalars, n, n, c, 1 | (half ? 2 : 0), 0, 0, dummy, &dinf, out_partial, rank, world);
+}
 // one rank's share: partial point as the opaque 48-word blob of the C ABI, and the combine step
 int emu_g1_msm_partial(const uint32_t* xy, const uint32_t* scalars, uint32_t n, uint32_t* out_partial) {
   if (n == 0) { memset(out_partial, 0, sizeof(XYZZ<Fp>)); return 0; }

@@ -28,17 +28,20 @@ def build_emu():
     return so
 
 
-def _worker(rank, world, port, so, xy, sc, n, ret):
+def _worker(rank, world, port, so, xy, sc, n, ret, split="points"):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     sharding = importlib.import_module("zk-toolkit_b200.sharding")
     lib = ctypes.CDLL(so)
     P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
-    lo, hi = sharding.shard_range(n, rank, world)
     part = np.zeros(48, dtype=np.uint32)
-    xs, ss = np.ascontiguousarray(xy[lo:hi]), np.ascontiguousarray(sc[lo:hi])
-    assert lib.emu_g1_msm_partial(P(xs), P(ss), hi - lo, P(part)) == 0
+    if split == "range":   # every rank: all terms, 1 / world of the bucket range (window 6, subgroup fold)
+        assert lib.emu_g1_msm_partial_range(P(xy), P(sc), n, 6, 1, rank, world, P(part)) == 0
+    else:
+        lo, hi = sharding.shard_range(n, rank, world)
+        xs, ss = np.ascontiguousarray(xy[lo:hi]), np.ascontiguousarray(sc[lo:hi])
+        assert lib.emu_g1_msm_partial(P(xs), P(ss), hi - lo, P(part)) == 0
     gathered = sharding.gather_partials(torch.from_numpy(part.view(np.int32)))
     assert gathered.shape == (world, 48)
     g = np.ascontiguousarray(gathered.numpy().view(np.uint32))
@@ -50,8 +53,8 @@ def _worker(rank, world, port, so, xy, sc, n, ret):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 3])
-def test_sharded_msm_over_gloo(world):
+@pytest.mark.parametrize("world,split", [(2, "points"), (3, "points"), (2, "range"), (4, "range")])
+def test_sharded_msm_over_gloo(world, split):
     so = build_emu()
     rnd = random.Random(100 + world)
     n = 37
@@ -64,7 +67,7 @@ def test_sharded_msm_over_gloo(world):
     port = 29500 + random.randrange(2000)
     with mp.Manager() as mgr:
         ret = mgr.dict()
-        mp.spawn(_worker, args=(world, port, so, xy, sc, n, ret), nprocs=world, join=True)
+        mp.spawn(_worker, args=(world, port, so, xy, sc, n, ret, split), nprocs=world, join=True)
         results = [ret[r] for r in range(world)]
     for out, inf in results:
         assert U.g1_from_array(np.array(out, dtype=np.uint32), inf) == exp

@@ -393,7 +393,10 @@ static int msm_enqueue_impl(zkmsm_ctx* ctx, const zkmsm_points* ps, const uint32
     if (d_partial_out) CU(ctx, cudaMemsetAsync(d_partial_out, 0, sizeof(XYZZ<F>), ctx->stream));
     return ZKMSM_OK;
   }
-  const MsmTuning& tune = ctx->tune;
+  MsmTuning tune = ctx->tune;
+  // G2: the one-launch bucket sums hold 96 + 48 words of points per thread and spill (888 B of stack); the chunked
+  // accumulation + fix-up tree measures faster there (7.0 against 9.4 ms at 2^18), so it stays the G2 path
+  if (curve != 1 && tune.acc_G == 0) tune.no_bucket_acc = 1;
   unsigned c = ps->precomp ? ps->c : (ctx->window_override ? ctx->window_override : msm_pick_c((uint32_t)n, false, ps->half));
   if (!msm_fits(n, c, ps->half))
     return fail(ctx, ZKMSM_ERR_INVALID_ARG, "%zu terms at window %u exceed 2^32 sorted pairs; use a wider window", n, c);
