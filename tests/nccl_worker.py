@@ -27,6 +27,11 @@ def main():
     S = import_module("zk-toolkit_b200.synthetic")
     ctx = z.default_context()
     assert ctx.device == local
+    # the library's kernels and the NCCL exchange must be ordered on ONE stream (as bench.py does): the context's own
+    # stream is non-blocking with respect to torch's
+    stream = torch.cuda.Stream()
+    ctx.set_stream(stream.cuda_stream)
+    torch.cuda.set_stream(stream)
     n = 1 << 14
     rnd = random.Random(1234)                      # the same instance on every rank
     dlogs = [rnd.randrange(1, O.R) for _ in range(n)]
