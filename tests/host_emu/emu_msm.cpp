@@ -23,7 +23,7 @@ struct HostExec {
   void zero(void* p, size_t bytes) { memset(p, 0, bytes); }
   template <class C> void accumulate_buckets(const MsmPlan& p, const uint32_t* offsets, const Entry* entries,
                                              const Affine<typename C::F>* points, uint32_t direct,
-                                             XYZZ<typename C::F>* bucket_sums, uint32_t* big) {
+                                             XYZZ<typename C::F>* bucket_sums, XYZZ<typename C::F>*, uint32_t* big) {
     launch<AccumulateBucketsRef<C>>(p.nb, p, offsets, entries, points, direct, bucket_sums, big);
   }
   template <class C> uint32_t bucket_reduce(const MsmPlan& p, const uint32_t* offsets, const XYZZ<typename C::F>* buckets,

@@ -197,6 +197,12 @@ def test_emu_bucket_accumulation_and_its_fallback(lib, g1_set, monkeypatch):
     monkeypatch.setenv("ZKMSM_NO_BUCKET_ACC", "1")
     assert emu_g1(lib, pts, sc, c=5, precomp=1) == (0, exp)
     assert lib.emu_last_fallback() == 0
+    # chunked path as the main path (what G2 runs): FixupDirect adds a bucket's partial sums in one launch; a bucket
+    # of more than 64 chunks raises the flag and the FixupLevel tree takes over
+    assert emu_g1(lib, pts, sc, c=4, precomp=0, L=2) == (0, exp)
+    assert lib.emu_last_fallback() == 0
+    assert emu_g1(lib, many_pts, many_sc, c=8, precomp=0, L=2) == (0, U.expected_from_dlogs(O.G1_GEN, many_d, many_sc))
+    assert lib.emu_last_fallback() == 1
 
 
 def test_emu_g1_mul_base_matches_reference_scalar_mul(lib):

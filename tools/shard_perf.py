@@ -54,6 +54,8 @@ def main():
     for kv in filter(None, os.environ.get("OPTS", "").split(",")):
         k, v = kv.split("=")
         ctx.set_option(k, int(v))
+    if os.environ.get("WINDOW"):
+        ctx.set_window(int(os.environ["WINDOW"]))
     gen = (z.G1Point if GROUP == 1 else z.G2Point).g().limbs()
     words = 48 if GROUP == 1 else 96
     with torch.cuda.stream(stream):

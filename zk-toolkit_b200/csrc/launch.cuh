@@ -87,9 +87,11 @@ struct Fp2;
 struct Entry;
 template <class F> struct Affine;
 cudaError_t zk_bucket_acc_g1(cudaStream_t st, const MsmPlan& p, const uint32_t* offsets, const Entry* entries,
-                             const Affine<Mont<FqCfg>>* points, uint32_t direct, XYZZ<Mont<FqCfg>>* bucket_sums, uint32_t* big);
+                             const Affine<Mont<FqCfg>>* points, uint32_t direct, XYZZ<Mont<FqCfg>>* bucket_sums,
+                             XYZZ<Mont<FqCfg>>* lane_sums, uint32_t* big);
 cudaError_t zk_bucket_acc_g2(cudaStream_t st, const MsmPlan& p, const uint32_t* offsets, const Entry* entries,
-                             const Affine<Fp2>* points, uint32_t direct, XYZZ<Fp2>* bucket_sums, uint32_t* big);
+                             const Affine<Fp2>* points, uint32_t direct, XYZZ<Fp2>* bucket_sums, XYZZ<Fp2>* lane_sums, uint32_t* big);
+template <class C> struct BucketLaneSum;
 // per-device opt-in to > 48 KB of dynamic shared memory for every kernel that needs it (once per device, before the
 // first launch there; zkmsm_create calls it for the context's device)
 cudaError_t zk_opt_in_shared_memory_coop_g1();
@@ -163,15 +165,18 @@ struct CudaExec {
     launches += nlaunch;
     if (e != cudaSuccess) err = e;
   }
-  // bucket sums with acc_G lanes per bucket meeting in a shuffle tree (tu_g{1,2}_bacc.cu)
+  // bucket sums with acc_G lanes per bucket (tu_g{1,2}_bacc.cu): the lane sums meet in a shuffle tree (G1) or, for G2,
+  // are left in lane_sums and added per bucket by a second small launch
   template <class C, class P, class E, class A, class Pt>
   void accumulate_buckets(const P& p, const uint32_t* offsets, const E* entries, const A* points, uint32_t direct, Pt* bucket_sums,
-                          uint32_t* big) {
+                          Pt* lane_sums, uint32_t* big) {
     const uint32_t threads = p.nb * p.acc_G;
-    if (std::is_same<C, G1>::value)
-      timed("accumulate_buckets", threads, 1, [&] { return zk_bucket_acc_g1(st, p, offsets, entries, (const Affine<Mont<FqCfg>>*)points, direct, (XYZZ<Mont<FqCfg>>*)bucket_sums, big); });
-    else
-      timed("accumulate_buckets", threads, 1, [&] { return zk_bucket_acc_g2(st, p, offsets, entries, (const Affine<Fp2>*)points, direct, (XYZZ<Fp2>*)bucket_sums, big); });
+    if (std::is_same<C, G1>::value) {
+      timed("accumulate_buckets", threads, 1, [&] { return zk_bucket_acc_g1(st, p, offsets, entries, (const Affine<Mont<FqCfg>>*)points, direct, (XYZZ<Mont<FqCfg>>*)bucket_sums, (XYZZ<Mont<FqCfg>>*)lane_sums, big); });
+    } else {
+      timed("accumulate_buckets", threads, 1, [&] { return zk_bucket_acc_g2(st, p, offsets, entries, (const Affine<Fp2>*)points, direct, (XYZZ<Fp2>*)bucket_sums, (XYZZ<Fp2>*)lane_sums, big); });
+      if (p.acc_G > 1) launch<BucketLaneSum<C>>(p.nb, p, offsets, (const Pt*)lane_sums, bucket_sums, (const uint32_t*)big);
+    }
   }
   // stages 6 / 7 of the MSM: block-cooperative kernels (coop.cuh), per-thread bodies as the wide / fallback path.
   // bucket_reduce returns the row length it left per window (row pitch stays B / K): the cooperative kernel also

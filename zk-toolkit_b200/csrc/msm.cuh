@@ -299,6 +299,19 @@ template <class C> struct BucketAccLane {
     if (e - s > cap) return false;
     uint32_t i = s + g;
     if (i >= e) return true;
+    if (sizeof(F) > 48) {
+      // G2: accumulator (96 words) + one point (48) already fill the register file; the next point is only pulled
+      // towards the SM (no registers held) instead of being double-buffered
+      for (; i < e; i += G) {
+        if (i + G < e) {
+          if (direct) zk_prefetch(&points[i + G], sizeof(Affine<F>));
+          else zk_prefetch(&points[entries[i + G].val & 0x7fffffffu], sizeof(Affine<F>));
+        }
+        Affine<F> q = item(i, entries, points, direct);
+        xyzz_madd(acc, q);
+      }
+      return true;
+    }
     Affine<F> qn = item(i, entries, points, direct);
     for (; i < e; i += G) {
       Affine<F> q = qn;
@@ -306,6 +319,18 @@ template <class C> struct BucketAccLane {
       xyzz_madd(acc, q);
     }
     return true;
+  }
+};
+// second half of the G2 form of the launch: thread b adds the acc_G lane sums of bucket b (left in lane_sums[b G ..])
+template <class C> struct BucketLaneSum {
+  typedef typename C::F F;
+  static const char* name() { return "bucket_lane_sum"; }
+  static ZK_HD void run(uint32_t tid, MsmPlan p, const uint32_t* offsets, const XYZZ<F>* lane_sums, XYZZ<F>* bucket_sums,
+                        const uint32_t* big) {
+    if (tid >= p.nb || offsets[tid] == offsets[tid + 1] || *big) return;   // (a raised flag: the fallback redoes every bucket)
+    XYZZ<F> acc = lane_sums[(size_t)tid * p.acc_G];
+    for (uint32_t g = 1; g < p.acc_G; g++) { XYZZ<F> q = lane_sums[(size_t)tid * p.acc_G + g]; xyzz_add(acc, q); }
+    bucket_sums[tid] = acc;
   }
 };
 // the emulation's form of the launch: one logical thread per bucket runs the G lanes one after the other and
@@ -367,6 +392,34 @@ template <class C> struct FixupLevel {
       else { parts_out[tid] = acc; out_key = key; }
     }
     keys_out[tid] = out_key;
+  }
+};
+
+// The fix-up in ONE launch for the common case (what G2 uses, whose per-bucket kernel is register-bound): chunk t of
+// the chunked accumulation covers the sorted pairs [t L, (t + 1) L), so bucket b = [s, e) is met by the chunks
+// floor(s / L) .. floor((e - 1) / L); the first of them wrote the head of the sum to bucket_sums[b], each later one
+// left a partial sum that continues b.  Thread b adds those partials -- at most `cap / L` of them: BucketSizeCheck
+// raises *big beforehand when a bucket is larger than cap (skewed scalars), this launch then does nothing and the
+// balanced tree of FixupLevel launches, gated the other way, does the work.
+struct BucketSizeCheck {
+  static const char* name() { return "bucket_size_check"; }
+  static ZK_HD void run(uint32_t tid, uint32_t nb, const uint32_t* offsets, uint32_t cap, uint32_t* big) {
+    if (tid < nb && offsets[tid + 1] - offsets[tid] > cap) zk_atomic_or(big, 1u);
+  }
+};
+template <class C> struct FixupDirect {
+  typedef typename C::F F;
+  static const char* name() { return "fixup_direct"; }
+  static ZK_HD void run(uint32_t tid, uint32_t nb, uint32_t L, const uint32_t* offsets, const XYZZ<F>* partials,
+                        XYZZ<F>* bucket_sums, const uint32_t* big) {
+    if (tid >= nb || *big) return;
+    const uint32_t s = offsets[tid], e = offsets[tid + 1];
+    if (s == e) return;
+    const uint32_t t0 = s / L, t1 = (e - 1) / L;
+    if (t1 == t0) return;
+    XYZZ<F> acc = bucket_sums[tid];
+    for (uint32_t t = t0 + 1; t <= t1; t++) { XYZZ<F> q = partials[t]; xyzz_add_ilp(acc, q); }
+    bucket_sums[tid] = acc;
   }
 };
 
@@ -496,13 +549,71 @@ template <class C, bool FIRST> struct BatchedAddRound {
       }
       const size_t at = prefix_at(tid, T, o - beg);
       prefix[at] = prod;
+#if !defined(ZK_BATCH_NO_DSTORE)
       prefix[dstride + at] = d;
+#endif
       fmul(prod, prod, d);
       if (o + 1 < end) { cur = nxt; x1 = nx1; x2 = nx2; }
     }
     F inv;
     finv(inv, prod);
     // backward: inverse of each denominator, then the affine formulas.  cur is the last output's item, b its bucket.
+#if defined(ZK_BATCH_NO_DSTORE)
+    // Variant: the denominators are not kept; d = x2 - x1 is recomputed from the coordinates the way back loads
+    // anyway (one subtraction instead of 48 B written and read back per addition), and the running inverse is
+    // advanced at the END of an iteration, once the coordinates have arrived.
+    size_t at = prefix_at(tid, T, end - 1 - beg);
+    F pk = prefix[at];
+    if (end - 1 > beg) {
+      while (end - 2 < off_out[b]) b--;
+      find(loc, end - 2, b, off_in, off_out, entries);
+    }
+    for (uint32_t o = end; o-- > beg;) {
+      const Item me = cur;
+      F y1 = me.p1->y, y2 = me.p2->y, dinv, lam, t, d;
+      x1 = me.p1->x; x2 = me.p2->x;
+      fmul(dinv, inv, pk);
+      if (FIRST) {
+        fcneg(y1, y1, me.neg1);
+        fcneg(y2, y2, me.neg2);
+      }
+      int kind = 0;
+      const bool rare = (rare_lo & 1u) != 0;
+      rare_lo = (rare_lo >> 1) | (rare_hi << 63);
+      rare_hi >>= 1;
+      fsub(d, x2, x1);
+      if (rare) kind = classify_rare(d, me.has2, x1, y1, x2, y2);   // d becomes 1 or 2 y, as in the forward pass
+      if (o > beg) {   // next output: its prefix product ahead of its use
+        resolve(cur, loc, src);
+        at = prefix_at(tid, T, o - 1 - beg);
+        pk = prefix[at];
+        if (o - 1 > beg) {
+          while (o - 2 < off_out[b]) b--;
+          find(loc, o - 2, b, off_in, off_out, entries);
+        }
+      }
+      fsub(t, y2, y1);
+      if (kind == 1) { fmul(t, x1, x1); fdbl(lam, t); fadd(t, lam, t); x2 = x1; }   // tangent: 3 x^2 / 2 y
+      fmul(lam, t, dinv);
+      fmul(inv, inv, d);
+      Affine<F> r;
+      fmul(t, lam, lam);
+      fsub(t, t, x1);
+      fsub(r.x, t, x2);
+      fsub(t, x1, r.x);
+      fmul(t, lam, t);
+      fsub(r.y, t, y1);
+      if (kind >= 2) {
+        if (kind == 2) { r.x = x1; r.y = y1; }
+        else if (kind == 3) { r.x = x2; r.y = y2; }
+        else set_inf(r);
+      }
+      dst[o] = r;
+      if (entries_out) { Entry e; e.key = me.b; e.val = o; entries_out[o] = e; }
+    }
+  }
+};
+#else
     size_t at = prefix_at(tid, T, end - 1 - beg);
     F pk = prefix[at], d = prefix[dstride + at];
     if (end - 1 > beg) {
@@ -556,6 +667,7 @@ template <class C, bool FIRST> struct BatchedAddRound {
     }
   }
 };
+#endif
 
 // p = s * p for a small scalar (left-to-right double-and-add)
 template <class F> ZK_HD void xyzz_mul_small(XYZZ<F>& p, uint32_t s) {
@@ -921,6 +1033,7 @@ inline void msm_pick_bucket_acc(MsmPlan& p, uint64_t left, const MsmTuning& tune
   const uint64_t slots = p.acc_slots ? p.acc_slots : 32768;
   while (G < 32 && (uint64_t)p.nb * G * 2 <= slots && (uint64_t)G * 2 <= (avg + 1) / 2) G *= 2;
   if (tune.acc_G >= 1 && tune.acc_G <= 32 && (tune.acc_G & (tune.acc_G - 1)) == 0) G = (uint32_t)tune.acc_G;
+  while (G > 1 && (uint64_t)p.nb * G > p.acc_threads) G /= 2;   // lane sums may pass through the partial-sum buffer
   if (avg / G > 256) return;   // huge buckets without pre-reduction (narrow forced windows): chunks balance better
   p.acc_G = G;
   const uint64_t cap = 4 * avg + 32 * G;
@@ -1064,15 +1177,22 @@ void msm_launch(Exec& ex, const MsmPlan& p, const MsmTuning& tune, const MsmBuff
   // distribution-independent fallback, gated on the flag a bucket over the cap raises (launches that return at once
   // otherwise), or as the only path when no lane count fits
   msm_pick_bucket_acc(pa, expected, tune);
-  const uint32_t* gate = nullptr;
+  const uint32_t* gate = nullptr;   // gates the chunked accumulation (nullptr: always runs)
   if (pa.acc_G) {
-    ex.template accumulate_buckets<C>(pa, acc_offsets, acc_entries, acc_points, p.batch_rounds > 0 ? 1u : 0u, b.bucket_sums, b.big);
+    ex.template accumulate_buckets<C>(pa, acc_offsets, acc_entries, acc_points, p.batch_rounds > 0 ? 1u : 0u, b.bucket_sums,
+                                      b.partials, b.big);   // (the partial-sum buffer doubles as the lane-sum scratch)
     gate = b.big;
+  } else {
+    ex.template launch<BucketSizeCheck>(p.nb, p.nb, acc_offsets, 64u * pa.L, b.big);
   }
-  // (as a gated fallback on a capped grid: the launches that find the gate closed cost a few hundred blocks each)
-  const uint32_t cap_blocks = gate ? (p.acc_slots ? p.acc_slots / 128 : 296) : 0xffffffffu;
-  ex.template launch_capped<Accumulate<C>>(cap_blocks, pa.acc_threads, pa, acc_offsets, acc_entries, acc_points, b.bucket_sums,
-                                           b.partials, b.partial_keys, gate);
+  // (gated launches go out on a capped grid: those that find the gate closed cost a few hundred blocks each)
+  const uint32_t cap_blocks = p.acc_slots ? p.acc_slots / 128 : 296;
+  ex.template launch_capped<Accumulate<C>>(gate ? cap_blocks : 0xffffffffu, pa.acc_threads, pa, acc_offsets, acc_entries, acc_points,
+                                           b.bucket_sums, b.partials, b.partial_keys, gate);
+  if (!pa.acc_G) {   // chunked path as the main path: one-launch fix-up unless a bucket is over the cap
+    ex.template launch<FixupDirect<C>>(p.nb, p.nb, pa.L, acc_offsets, (const XYZZ<F>*)b.partials, b.bucket_sums, (const uint32_t*)b.big);
+    gate = b.big;    // the tree below runs only when FixupDirect stood back
+  }
   {  // fix-up tree over the per-chunk partial sums: level l reads region l, writes region l+1
     uint32_t count = pa.acc_threads, level = 0;
     XYZZ<F>* pin = b.partials;

@@ -5,3 +5,4 @@
 #include "msm.cuh"
 ZK_INSTANTIATE_KERNEL(zk::BucketReduce<zk::G2>);
 ZK_INSTANTIATE_KERNEL(zk::PairSum<zk::G2>);
+ZK_INSTANTIATE_KERNEL(zk::BucketLaneSum<zk::G2>);

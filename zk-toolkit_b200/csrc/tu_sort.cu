@@ -5,6 +5,7 @@
 #include "msm.cuh"
 ZK_INSTANTIATE_KERNEL(zk::RecodeCount);
 ZK_INSTANTIATE_KERNEL(zk::Scatter);
+ZK_INSTANTIATE_KERNEL(zk::BucketSizeCheck);
 
 namespace zk {
 

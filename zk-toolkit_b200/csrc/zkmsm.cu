@@ -394,8 +394,8 @@ static int msm_enqueue_impl(zkmsm_ctx* ctx, const zkmsm_points* ps, const uint32
     return ZKMSM_OK;
   }
   MsmTuning tune = ctx->tune;
-  // G2: the one-launch bucket sums hold 96 + 48 words of points per thread and spill (888 B of stack); the chunked
-  // accumulation + fix-up tree measures faster there (7.0 against 9.4 ms at 2^18), so it stays the G2 path
+  // G2 keeps the chunked accumulation (+ the one-launch fix-up): its per-bucket kernel is bound by registers and by
+  // the spread of the bucket sizes without pre-reduction rounds (measured 7.9 against 4.7 ms at 2^18)
   if (curve != 1 && tune.acc_G == 0) tune.no_bucket_acc = 1;
   unsigned c = ps->precomp ? ps->c : (ctx->window_override ? ctx->window_override : msm_pick_c((uint32_t)n, false, ps->half));
   if (!msm_fits(n, c, ps->half))
