@@ -1,1 +1,1 @@
-for w in 16 17; do for o in "" "acc_G=1" "acc_G=2" "no_bucket_acc=1"; do echo "#### WINDOW=$w OPTS=$o"; WINDOW=$w OPTS=$o GROUP=2 python tools/shard_perf.py 18 1,8 2>&1 | grep -E "^==|accumulate|fixup|bucket_|row_sum"; done; done
+for o in "L=24" "L=32" "L=48" "L=64"; do echo "#### OPTS=$o"; OPTS=$o GROUP=2 python tools/shard_perf.py 18 1,8 2>&1 | grep -E "^==|accumulate|fixup_d|bucket_red"; done

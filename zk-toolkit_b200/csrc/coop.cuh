@@ -193,7 +193,7 @@ template <class F> __device__ __forceinline__ void point_store_global(const Slot
   reinterpret_cast<F*>(g)[w] = S.load(A + w, l);
 }
 
-enum { S_RUN = 0, S_ACC = 4, S_Q = 8, S_BASE = 12, S_TMP = 16, S_TOTAL = S_TMP + T_COUNT };
+enum { S_RUN = 0, S_ACC = 4, S_Q = 8, S_BASE = 12, S_B2 = 16, S_B3 = 20, S_TMP = 24, S_TOTAL = S_TMP + T_COUNT };
 
 // Sum over the lanes of a block: lane 0's S_ACC += the S_ACC of lanes 1 .. cnt-1 (log2 levels; lane l takes lane
 // l + stride's point as its addend, only the lower half accumulates).  cnt is block-uniform; the caller has synced.
@@ -225,28 +225,61 @@ __global__ void __launch_bounds__(kThreads) bucket_reduce_kernel(MsmPlan p, cons
   const bool valid = chain < total;
   const uint32_t win = valid ? chain / chunks : 0, k = valid ? chain % chunks : 0;
   const size_t base = (size_t)win * p.B + (size_t)k * p.K;
-  point_set_inf(S, S_RUN);
-  point_set_inf(S, S_ACC);
-  __syncthreads();
-  for (int i = (int)p.K - 1; i >= 0; i--) {
+  // last bucket of the chain: run = acc = bucket (nothing is added to infinity)
+  {
+    const int i = (int)p.K - 1;
+    bool present = valid && offsets[base + i] != offsets[base + i + 1];
+    point_load_global(S, S_RUN, bucket_sums + base + i, present);
+    __syncthreads();
+    point_copy(S, S_ACC, S_RUN);
+    __syncthreads();
+  }
+  for (int i = (int)p.K - 2; i >= 0; i--) {
     bool present = valid && offsets[base + i] != offsets[base + i + 1];
     point_load_global(S, S_Q, bucket_sums + base + i, present);
     __syncthreads();
     point_add(S, fl, S_RUN, S_Q, S_TMP, false);
     point_add(S, fl, S_ACC, S_RUN, S_TMP, false);
   }
-  // run = (b_lo + k K) * run, MSB first over the bit length of the largest multiplier (uniform for the grid);
-  // b_lo (bucket-range split) is a multiple of B, hence of K
+  // run = (b_lo + k K) * run over the bit length of the largest multiplier (uniform for the grid), MSB first in
+  // 2-bit windows over the multiples 1x, 2x, 3x of run: half the additions of the bit-by-bit method.  b_lo
+  // (bucket-range split) is a multiple of B, hence of K, so the low log2(K) bits are zero: doublings only.
   const uint32_t s = p.b_lo + k * p.K;
-  int nbits = 32 - __clz((p.b_lo + (chunks - 1) * p.K) | 1u);
+  const int nbits = 32 - __clz((p.b_lo + (chunks - 1) * p.K) | 1u);
+  const int low = __ffs((int)p.K) - 1;
+  const int w4 = threadIdx.x >> 5;
   point_copy(S, S_BASE, S_RUN);
+  point_copy(S, S_B2, S_RUN);
   __syncthreads();
-  point_set_inf(S, S_RUN);
+  point_dbl(S, S_B2, S_TMP);
+  point_copy(S, S_B3, S_B2);
   __syncthreads();
-  const int low = __ffs((int)p.K) - 1;   // k K has at least this many trailing zero bits: no addition there
-  for (int b = nbits - 1; b >= 0; b--) {
-    if (b != nbits - 1) point_dbl(S, S_RUN, S_TMP);   // the first doubling would double infinity
-    if (b >= low) point_add(S, fl, S_RUN, S_BASE, S_TMP, ((s >> b) & 1u) == 0);
+  point_add(S, fl, S_B3, S_BASE, S_TMP, false);
+  auto window_to = [&](int dst, uint32_t w) {   // lane's dst = w * base (w in 0..3; 0 = infinity); warp w4 moves coordinate w4
+    F v;
+    if (w == 0) fset_zero(v);
+    else v = S.load((w == 1 ? S_BASE : (w == 2 ? S_B2 : S_B3)) + w4, l);
+    S.store(dst + w4, l, v);
+  };
+  int b = nbits;
+  if (b <= low) {
+    point_set_inf(S, S_RUN);   // multiplier 0 for every chain (a single chunk at b_lo = 0)
+    __syncthreads();
+  } else {
+    const int top = ((b - low) & 1) ? 1 : 2;   // odd number of positions: the top window is one bit
+    b -= top;
+    window_to(S_RUN, (s >> b) & (top == 1 ? 1u : 3u));
+    __syncthreads();
+    while (b > low) {
+      b -= 2;
+      point_dbl(S, S_RUN, S_TMP);
+      point_dbl(S, S_RUN, S_TMP);
+      const uint32_t w = (s >> b) & 3u;
+      window_to(S_Q, w);
+      __syncthreads();
+      point_add(S, fl, S_RUN, S_Q, S_TMP, w == 0);
+    }
+    for (int i = 0; i < low; i++) point_dbl(S, S_RUN, S_TMP);
   }
   point_add(S, fl, S_ACC, S_RUN, S_TMP, false);
   if (!tree) {

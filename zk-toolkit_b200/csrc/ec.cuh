@@ -126,6 +126,7 @@ template <class F> ZK_HD void xyzz_add(XYZZ<F>& acc, const XYZZ<F>& q) {
 // kernels after the accumulation, which run a handful of warps and are bound by the length of one
 // thread's dependency chain, not by multiplier throughput.  Same formulas, same results.
 template <class F> ZK_HD void xyzz_dbl_ilp(XYZZ<F>& p) {
+  if (sizeof(F) > 48) { xyzz_dbl(p); return; }   // Fq2: two products in lockstep do not fit the register file (measured 2x slower)
   if (is_inf(p)) return;
   F u, v, w, s, m, t, t2;
   fdbl(u, p.y);
@@ -142,6 +143,7 @@ template <class F> ZK_HD void xyzz_dbl_ilp(XYZZ<F>& p) {
 }
 
 template <class F> ZK_HD void xyzz_add_ilp(XYZZ<F>& acc, const XYZZ<F>& q) {
+  if (sizeof(F) > 48) { xyzz_add(acc, q); return; }
   if (is_inf(q)) return;
   if (is_inf(acc)) { acc = q; return; }
   F u1, s1, p, r, t, t2, pp, ppp, qq;

