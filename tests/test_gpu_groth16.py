@@ -191,3 +191,27 @@ def test_pinocchio_proof_identical_to_oracle_and_verifies(z):
     conv = {k: (g2_to_o(v) if isinstance(v, z.G2Point) else g1_to_o(v)) for k, v in got.items()}
     assert conv == want
     assert O.pinocchio_verify(conv, crs, op.io())
+
+
+def test_crs_new_matches_oracle_crs_and_proves(z):
+    """CRS::new (crs.rs:49-146) on the device for config 1: every CRS vector equals the oracle's, and the resident CRS
+    built from it gives the oracle's proof"""
+    from importlib import import_module
+    G = import_module("zk-toolkit_b200.groth16")
+    op = O.Prover(**O.CONFIG1)
+    td = dict(alpha=0x1111, beta=0x22223333, gamma=0x444455556666, delta=0x777788889999aaaa, x=0xbbbbccccddddeeeeffff)
+    ocrs = O.CRS(op, with_pairing=False, **td)
+    crs = G.CRS([p.coeffs for p in op.ui], [p.coeffs for p in op.vi], [p.coeffs for p in op.wi], op.l, op.n, **td)
+    for name in ("g1_xi", "g1_uvw_stmt", "g1_uvw_wit", "g1_xt_by_delta"):
+        want = [O.g1_to_limbs(p) for p in getattr(ocrs, name)]
+        assert getattr(crs, name).tolist() == want, name
+        assert not getattr(crs, name + "_inf").any()
+    assert crs.g2_xi.tolist() == [O.g2_to_limbs(p) for p in ocrs.g2_xi]
+    for name in ("g1_alpha", "g1_beta", "g1_delta"):
+        assert getattr(crs, name).tolist() == O.g1_to_limbs(getattr(ocrs, name)), name
+    for name in ("g2_beta", "g2_gamma", "g2_delta"):
+        assert getattr(crs, name).tolist() == O.g2_to_limbs(getattr(ocrs, name)), name
+    r, s = 0x5555, 0x7777
+    gp = G.Prover.from_qap([p.coeffs for p in op.ui], [p.coeffs for p in op.vi], [p.coeffs for p in op.wi], op.wires, op.l, op.n)
+    proof = gp.prove(crs.device(), r, s)
+    assert (g1_to_o(proof.A), g2_to_o(proof.B), g1_to_o(proof.C)) == op.prove(ocrs, r, s)

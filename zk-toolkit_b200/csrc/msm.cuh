@@ -505,6 +505,18 @@ template <class C, bool FIRST> struct BatchedAddRound {
   // Forward pass: d_o = denominator of output o, prefix_o = d_beg ... d_(o-1); both are stored (dstride apart) so
   // that the way back starts each output from two coalesced loads and fetches the four coordinates while the
   // first two multiplications run.
+  // In the FIRST round -- bound by its random gathers, not by the multiplier -- the denominators are NOT kept:
+  // d = x2 - x1 is recomputed from the coordinates the way back loads anyway (one subtraction instead of 48 B
+  // written and read back per addition) and the running inverse is advanced at the end of an iteration, once the
+  // coordinates have arrived.  Measured at 2^20: first round 2.70 -> 2.63 ms; the streamed rounds lose 3.5 % with
+  // the same change (their loads are coalesced and cheap), so they keep the stored denominators.
+#if defined(ZK_BATCH_NO_DSTORE)
+  static constexpr bool kNoDStore = true;
+#elif defined(ZK_BATCH_DSTORE)
+  static constexpr bool kNoDStore = false;
+#else
+  static constexpr bool kNoDStore = FIRST;
+#endif
   static ZK_HD void run(uint32_t tid, MsmPlan p, const uint32_t* off_in, const uint32_t* off_out, const Entry* entries,
                         const Affine<F>* src, Affine<F>* dst, F* prefix, size_t dstride, Entry* entries_out) {
     const uint32_t total = off_out[p.nb], T = p.batch_T;
@@ -549,125 +561,118 @@ template <class C, bool FIRST> struct BatchedAddRound {
       }
       const size_t at = prefix_at(tid, T, o - beg);
       prefix[at] = prod;
-#if !defined(ZK_BATCH_NO_DSTORE)
-      prefix[dstride + at] = d;
-#endif
+      if (!kNoDStore) prefix[dstride + at] = d;
       fmul(prod, prod, d);
       if (o + 1 < end) { cur = nxt; x1 = nx1; x2 = nx2; }
     }
     F inv;
     finv(inv, prod);
     // backward: inverse of each denominator, then the affine formulas.  cur is the last output's item, b its bucket.
-#if defined(ZK_BATCH_NO_DSTORE)
-    // Variant: the denominators are not kept; d = x2 - x1 is recomputed from the coordinates the way back loads
-    // anyway (one subtraction instead of 48 B written and read back per addition), and the running inverse is
-    // advanced at the END of an iteration, once the coordinates have arrived.
-    size_t at = prefix_at(tid, T, end - 1 - beg);
-    F pk = prefix[at];
-    if (end - 1 > beg) {
-      while (end - 2 < off_out[b]) b--;
-      find(loc, end - 2, b, off_in, off_out, entries);
-    }
-    for (uint32_t o = end; o-- > beg;) {
-      const Item me = cur;
-      F y1 = me.p1->y, y2 = me.p2->y, dinv, lam, t, d;
-      x1 = me.p1->x; x2 = me.p2->x;
-      fmul(dinv, inv, pk);
-      if (FIRST) {
-        fcneg(y1, y1, me.neg1);
-        fcneg(y2, y2, me.neg2);
+    if (kNoDStore) {
+      size_t at = prefix_at(tid, T, end - 1 - beg);
+      F pk = prefix[at];
+      if (end - 1 > beg) {
+        while (end - 2 < off_out[b]) b--;
+        find(loc, end - 2, b, off_in, off_out, entries);
       }
-      int kind = 0;
-      const bool rare = (rare_lo & 1u) != 0;
-      rare_lo = (rare_lo >> 1) | (rare_hi << 63);
-      rare_hi >>= 1;
-      fsub(d, x2, x1);
-      if (rare) kind = classify_rare(d, me.has2, x1, y1, x2, y2);   // d becomes 1 or 2 y, as in the forward pass
-      if (o > beg) {   // next output: its prefix product ahead of its use
-        resolve(cur, loc, src);
-        at = prefix_at(tid, T, o - 1 - beg);
-        pk = prefix[at];
-        if (o - 1 > beg) {
-          while (o - 2 < off_out[b]) b--;
-          find(loc, o - 2, b, off_in, off_out, entries);
+      for (uint32_t o = end; o-- > beg;) {
+        const Item me = cur;
+        F y1 = me.p1->y, y2 = me.p2->y, dinv, lam, t, d;
+        x1 = me.p1->x; x2 = me.p2->x;
+        fmul(dinv, inv, pk);
+        if (FIRST) {
+          fcneg(y1, y1, me.neg1);
+          fcneg(y2, y2, me.neg2);
         }
+        int kind = 0;
+        const bool rare = (rare_lo & 1u) != 0;
+        rare_lo = (rare_lo >> 1) | (rare_hi << 63);
+        rare_hi >>= 1;
+        fsub(d, x2, x1);
+        if (rare) kind = classify_rare(d, me.has2, x1, y1, x2, y2);   // d becomes 1 or 2 y, as in the forward pass
+        if (o > beg) {   // next output: its prefix product ahead of its use
+          resolve(cur, loc, src);
+          at = prefix_at(tid, T, o - 1 - beg);
+          pk = prefix[at];
+          if (o - 1 > beg) {
+            while (o - 2 < off_out[b]) b--;
+            find(loc, o - 2, b, off_in, off_out, entries);
+          }
+        }
+        fsub(t, y2, y1);
+        if (kind == 1) { fmul(t, x1, x1); fdbl(lam, t); fadd(t, lam, t); x2 = x1; }   // tangent: 3 x^2 / 2 y
+        fmul(lam, t, dinv);
+        fmul(inv, inv, d);
+        Affine<F> r;
+        fmul(t, lam, lam);
+        fsub(t, t, x1);
+        fsub(r.x, t, x2);
+        fsub(t, x1, r.x);
+        fmul(t, lam, t);
+        fsub(r.y, t, y1);
+        if (kind >= 2) {
+          if (kind == 2) { r.x = x1; r.y = y1; }
+          else if (kind == 3) { r.x = x2; r.y = y2; }
+          else set_inf(r);
+        }
+        dst[o] = r;
+        if (entries_out) { Entry e; e.key = me.b; e.val = o; entries_out[o] = e; }
       }
-      fsub(t, y2, y1);
-      if (kind == 1) { fmul(t, x1, x1); fdbl(lam, t); fadd(t, lam, t); x2 = x1; }   // tangent: 3 x^2 / 2 y
-      fmul(lam, t, dinv);
-      fmul(inv, inv, d);
-      Affine<F> r;
-      fmul(t, lam, lam);
-      fsub(t, t, x1);
-      fsub(r.x, t, x2);
-      fsub(t, x1, r.x);
-      fmul(t, lam, t);
-      fsub(r.y, t, y1);
-      if (kind >= 2) {
-        if (kind == 2) { r.x = x1; r.y = y1; }
-        else if (kind == 3) { r.x = x2; r.y = y2; }
-        else set_inf(r);
+    } else {
+      size_t at = prefix_at(tid, T, end - 1 - beg);
+      F pk = prefix[at], d = prefix[dstride + at];
+      if (end - 1 > beg) {
+        while (end - 2 < off_out[b]) b--;
+        find(loc, end - 2, b, off_in, off_out, entries);
       }
-      dst[o] = r;
-      if (entries_out) { Entry e; e.key = me.b; e.val = o; entries_out[o] = e; }
+      for (uint32_t o = end; o-- > beg;) {
+        const Item me = cur;
+        F y1 = me.p1->y, y2 = me.p2->y, dinv, lam, t;
+        x1 = me.p1->x; x2 = me.p2->x;
+        fmul(dinv, inv, pk);
+        fmul(inv, inv, d);
+        if (FIRST) {
+          fcneg(y1, y1, me.neg1);
+          fcneg(y2, y2, me.neg2);
+        }
+        int kind = 0;
+        const bool rare = (rare_lo & 1u) != 0;
+        rare_lo = (rare_lo >> 1) | (rare_hi << 63);
+        rare_hi >>= 1;
+        if (rare) {
+          fsub(t, x2, x1);   // the raw difference decides the case (the stored d is 1 or 2y here)
+          kind = classify_rare(t, me.has2, x1, y1, x2, y2);
+        }
+        if (o > beg) {   // next output: its prefix / denominator three multiplications ahead of their use
+          resolve(cur, loc, src);
+          at = prefix_at(tid, T, o - 1 - beg);
+          pk = prefix[at]; d = prefix[dstride + at];
+          if (o - 1 > beg) {
+            while (o - 2 < off_out[b]) b--;
+            find(loc, o - 2, b, off_in, off_out, entries);
+          }
+        }
+        fsub(t, y2, y1);
+        if (kind == 1) { fmul(t, x1, x1); fdbl(lam, t); fadd(t, lam, t); x2 = x1; }   // tangent: 3 x^2 / 2 y
+        fmul(lam, t, dinv);
+        Affine<F> r;
+        fmul(t, lam, lam);
+        fsub(t, t, x1);
+        fsub(r.x, t, x2);
+        fsub(t, x1, r.x);
+        fmul(t, lam, t);
+        fsub(r.y, t, y1);
+        if (kind >= 2) {
+          if (kind == 2) { r.x = x1; r.y = y1; }
+          else if (kind == 3) { r.x = x2; r.y = y2; }
+          else set_inf(r);
+        }
+        dst[o] = r;
+        if (entries_out) { Entry e; e.key = me.b; e.val = o; entries_out[o] = e; }
+      }
     }
   }
 };
-#else
-    size_t at = prefix_at(tid, T, end - 1 - beg);
-    F pk = prefix[at], d = prefix[dstride + at];
-    if (end - 1 > beg) {
-      while (end - 2 < off_out[b]) b--;
-      find(loc, end - 2, b, off_in, off_out, entries);
-    }
-    for (uint32_t o = end; o-- > beg;) {
-      const Item me = cur;
-      F y1 = me.p1->y, y2 = me.p2->y, dinv, lam, t;
-      x1 = me.p1->x; x2 = me.p2->x;
-      fmul(dinv, inv, pk);
-      fmul(inv, inv, d);
-      if (FIRST) {
-        fcneg(y1, y1, me.neg1);
-        fcneg(y2, y2, me.neg2);
-      }
-      int kind = 0;
-      const bool rare = (rare_lo & 1u) != 0;
-      rare_lo = (rare_lo >> 1) | (rare_hi << 63);
-      rare_hi >>= 1;
-      if (rare) {
-        fsub(t, x2, x1);   // the raw difference decides the case (the stored d is 1 or 2y here)
-        kind = classify_rare(t, me.has2, x1, y1, x2, y2);
-      }
-      if (o > beg) {   // next output: its prefix / denominator three multiplications ahead of their use
-        resolve(cur, loc, src);
-        at = prefix_at(tid, T, o - 1 - beg);
-        pk = prefix[at]; d = prefix[dstride + at];
-        if (o - 1 > beg) {
-          while (o - 2 < off_out[b]) b--;
-          find(loc, o - 2, b, off_in, off_out, entries);
-        }
-      }
-      fsub(t, y2, y1);
-      if (kind == 1) { fmul(t, x1, x1); fdbl(lam, t); fadd(t, lam, t); x2 = x1; }   // tangent: 3 x^2 / 2 y
-      fmul(lam, t, dinv);
-      Affine<F> r;
-      fmul(t, lam, lam);
-      fsub(t, t, x1);
-      fsub(r.x, t, x2);
-      fsub(t, x1, r.x);
-      fmul(t, lam, t);
-      fsub(r.y, t, y1);
-      if (kind >= 2) {
-        if (kind == 2) { r.x = x1; r.y = y1; }
-        else if (kind == 3) { r.x = x2; r.y = y2; }
-        else set_inf(r);
-      }
-      dst[o] = r;
-      if (entries_out) { Entry e; e.key = me.b; e.val = o; entries_out[o] = e; }
-    }
-  }
-};
-#endif
 
 // p = s * p for a small scalar (left-to-right double-and-add)
 template <class F> ZK_HD void xyzz_mul_small(XYZZ<F>& p, uint32_t s) {

@@ -215,3 +215,45 @@ def prove_distributed(prover: Prover, crs: DeviceCRS, r: int, s: int) -> Proof:
     out = torch.empty(world * L.GROTH16_PARTIAL_WORDS, dtype=torch.int32, device=dev)
     dist.all_gather_into_tensor(out, t)
     return combine_partials(out.cpu().numpy().view(np.uint32), crs.ctx)
+
+
+class CRS:
+    """CRS::new (groth16/zktoolkit_based/crs.rs:49-146) with the trapdoor supplied by the caller: the scalars of
+    crs.rs:65-116 are formed on the host (setup, exact Python integers mod r), every point is a device fixed-base
+    multiplication (`&G1Point * &Fq1` for a vector of scalars, zkmsm_g{1,2}_mul_base), and `device()` makes the
+    resident prover-side CRS.  Fields as the reference's: g1.alpha, beta, delta, xi, uvw_stmt, uvw_wit, xt_by_delta;
+    g2.beta, gamma, delta, xi (canonical limb arrays + AtInfinity flags)."""
+
+    def __init__(self, ui, vi, wi, l, n, alpha, beta, gamma, delta, x, ctx=None):
+        self.ctx = ctx or default_context()
+        ev = lambda poly: sum(int(c) * pow(x, j, R) for j, c in enumerate(poly)) % R       # Polynomial::eval_at
+        inv = lambda a: pow(a % R, -1, R)
+        m = len(ui) - 1
+
+        def uvw_div(lo, hi, div):                                                          # crs.rs:65-83
+            return [((beta * ev(ui[i]) + alpha * ev(vi[i]) + ev(wi[i])) * div) % R for i in range(lo, hi + 1)]
+
+        xp = [pow(x, j, R) for j in range(n)]                                              # crs.rs:88-102
+        t = 1
+        for k in range(1, n + 1):                                                          # QAP::build_t at x, qap.rs:115-135
+            t = t * ((x - k) % R) % R
+        g1 = lambda ks: self.ctx.mul_base(1, G1Point.g().limbs(), scalars_to_array([k % R for k in ks]))
+        g2 = lambda ks: self.ctx.mul_base(2, G2Point.g().limbs(), scalars_to_array([k % R for k in ks]))
+        self.n, self.l, self.m = n, l, m
+        self.g1_uvw_stmt, self.g1_uvw_stmt_inf = g1(uvw_div(0, l, inv(gamma)))             # crs.rs:85
+        self.g1_uvw_wit, self.g1_uvw_wit_inf = g1(uvw_div(l + 1, m, inv(delta)))           # crs.rs:86
+        self.g1_xi, self.g1_xi_inf = g1(xp)
+        self.g1_xt_by_delta, self.g1_xt_by_delta_inf = g1([p * t % R * inv(delta) % R for p in xp])   # crs.rs:104-116
+        singles1, _ = g1([alpha, beta, delta])
+        self.g1_alpha, self.g1_beta, self.g1_delta = singles1
+        self.g2_xi, self.g2_xi_inf = g2(xp)
+        singles2, _ = g2([beta, gamma, delta])
+        self.g2_beta, self.g2_gamma, self.g2_delta = singles2
+
+    def device(self, precompute=True) -> DeviceCRS:
+        arrs = {k: getattr(self, k) for k in ("g1_alpha", "g1_beta", "g1_delta", "g1_xi", "g1_uvw_wit", "g1_xt_by_delta",
+                                              "g2_beta", "g2_delta", "g2_xi")}
+        crs = DeviceCRS.__new__(DeviceCRS)
+        crs._load(arrs, {k: getattr(self, k + "_inf") for k in ("g1_xi", "g1_uvw_wit", "g1_xt_by_delta", "g2_xi")},
+                  precompute, self.ctx, True)
+        return crs
