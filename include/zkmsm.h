@@ -149,8 +149,9 @@ int zkmsm_g1_msm_partial_device(zkmsm_ctx* ctx, const zkmsm_points* pts, const u
 int zkmsm_g2_msm_partial_device(zkmsm_ctx* ctx, const zkmsm_points* pts, const uint32_t* scalars_device, size_t n,
                                 uint32_t* out_partial_device);
 /* The other way to split one MSM over `world` devices (a power of two): every device holds the WHOLE precomputed
- * point set and sees all n scalars, but owns only 1/world of the bucket range, so that sorted pairs AND buckets
- * (the latency-bound reduction) shrink by `world`.  The partials of ranks 0..world-1 add up to the MSM exactly as
+ * point set and sees all n scalars, but owns only 1/world of the buckets (stripes of consecutive buckets dealt out
+ * round-robin, so that every rank sees the same load), so that sorted pairs AND buckets (the latency-bound
+ * reduction) shrink by `world`.  The partials of ranks 0..world-1 add up to the MSM exactly as
  * above.  Needs a ZKMSM_PRECOMPUTE set; world = 1 is the plain partial. */
 int zkmsm_g1_msm_partial_range(zkmsm_ctx* ctx, const zkmsm_points* pts, const uint32_t* scalars, size_t n, unsigned rank,
                                unsigned world, uint32_t out_partial[ZKMSM_G1_PARTIAL_WORDS]);

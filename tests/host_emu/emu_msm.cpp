@@ -68,7 +68,7 @@ static int emu_msm(const uint32_t* xy, const uint8_t* inf, const uint32_t* scala
   uint32_t W = msm_windows(c, half);
   std::vector<Affine<F>> pts((size_t)npts * (precomp ? W : 1) + 1);
   ex.launch<LoadPoints<C>>(npts, npts, xy, inf, pts.data());
-  if (precomp) ex.launch<PrecomputeSlabs<C>>(npts, npts, npts, c, W, pts.data());
+  if (precomp) ex.launch<PrecomputeSlabs<C>>(npts, npts, npts, c, W, msm_wide_windows(c, W, half, true), pts.data());
   if (n == 0) { *out_inf = 1; memset(out_xy, 0, 4 * C::AFF_LIMBS); return 0; }
   const MsmTuning tune = MsmTuning::from_env();   // test infrastructure: the switches are read per call here
   MsmPlan p = msm_plan(n, c, precomp != 0, npts, half, false, 0, tune, rank, world);

@@ -112,6 +112,12 @@ def test_emu_g1_edge_cases(lib, g1_set):
     # largest accepted scalars
     sc = [(1 << 255) - 1, (1 << 255) - 19]
     assert emu_g1(lib, P[:2], sc) == (0, O.msm(P[:2], sc))
+    # the same on precomputed sets, whose windows are balanced (c and c - 1 bits, the top one never recoded):
+    # c = 10: 255 = 21 x 10 + 5 x 9; c = 7: 255 = 33 x 7 + 4 x 6
+    for cc in (10, 7, 4):
+        assert emu_g1(lib, P[:2], sc, precomp=1, c=cc) == (0, O.msm(P[:2], sc))
+        assert emu_g1(lib, P[:3], [(1 << 255) - 1, 1 << 254, (1 << 254) - 1], precomp=1, c=cc) == \
+            (0, O.msm(P[:3], [(1 << 255) - 1, 1 << 254, (1 << 254) - 1]))
     # r * P = AtInfinity
     assert emu_g1(lib, P[:1], [O.R]) == (0, O.INF)
     # subgroup point sets: scalars around (r-1)/2 and r-1 are folded to r - s with the point negated

@@ -64,7 +64,8 @@ def main():
         d_out = torch.zeros(words, dtype=torch.int32, device="cuda")
         stream.synchronize()
         for world in worlds:
-            cases = [("range", full, n, lambda: ctx.msm_partial_range_device(full, d_sc.data_ptr(), n, world - 1, world, d_out.data_ptr()))]
+            cases = [(f"range[rank {rk}]", full, n, (lambda rk=rk: ctx.msm_partial_range_device(full, d_sc.data_ptr(), n, rk, world, d_out.data_ptr())))
+                     for rk in sorted({0, world - 1})]
             shard = None
             if world > 1:
                 m = n // world

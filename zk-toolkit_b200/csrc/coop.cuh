@@ -210,7 +210,8 @@ template <class F> __device__ __forceinline__ void lane_tree(const Slots<F>& S, 
 
 template <class F> constexpr size_t smem_bytes() { return (size_t)S_TOTAL * (sizeof(F) / 4) * 32 * 4 + sizeof(Flags); }
 
-// 32 chains per block; chain (win, k): out = sum_{i<K} (b_lo + k K + i + 1) * bucket[win*B + k*K + i]   (as BucketReduce)
+// 32 chains per block; chain (win, k): out = sum_{i<K} (g + i + 1) * bucket[win*B + k*K + i], g = global index of the
+// chain's first bucket (as BucketReduce)
 template <class C>
 __global__ void __launch_bounds__(kThreads) bucket_reduce_kernel(MsmPlan p, const uint32_t* offsets,
                                                                  const XYZZ<typename C::F>* bucket_sums,
@@ -241,11 +242,12 @@ __global__ void __launch_bounds__(kThreads) bucket_reduce_kernel(MsmPlan p, cons
     point_add(S, fl, S_RUN, S_Q, S_TMP, false);
     point_add(S, fl, S_ACC, S_RUN, S_TMP, false);
   }
-  // run = (b_lo + k K) * run over the bit length of the largest multiplier (uniform for the grid), MSB first in
-  // 2-bit windows over the multiples 1x, 2x, 3x of run: half the additions of the bit-by-bit method.  b_lo
-  // (bucket-range split) is a multiple of B, hence of K, so the low log2(K) bits are zero: doublings only.
-  const uint32_t s = p.b_lo + k * p.K;
-  const int nbits = 32 - __clz((p.b_lo + (chunks - 1) * p.K) | 1u);
+  // run = g * run, g = global index of the chain's first bucket (msm_global_bucket: the chain's own k K without the
+  // bucket-range split), over the bit length of the largest multiplier of any rank (uniform for the grid), MSB first
+  // in 2-bit windows over the multiples 1x, 2x, 3x of run: half the additions of the bit-by-bit method.  g is a
+  // multiple of K, so the low log2(K) bits are zero: doublings only.
+  const uint32_t s = msm_global_bucket(p, k * p.K);
+  const int nbits = 32 - __clz((((uint32_t)p.B << p.world_log) - p.K) | 1u);
   const int low = __ffs((int)p.K) - 1;
   const int w4 = threadIdx.x >> 5;
   point_copy(S, S_BASE, S_RUN);
@@ -263,7 +265,7 @@ __global__ void __launch_bounds__(kThreads) bucket_reduce_kernel(MsmPlan p, cons
   };
   int b = nbits;
   if (b <= low) {
-    point_set_inf(S, S_RUN);   // multiplier 0 for every chain (a single chunk at b_lo = 0)
+    point_set_inf(S, S_RUN);   // multiplier 0 for every chain (a single chunk)
     __syncthreads();
   } else {
     const int top = ((b - low) & 1) ? 1 : 2;   // odd number of positions: the top window is one bit

@@ -67,6 +67,8 @@ struct MsmPlan {
   uint32_t n;          // terms
   uint32_t c;          // window bits
   uint32_t W;          // windows = floor(255 / c) + 1
+  uint32_t a;          // windows 0 .. a-1 are c bits wide, windows a .. W-1 are c-1 bits wide (a = W: all c bits, the top
+                       // one running out of scalar; precomputed sets balance the widths, see msm_wide_windows)
   uint32_t B;          // buckets per window = 2^(c-1)
   uint32_t nwin;       // bucket sets: W, or 1 with precomputed points
   uint32_t nb;         // total buckets = nwin * B
@@ -82,28 +84,49 @@ struct MsmPlan {
   uint32_t acc_slots;     // accumulate threads the device keeps resident at 2 blocks of 128 per SM (0 = unknown)
   uint32_t half;          // 1: point set is in the prime-order subgroup; scalars s > (r-1)/2 become r - s with
                           //    the point negated, so 254 bits are recoded and no carry-only top window exists
-  uint32_t b_lo;          // bucket-range split (precomputed sets): this plan owns the global buckets [b_lo, b_lo + B)
-                          //    of the 2^(c-1) and keeps only the digits that fall there; 0 with B = 2^(c-1) otherwise
+  // bucket-range split (precomputed sets) over 2^world_log ranks: the 2^(c-1) global buckets are cut into stripes of
+  // 2^stripe_log consecutive buckets dealt out round-robin, this plan owns the stripes = rank (mod world), B of the
+  // buckets in all, and keeps only the digits that fall there (striped, not contiguous: the balanced windows of a
+  // precomputed set load the lower half of the bucket range more than the upper one).  world_log = 0: everything.
+  uint32_t rank, world_log, stripe_log;
   uint32_t acc_G;         // > 0: bucket sums by AccumulateBuckets with acc_G lanes per bucket (no fix-up tree unless
                           //    a bucket holds more than acc_cap items); 0: chunked Accumulate + fix-up tree
   uint32_t acc_cap;       //    items per bucket above which the chunked fallback takes over
 };
 
+// global bucket (0-based magnitude - 1) -> this rank's local bucket, or false when another rank owns it
+ZK_HD bool msm_local_bucket(const MsmPlan& p, uint32_t mag, uint32_t* local) {
+  const uint32_t stripe = mag >> p.stripe_log;
+  if ((stripe & ((1u << p.world_log) - 1u)) != p.rank) return false;
+  *local = ((stripe >> p.world_log) << p.stripe_log) | (mag & ((1u << p.stripe_log) - 1u));
+  return true;
+}
+// local bucket -> global bucket
+ZK_HD uint32_t msm_global_bucket(const MsmPlan& p, uint32_t local) {
+  const uint32_t stripe = local >> p.stripe_log;
+  return (((stripe << p.world_log) | p.rank) << p.stripe_log) | (local & ((1u << p.stripe_log) - 1u));
+}
+
 // ---------------------------------------------------------------- signed-digit recoding
-// digits d_w in [-(2^(c-1) - 1), 2^(c-1)], sum_w d_w 2^(c w) = scalar (scalar < 2^255)
+// Window w covers `width(w)` bits from `pos(w)`: the first `a` windows are c bits wide, the others c - 1 (a = W: the
+// plain layout, every window c bits, the top one short because the scalar ends).  Digits d_w of a window of width
+// t lie in [-(2^(t-1) - 1), 2^(t-1)]; the LAST window is not recoded (nothing could take its carry): it holds its
+// bits plus the incoming carry, at most 2^(c-1), still a valid bucket.  sum_w d_w 2^pos(w) = scalar.
 struct Digits {
   const uint32_t* s;
-  uint32_t c, carry;
-  ZK_HD Digits(const uint32_t* scalar, uint32_t c_) : s(scalar), c(c_), carry(0) {}
+  uint32_t c, a, W, carry;
+  ZK_HD Digits(const uint32_t* scalar, uint32_t c_, uint32_t a_, uint32_t W_) : s(scalar), c(c_), a(a_), W(W_), carry(0) {}
   ZK_HD int32_t next(uint32_t w) {
-    uint32_t bit = w * c, limb = bit >> 5, sh = bit & 31;
+    const uint32_t t = w < a ? c : c - 1;                             // width
+    const uint32_t bit = w < a ? w * c : a * c + (w - a) * (c - 1);   // position
+    uint32_t limb = bit >> 5, sh = bit & 31;
     uint32_t v = 0;
     if (limb < SCALAR_LIMBS) {
       v = s[limb] >> sh;
-      if (sh + c > 32 && limb + 1 < SCALAR_LIMBS) v |= s[limb + 1] << (32 - sh);
+      if (sh + t > 32 && limb + 1 < SCALAR_LIMBS) v |= s[limb + 1] << (32 - sh);
     }
-    v = (v & ((1u << c) - 1)) + carry;
-    if (v > (1u << (c - 1))) { carry = 1; return (int32_t)v - (int32_t)(1u << c); }
+    v = (v & ((1u << t) - 1)) + carry;
+    if (w + 1 < W && v > (1u << (t - 1))) { carry = 1; return (int32_t)v - (int32_t)(1u << t); }
     carry = 0;
     return (int32_t)v;
   }
@@ -145,12 +168,12 @@ struct RecodeCount {
     uint32_t s[SCALAR_LIMBS];
     bool negate;
     if (!load_scalar(p, scalars, tid, s, &negate)) { zk_atomic_or(err, ERR_SCALAR_RANGE); return; }
-    Digits dg(s, p.c);
+    Digits dg(s, p.c, p.a, p.W);
     for (uint32_t w = 0; w < p.W; w++) {
       int32_t d = dg.next(w);
       if (d == 0) continue;
-      uint32_t mag = (uint32_t)(d < 0 ? -d : d) - 1 - p.b_lo;   // wraps below the range
-      if (mag >= p.B) continue;                                 // another rank's bucket (range split)
+      uint32_t mag;
+      if (!msm_local_bucket(p, (uint32_t)(d < 0 ? -d : d) - 1, &mag)) continue;   // another rank's bucket (range split)
       zk_atomic_add(&hist[(p.precomp ? 0 : w * p.B) + mag], 1u);
     }
   }
@@ -197,12 +220,12 @@ struct Scatter {
     uint32_t s[SCALAR_LIMBS];
     bool negate;
     if (!load_scalar(p, scalars, tid, s, &negate)) return;
-    Digits dg(s, p.c);
+    Digits dg(s, p.c, p.a, p.W);
     for (uint32_t w = 0; w < p.W; w++) {
       int32_t d = dg.next(w);
       if (d == 0) continue;
-      uint32_t neg = d < 0, mag = (uint32_t)(neg ? -d : d) - 1 - p.b_lo;
-      if (mag >= p.B) continue;
+      uint32_t neg = d < 0, mag;
+      if (!msm_local_bucket(p, (uint32_t)(neg ? -d : d) - 1, &mag)) continue;
       neg ^= negate ? 1u : 0u;
       uint32_t key = (p.precomp ? 0 : w * p.B) + mag;
       uint32_t idx = p.precomp ? w * p.stride + tid : tid;
@@ -686,7 +709,8 @@ template <class F> ZK_HD void xyzz_mul_small(XYZZ<F>& p, uint32_t s) {
   }
 }
 
-// thread (win, k): out = sum_{i<K} (b_lo + k K + i + 1) * bucket[win*B + k*K + i]; empty buckets were never written
+// thread (win, k): out = sum_{i<K} (g + i + 1) * bucket[win*B + k*K + i], g = global index of local bucket k K (a chain
+// never straddles a stripe: K divides the stripe length); empty buckets were never written
 template <class C> struct BucketReduce {
   typedef typename C::F F;
   static const char* name() { return "bucket_reduce"; }
@@ -702,7 +726,7 @@ template <class C> struct BucketReduce {
       if (offsets[base + i] != offsets[base + i + 1]) { XYZZ<F> q = bucket_sums[base + i]; xyzz_add_ilp(run, q); }
       xyzz_add_ilp(acc, run);
     }
-    xyzz_mul_small(run, p.b_lo + k * p.K);
+    xyzz_mul_small(run, msm_global_bucket(p, k * p.K));
     xyzz_add_ilp(acc, run);
     out[tid] = acc;
   }
@@ -818,18 +842,20 @@ template <class C> struct LoadPoints {
   }
 };
 
-// slab w = 2^c * slab (w-1), w = 1 .. W-1 (one thread per point walks all levels)
+// slab w = 2^width(w-1) * slab (w-1), w = 1 .. W-1, i.e. 2^pos(w) P (one thread per point walks all levels); the first
+// `wide` windows are c bits wide, the others c - 1 (Digits)
 template <class C> struct PrecomputeSlabs {
   typedef typename C::F F;
   static const char* name() { return "precompute_slabs"; }
-  static ZK_HD void run(uint32_t tid, uint32_t n, uint32_t stride, uint32_t c, uint32_t W, Affine<F>* pts) {
+  static ZK_HD void run(uint32_t tid, uint32_t n, uint32_t stride, uint32_t c, uint32_t W, uint32_t wide, Affine<F>* pts) {
     if (tid >= n) return;
     Affine<F> a = pts[tid];
     for (uint32_t w = 1; w < W; w++) {
+      const uint32_t t = w - 1 < wide ? c : c - 1;
       if (!is_inf(a)) {
         XYZZ<F> x;
         xyzz_mdbl(x, a);
-        for (uint32_t i = 1; i < c; i++) xyzz_dbl(x);
+        for (uint32_t i = 1; i < t; i++) xyzz_dbl(x);
         xyzz_to_affine(a, x);
       }
       pts[(size_t)w * stride + tid] = a;
@@ -934,6 +960,18 @@ struct MsmTuning {
 // windows needed for 255-bit scalars (254-bit after the half-range fold): the last one absorbs the recoding carry
 inline uint32_t msm_windows(uint32_t c, bool half = false) { return (half ? 254u : 255u) / c + 1; }
 
+// Wide (c-bit) windows of a set's layout.  A plain set keeps every window at c bits (the top one is whatever the
+// scalar leaves: 255 - (W - 1) c bits).  A precomputed set shares ONE bucket set between all windows, and a short top
+// window would pour its n digits into 2^(tb-1) of the 2^(c-1) buckets -- 4096 buckets with 4096 extra entries each
+// at 2^24 (c = 22, tb = 12): giant buckets for the per-bucket kernels and, under the bucket-range split, for rank 0.
+// Its windows are therefore balanced: `wide` of c bits, the rest of c - 1, together exactly the scalar's bits
+// (2^20: 14 x 17 + 16, the layout it always had; 2^24: 2 x 22 + 10 x 21).
+inline uint32_t msm_wide_windows(uint32_t c, uint32_t W, bool half, bool precomp) {
+  if (!precomp) return W;
+  const uint32_t bits = half ? 254u : 255u;
+  return bits > W * (c - 1) ? bits - W * (c - 1) : 0u;
+}
+
 // Window choice.  Cost model in mixed-add units, calibrated on B200 at n = 2^20 (profiles/): expected
 // sorted pairs (a full window contributes n, a top window of tb bits n (1 - 2^-tb), a carry-only top
 // window n / 2) plus a per-bucket charge for fix-up + reduction (11 per bucket, times W without a shared
@@ -968,12 +1006,16 @@ inline MsmPlan msm_plan(uint32_t n, uint32_t c, bool precomp, uint32_t stride, b
   p.c = c;
   p.half = half ? 1 : 0;
   p.W = msm_windows(c, half);
+  p.a = msm_wide_windows(c, p.W, half, precomp);
   p.B = 1u << (c - 1);
-  p.b_lo = 0;
+  p.rank = 0;
+  p.world_log = 0;
+  p.stripe_log = 0;
   p.precomp = precomp ? 1 : 0;
   if (precomp && world > 1 && (world & (world - 1)) == 0 && world <= p.B && rank < world) {
     p.B /= world;
-    p.b_lo = rank * p.B;
+    p.rank = rank;
+    while ((1u << p.world_log) < world) p.world_log++;
   }
   p.nwin = precomp ? 1 : p.W;
   p.nb = p.nwin * p.B;
@@ -1014,6 +1056,13 @@ inline MsmPlan msm_plan(uint32_t n, uint32_t c, bool precomp, uint32_t stride, b
   }
   if (tune.L >= 1 && tune.L <= 4096) p.L = (uint32_t)tune.L;   // tuning overrides
   if (tune.K >= 1 && (uint32_t)tune.K <= p.B && (tune.K & (tune.K - 1)) == 0) p.K = (uint32_t)tune.K;
+  // stripes of the bucket-range split: 32 reduction chains' worth of buckets (one cooperative block), never more
+  // than this rank's share
+  {
+    uint32_t stripe = 32 * p.K;
+    while (stripe > p.B) stripe /= 2;
+    while ((1u << p.stripe_log) < stripe) p.stripe_log++;
+  }
   p.acc_threads = (p.max_entries + p.L - 1) / p.L;
   if (p.acc_threads == 0) p.acc_threads = 1;
   return p;

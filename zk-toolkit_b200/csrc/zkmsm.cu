@@ -260,7 +260,7 @@ static int finish_point_set(zkmsm_ctx* ctx, zkmsm_points* ps, CudaExec& ex) {
   typedef typename C::F F;
   if (ps->precomp && ps->n > 0)
     ex.template launch<PrecomputeSlabs<C>>((uint32_t)ps->n, (uint32_t)ps->n, (uint32_t)ps->n, ps->c, ps->W,
-                                           (Affine<F>*)ps->d_pts);
+                                           msm_wide_windows(ps->c, ps->W, ps->half, true), (Affine<F>*)ps->d_pts);
   if (ex.err != cudaSuccess) return fail(ctx, ZKMSM_ERR_CUDA, "point set kernels: %s", cudaGetErrorString(ex.err));
   CU(ctx, cudaStreamSynchronize(ctx->stream));
   return ZKMSM_OK;
