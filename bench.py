@@ -153,6 +153,8 @@ def main():
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--g2-logn", type=int, default=18, help="size of the G2 MSM block (0 = skip)")
     ap.add_argument("--groth16-logn", type=int, default=18, help="constraints of the Groth16 block (0 = skip)")
+    ap.add_argument("--big-logn", type=int, default=24, help="size of the large-MSM block that runs when --gpus is 8 "
+                                                            "(BASELINE configs[3]: 2^24 across 8 B200; 0 = skip)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -482,6 +484,12 @@ def main():
     torch.cuda.empty_cache()
     g2_block = g2_bench(args, ctx, stream, rank, world, lp_peak) if args.g2_logn else None
     groth16_block = groth16_bench(args, ctx, rank, world) if args.groth16_logn else None
+    big_block = None
+    if args.big_logn and world == 8 and not args.no_precompute:
+        try:
+            big_block = big_msm_bench(args, ctx, stream, rank, world)
+        except z.ZkmsmError as e:          # e.g. not enough device memory next to another tenant: reported, not fatal
+            big_block = {"error": str(e)}
 
     if rank == 0:
         line = {
@@ -499,7 +507,7 @@ def main():
                                        "(oracle/zkt_oracle.py scalar_mul), before timing and again on the timed steps' result"},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,
             "gpu_launches": launches, "clocks": clocks,
-            "g2": g2_block, "groth16": groth16_block,
+            "g2": g2_block, "groth16": groth16_block, "msm_big": big_block,
         }
         if world > 1:
             line["multi_gpu"] = {"exchange": "one all-gather of 48 words per rank (NCCL), rank-order sum + affine on every rank",
@@ -574,6 +582,80 @@ def g2_bench(args, ctx, stream, rank, world, lp_peak):
             "result_check": "oracle closed form (sum s_i k_i) * g2"}
 
 
+def big_msm_bench(args, ctx, stream, rank, world):
+    """BASELINE configs[3]: G1 MSM of 2^big_logn terms across the 8 GPUs (bucket-range split: every rank holds the
+    whole precomputed table -- 19 GiB at 2^24 -- and all scalars).  Same protocol as the headline; points k_i g and
+    scalars from a counter-based generator (numpy) so that 2^24 of them take seconds, not minutes; checked against
+    the ORACLE through the closed form (sum s_i k_i) g."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import zk_toolkit_b200 as z
+    from importlib import import_module
+    sharding = import_module("zk-toolkit_b200.sharding")
+    n = 1 << args.big_logn
+
+    def limbs(seed):   # uniform 254-bit values (< r), reproducible on every rank
+        a = np.random.default_rng(seed).integers(0, 1 << 32, size=(n, 8), dtype=np.uint64).astype(np.uint32)
+        a[:, 7] &= 0x3FFFFFFF
+        return a
+
+    def to_int_sum_of_products(a, b):
+        """sum a_i b_i mod r from limb arrays, exact: 16 x 16 dot products of the 16-bit half-limb columns (each term
+        < 2^32, each sum of 2^24 terms < 2^56: exact in uint64), recombined with Python integers"""
+        a16 = np.ascontiguousarray(a.view(np.uint16).astype(np.uint64).T)     # (16, n)
+        b16 = np.ascontiguousarray(b.view(np.uint16).astype(np.uint64).T)
+        tot = 0
+        for j in range(16):
+            for k in range(16):
+                tot += int(np.dot(a16[j], b16[k])) << (16 * (j + k))
+        return tot % R
+
+    t0 = time.time()
+    dl, sc = limbs(args.seed + 21), limbs(args.seed + 22)
+    dl[:, 0] |= 1                                    # k_i != 0
+    with torch.cuda.stream(stream):
+        pts = ctx.points_from_scalars(1, z.G1Point.g().limbs(), dl, precompute=True, in_subgroup=True)
+        d_sc = torch.from_numpy(sc.view(np.int32)).cuda()
+        d_partial = torch.zeros(48, dtype=torch.int32, device="cuda")
+        stream.synchronize()
+        setup_s = time.time() - t0
+
+        def enqueue():
+            ctx.msm_partial_range_device(pts, d_sc.data_ptr(), n, rank, world, d_partial.data_ptr())
+            g = sharding.gather_partials(d_partial)
+            ctx.combine_enqueue(g.data_ptr(), world)
+            return g
+
+        for _ in range(3):
+            enqueue()
+            res = ctx.msm_result(1)
+        want = oracle_g1_multiple(to_int_sum_of_products(dl, sc)) if rank == 0 else None
+        if rank == 0 and not same_point(res, want):
+            raise SystemExit("2^%d MSM result does not match the oracle's closed form" % args.big_logn)
+        dist.barrier()
+        torch.cuda.synchronize()
+        steps = max(3, min(args.steps, 10))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        keep = [enqueue() for _ in range(steps)]
+        e1.record(stream)
+        e1.synchronize()
+        res2 = ctx.msm_result(1)
+        ms = e0.elapsed_time(e1) / steps
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        if res2[0].tolist() != res[0].tolist():
+            raise SystemExit("2^%d MSM: timed result differs" % args.big_logn)
+        info = pts.info()
+        pts.free()
+    return {"metric": "bls12_381_g1_msm_mpoints_per_s", "n": n, "n_gpus": world, "value": round(n / (ms * 1e-3) / 1e6, 3),
+            "unit": "Mpoints/s", "ms_per_step": round(ms, 4), "steps": steps, "window_bits": info["c"], "windows": info["windows"],
+            "split": "bucket range (striped), CRS tables replicated", "setup_s": round(setup_s, 1),
+            "result_check": "oracle closed form (sum s_i k_i) * g on rank 0"}
+
+
 def groth16_bench(args, ctx, rank, world):
     """Groth16 prove (Prover::prove, prover.rs:96-147) on the synthetic instance of BASELINE.json configs[4]
     (n constraints, n witness wires), end to end through the API: the coefficient vectors come
@@ -603,11 +685,14 @@ def groth16_bench(args, ctx, rank, world):
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    times = []
+    times, split = [], {}
     for _ in range(args.steps):
         t0 = time.perf_counter()
         p2 = prove()
         times.append((time.perf_counter() - t0) * 1e3)
+    if use_dist:
+        G.prove_distributed(inst["prover"], inst["crs"], r, s, timings=split)
+        split = {k: round(v, 3) for k, v in split.items()}
     if (p2.A, p2.B, p2.C) != (proof.A, proof.B, proof.C):
         raise SystemExit("Groth16 proofs differ between runs")
     ms = sum(times) / len(times)
@@ -619,7 +704,7 @@ def groth16_bench(args, ctx, rank, world):
     return {"metric": "groth16_prove_ms", "n_constraints": n, "n_witness": n, "prove_ms": round(ms, 3), "min_ms": round(min(times), 3),
             "unit": "ms", "higher_is_better": False, "n_gpus": world, "setup_s": round(setup_s, 1),
             "msms": "A: G1 n+2 | B: G2 n+2 | C: G1 3n+3 (s A + r B_g1 - r s delta folded into C's scalars), three streams",
-            "h2d_bytes_per_proof": 4 * n * 32, "d2h_bytes_per_proof": 96 * 4,
+            "h2d_bytes_per_proof": 4 * n * 32, "d2h_bytes_per_proof": 96 * 4, "phase_ms_one_proof": split or None,
             "api": "zkmsm_groth16_prove" if not use_dist else "zkmsm_groth16_prove_partial per rank + NCCL all-gather + zkmsm_groth16_combine",
             "result_check": "A, B, C equal their closed-form discrete logs times the generators, right-hand sides by the ORACLE"}
 

@@ -376,11 +376,11 @@ def test_launch_plan_policies(lib):
     assert policy(20, precomp=0)["rounds"] == 0                             # plain point sets: per-window buckets
     assert policy(20, s=0)["rounds"] == 0                                   # unknown device (CPU emulation)
     p20 = policy(20)
-    assert p20["c"] == 17 and p20["rounds"] == 4 and p20["coop"] == 1 and p20["K"] == 16
-    assert p20["G"] == 1 and p20["cap"] >= 64                               # ~15 items per bucket left: one lane each
-    # rounds continue while a round keeps every resident thread at >= 8 additions and >= 12 items per bucket remain
-    assert policy(19)["rounds"] == 3 and policy(22)["rounds"] >= 3
-    assert policy(18, c=16)["rounds"] == 3 and policy(18, c=17)["rounds"] == 2
+    assert p20["c"] == 17 and p20["rounds"] == 5 and p20["coop"] == 1 and p20["K"] == 16
+    assert p20["G"] == 1 and p20["cap"] >= 32                               # ~8 items per bucket left: one lane each
+    # rounds continue while a round keeps every resident thread at >= 8 additions and >= 6 items per bucket remain
+    assert policy(19)["rounds"] == 4 and policy(22)["rounds"] >= 4
+    assert policy(18, c=16)["rounds"] == 3 and policy(18, c=17)["rounds"] == 3
     # bucket-range split over 8 devices: an eighth of the buckets and of the expected pairs, several lanes per bucket
     p8 = policy(20, world=8)
     assert p8["nb"] == (1 << 16) // 8 and p8["rounds"] in (2, 3) and p8["G"] >= 4

@@ -937,6 +937,8 @@ struct MsmTuning {
   int no_graph = 0;        // ZKMSM_NO_GRAPH: launch kernel by kernel instead of replaying a captured CUDA graph
   int no_bucket_acc = 0;   // ZKMSM_NO_BUCKET_ACC: always the chunked accumulation + fix-up tree
   int acc_G = 0;           // ZKMSM_ACC_G: lanes per bucket of AccumulateBuckets (power of two <= 32)
+  int coop_max_chains = 0; // ZKMSM_COOP_MAX_CHAINS: most reduction chains the cooperative kernel takes (default 9472)
+  int min_left = 0;        // ZKMSM_MIN_LEFT: batched rounds stop at about this many items per bucket (default 6)
   static int env_int(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; }
   static MsmTuning from_env() {
     MsmTuning t;
@@ -953,6 +955,8 @@ struct MsmTuning {
     t.no_graph = getenv("ZKMSM_NO_GRAPH") ? 1 : 0;
     t.no_bucket_acc = getenv("ZKMSM_NO_BUCKET_ACC") ? 1 : 0;
     t.acc_G = env_int("ZKMSM_ACC_G", 0);
+    t.coop_max_chains = env_int("ZKMSM_COOP_MAX_CHAINS", 0);
+    t.min_left = env_int("ZKMSM_MIN_LEFT", 0);
     return t;
   }
 };
@@ -1052,7 +1056,8 @@ inline MsmPlan msm_plan(uint32_t n, uint32_t c, bool precomp, uint32_t stride, b
     // (2^19 buckets at K = 64: 256 blocks, 0.9 ms against 1.8 ms for the per-thread kernel at K = 32)
     uint32_t k = 2;
     while (k < 64 && (uint64_t)p.nwin * (p.B / k) > 4736) k *= 2;
-    if (k <= p.B && (uint64_t)p.nwin * (p.B / k) <= 2 * 4736) { p.K = k; p.coop = 1; }
+    const uint64_t coop_max = tune.coop_max_chains > 0 ? (uint64_t)tune.coop_max_chains : 2 * 4736;
+    if (k <= p.B && (uint64_t)p.nwin * (p.B / k) <= coop_max) { p.K = k; p.coop = 1; }
   }
   if (tune.L >= 1 && tune.L <= 4096) p.L = (uint32_t)tune.L;   // tuning overrides
   if (tune.K >= 1 && (uint32_t)tune.K <= p.B && (tune.K & (tune.K - 1)) == 0) p.K = (uint32_t)tune.K;
@@ -1113,14 +1118,16 @@ inline uint64_t msm_batch_slots(const MsmPlan& p, const MsmTuning& tune) {
 // profiles/): an affine addition sharing its inversion costs ~0.29 ns against 0.35 ns for the XYZZ mixed addition
 // while a round keeps every resident thread busy with >= 8 additions per inversion; a smaller round is bound by
 // the latency of its one inversion per thread (~40 us) and AccumulateBuckets is the better tool.  Rounds stop at
-// ~12 items per bucket.  The scratch (~250 bytes per pair) is capped.
+// ~6 items per bucket (measured: 2^22 20.6 -> 20.2 ms, 2^24 74.3 -> 72.8 ms against stopping at 12; 2^20 unchanged).
+// The scratch (~250 bytes per pair) is capped.
 inline uint32_t msm_default_batch_rounds(const MsmPlan& p, const MsmTuning& tune = MsmTuning()) {
   if (!p.precomp || !p.acc_slots) return 0;
   if ((uint64_t)p.max_entries / 2 * 250 > (40ull << 30)) return 0;
   const uint64_t expected = msm_expected_entries(p), per_bucket = expected / p.nb;
   const uint64_t min_adds = 8 * msm_batch_slots(p, tune);
   uint32_t r = 0;
-  while (r < 8 && (expected >> (r + 1)) >= min_adds && (per_bucket >> (r + 1)) >= 12) r++;
+  const uint64_t min_left = tune.min_left > 0 ? (uint64_t)tune.min_left : 6;
+  while (r < 8 && (expected >> (r + 1)) >= min_adds && (per_bucket >> (r + 1)) >= min_left) r++;
   return r < 2 ? 0 : r;
 }
 

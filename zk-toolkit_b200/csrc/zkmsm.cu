@@ -203,7 +203,8 @@ extern "C" int zkmsm_set_option(zkmsm_ctx* ctx, const char* name, long value) {
       {"batch_blocks", &MsmTuning::batch_blocks}, {"L", &MsmTuning::L}, {"K", &MsmTuning::K},
       {"no_wave_L", &MsmTuning::no_wave_L}, {"no_coop", &MsmTuning::no_coop}, {"ntt_no_fuse", &MsmTuning::ntt_no_fuse},
       {"quotient_schoolbook", &MsmTuning::quotient_schoolbook}, {"no_graph", &MsmTuning::no_graph},
-      {"no_bucket_acc", &MsmTuning::no_bucket_acc}, {"acc_G", &MsmTuning::acc_G}};
+      {"no_bucket_acc", &MsmTuning::no_bucket_acc}, {"acc_G", &MsmTuning::acc_G},
+      {"coop_max_chains", &MsmTuning::coop_max_chains}, {"min_left", &MsmTuning::min_left}};
   for (auto& t : table)
     if (strcmp(t.name, name) == 0) {
       ctx->tune.*(t.field) = (int)value;
