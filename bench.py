@@ -205,6 +205,7 @@ def main():
         h_sc = torch.from_numpy(sc_arr.view(np.int32)).pin_memory()
         d_sc = h_sc.to("cuda", non_blocking=True)
         d_partial = torch.zeros(48, dtype=torch.int32, device="cuda")
+        d_slice = torch.empty(max(1, n // world), 8, dtype=torch.int32, device="cuda") if world > 1 else None
         stream.synchronize()
 
         def enqueue_step():
@@ -228,7 +229,14 @@ def main():
             """through the public call with HOST scalars: H2D copy + MSM + D2H of the result"""
             if world == 1:
                 return ctx.msm_host_ptr(pts, h_sc.data_ptr(), n)
-            d_sc.copy_(h_sc, non_blocking=True)
+            if split == "range":
+                # every rank needs all scalars: each uploads 1/N of them and the slices are all-gathered over NVLink, so
+                # the vector crosses PCIe once per step, not once per GPU
+                per = n // world
+                d_slice.copy_(h_sc[rank * per:(rank + 1) * per], non_blocking=True)
+                dist.all_gather_into_tensor(d_sc.view(-1), d_slice.view(-1))
+            else:
+                d_sc.copy_(h_sc, non_blocking=True)
             enqueue_step()
             return fetch()
 
@@ -356,9 +364,10 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             e2e_s = float(t.item())
         e2e = {"value": round(n_total / e2e_s / 1e6, 3), "unit": "Mpoints/s", "ms_per_step": round(e2e_s * 1e3, 4),
-               "h2d_bytes_per_step": n * 32, "d2h_bytes_per_step": 24 * 4 + 8,
+               "h2d_bytes_per_step": (n // world if world > 1 and split == "range" else n) * 32, "d2h_bytes_per_step": 24 * 4 + 8,
                "api": "zkmsm_g1_msm(ctx, resident CRS points, host scalars) -> host affine point" if world == 1 else
-                      "per rank: H2D of its scalars, zkmsm_g1_msm_partial_*_device, NCCL all-gather, zkmsm_g1_combine_enqueue + result"}
+                      "per rank: H2D of 1/N of the scalars + NVLink all-gather of the slices (range split; all of its own under the points split), "
+                      "zkmsm_g1_msm_partial_*_device, NCCL all-gather of the partials, zkmsm_g1_combine_enqueue + result"}
         if world == 1:
             # the same steps issued through the asynchronous pair of calls on two contexts, so that the copy of step
             # k + 1 runs under the kernels of step k (what a prover with several MSMs per proof does);
@@ -704,7 +713,7 @@ def groth16_bench(args, ctx, rank, world):
     return {"metric": "groth16_prove_ms", "n_constraints": n, "n_witness": n, "prove_ms": round(ms, 3), "min_ms": round(min(times), 3),
             "unit": "ms", "higher_is_better": False, "n_gpus": world, "setup_s": round(setup_s, 1),
             "msms": "A: G1 n+2 | B: G2 n+2 | C: G1 3n+3 (s A + r B_g1 - r s delta folded into C's scalars), three streams",
-            "h2d_bytes_per_proof": 4 * n * 32, "d2h_bytes_per_proof": 96 * 4, "phase_ms_one_proof": split or None,
+            "h2d_bytes_per_proof": 4 * n * 32 // (world if use_dist else 1), "d2h_bytes_per_proof": 96 * 4, "phase_ms_one_proof": split or None,
             "api": "zkmsm_groth16_prove" if not use_dist else "zkmsm_groth16_prove_partial per rank + NCCL all-gather + zkmsm_groth16_combine",
             "result_check": "A, B, C equal their closed-form discrete logs times the generators, right-hand sides by the ORACLE"}
 

@@ -213,7 +213,8 @@ int zkmsm_fr_quotient(zkmsm_ctx* ctx, const uint32_t* u, const uint32_t* v, cons
  * AtInfinity flag each.  A, B and C are three MSMs running concurrently on three streams; C uses the identity
  *   s A + r B_g1 - r s delta = sum_j (s u_j + r v_j) [x^j]_1 + s alpha + r beta + r s delta
  * so that B_g1 (prover.rs:120) and the two scalar multiplications of prover.rs:137-138 are folded into its MSM.
- * All vectors: 8 words per element, canonical, < r.  flags as for zkmsm_*_load_points (a CRS is made of multiples
+ * All vectors: 8 words per element, canonical, < r, in host memory or already on the context's device (a
+ * multi-GPU host can upload one slice per device and all-gather them over NVLink).  flags as for zkmsm_*_load_points (a CRS is made of multiples
  * of the generators: ZKMSM_PRECOMPUTE | ZKMSM_SUBGROUP is the intended use).  `inf` arrays are optional
  * AtInfinity flags (NULL = none).  n_xt <= n. */
 typedef struct zkmsm_crs zkmsm_crs;

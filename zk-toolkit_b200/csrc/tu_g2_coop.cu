@@ -11,6 +11,7 @@ cudaError_t zk_opt_in_shared_memory_coop_g2() {
   cudaError_t e = cudaSuccess;
   if (e == cudaSuccess) e = cudaFuncSetAttribute(coop::bucket_reduce_kernel<G2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(coop::row_sum_kernel<G2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(coop::combine_kernel<G2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
   return e;
 }
 
@@ -28,6 +29,13 @@ cudaError_t zk_coop_row_sum_g2(cudaStream_t st, uint32_t nwin, uint32_t pitch_in
   uint32_t blocks_per_row = (m + per_block - 1) / per_block;
   coop::row_sum_kernel<G2><<<nwin * blocks_per_row, coop::kThreads, smem, st>>>(pitch_in, m, per_block, blocks_per_row, in,
                                                                                pitch_out, out);
+  return cudaGetLastError();
+}
+
+cudaError_t zk_coop_combine_g2(cudaStream_t st, uint32_t k, const XYZZ<Fp2>* parts, uint32_t* out_affine, uint32_t* out_inf,
+                               uint32_t* err) {
+  const size_t smem = coop::smem_bytes<Fp2>();
+  coop::combine_kernel<G2><<<1, coop::kThreads, smem, st>>>(k, parts, out_affine, out_inf, err);
   return cudaGetLastError();
 }
 

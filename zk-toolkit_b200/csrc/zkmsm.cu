@@ -692,6 +692,8 @@ static int combine_impl(zkmsm_ctx* ctx, const uint32_t* parts, bool on_device, s
   CudaExec ex(ctx->stream, nullptr, ctx->tune.no_coop != 0);
   if (std::is_same<C, G1>::value && k > 2 && k <= 32 && !ctx->tune.no_coop)
     ex.timed("combine_partials", (uint32_t)k, 1, [&] { return zk_coop_combine_g1(ctx->stream, (uint32_t)k, (const XYZZ<Fp>*)d_parts, ctx->d_res->affine, &ctx->d_res->inf, &ctx->d_res->err); });
+  else if (std::is_same<C, G2>::value && k > 1 && k <= 32 && !ctx->tune.no_coop)   // a lone thread needs ~0.1 ms per G2 addition
+    ex.timed("combine_partials", (uint32_t)k, 1, [&] { return zk_coop_combine_g2(ctx->stream, (uint32_t)k, (const XYZZ<Fp2>*)d_parts, ctx->d_res->affine, &ctx->d_res->inf, &ctx->d_res->err); });
   else
     ex.template launch<CombinePartials<C>>(1u, (uint32_t)k, d_parts, ctx->d_res->affine, &ctx->d_res->inf, &ctx->d_res->err);
   if (ex.err != cudaSuccess) return fail(ctx, ZKMSM_ERR_CUDA, "combine: %s", cudaGetErrorString(ex.err));
@@ -1037,6 +1039,23 @@ extern "C" int zkmsm_crs_load(zkmsm_ctx* ctx, const zkmsm_crs_desc* d, unsigned 
   }
   if (rc) { zkmsm_crs_free(ctx, crs); return rc; }
   for (int i = 0; i < 2; i++) { crs->lane[i]->tune = ctx->tune; crs->lane[i]->window_override = ctx->window_override; }
+  // Stream priorities: the G2 MSM (lane 0) has the longest latency-bound tail, then C (lane 1); with the higher
+  // priority their bucket accumulation goes first and their tails then run under the other MSMs' accumulation
+  // instead of at the end of the proof.
+  {
+    int least = 0, greatest = 0;
+    if (cudaDeviceGetStreamPriorityRange(&least, &greatest) == cudaSuccess && greatest < least) {
+      for (int i = 0; i < 2; i++) {
+        cudaStream_t st = nullptr;
+        int prio = greatest + i < least ? greatest + i : least;
+        if (cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, prio) == cudaSuccess) {
+          cudaStreamDestroy(crs->lane[i]->own_stream);
+          crs->lane[i]->own_stream = crs->lane[i]->stream = st;
+        }
+      }
+    }
+    cudaGetLastError();
+  }
   *out = crs;
   return ZKMSM_OK;
 }
@@ -1070,11 +1089,12 @@ static int groth16_enqueue(zkmsm_ctx* ctx, zkmsm_crs* crs, const uint32_t* u, co
   memcpy(crs->h_rs + 8, s, 32);
   const size_t row = sizeof(uint32_t) * 8;
   if (n) {
-    CU(ctx, cudaMemcpyAsync(su, u, row * n, cudaMemcpyHostToDevice, st));
-    CU(ctx, cudaMemcpyAsync(sv, v, row * n, cudaMemcpyHostToDevice, st));
+    // (cudaMemcpyDefault: the four vectors may live in host memory or already on this device)
+    CU(ctx, cudaMemcpyAsync(su, u, row * n, cudaMemcpyDefault, st));
+    CU(ctx, cudaMemcpyAsync(sv, v, row * n, cudaMemcpyDefault, st));
   }
-  if (crs->n_wit) CU(ctx, cudaMemcpyAsync(sc, wit, row * crs->n_wit, cudaMemcpyHostToDevice, st));
-  if (crs->n_xt) CU(ctx, cudaMemcpyAsync(sc + 8 * crs->n_wit, h, row * crs->n_xt, cudaMemcpyHostToDevice, st));
+  if (crs->n_wit) CU(ctx, cudaMemcpyAsync(sc, wit, row * crs->n_wit, cudaMemcpyDefault, st));
+  if (crs->n_xt) CU(ctx, cudaMemcpyAsync(sc + 8 * crs->n_wit, h, row * crs->n_xt, cudaMemcpyDefault, st));
   CU(ctx, cudaMemcpyAsync(d_rs, crs->h_rs, 64, cudaMemcpyHostToDevice, st));
   CU(ctx, cudaMemsetAsync(&ctx->d_res->aux_err, 0, sizeof(uint32_t), st));
   CudaExec ex(st);

@@ -190,6 +190,41 @@ class Prover:
         return out
 
 
+def _prove_partial_gathered(self, crs, r, s, rank, world):
+    import torch
+    import torch.distributed as dist
+    u, v, h, wit = self._arrays(crs)
+    key = ("gathered", id(crs.ctx), crs.n, crs.n_xt, crs.n_wit, world)
+    if key not in self._limbs:
+        dev = torch.device("cuda", crs.ctx.device)
+        bufs = []
+        for vec, m in ((u, crs.n), (v, crs.n), (h, crs.n_xt), (wit, crs.n_wit)):
+            per = max(1, -(-m // world))
+            lo, hi = min(m, rank * per), min(m, (rank + 1) * per)
+            src = torch.from_numpy(vec[lo:hi].view(np.int32)) if hi > lo else None
+            d_slice = torch.zeros(per, 8, dtype=torch.int32, device=dev)
+            d_full = torch.empty(world * per, 8, dtype=torch.int32, device=dev)
+            bufs.append((src, hi - lo, d_slice, d_full))
+        self._limbs[key] = (crs.ctx, bufs)
+    bufs = self._limbs[key][1]
+    for src, cnt, d_slice, d_full in bufs:
+        if cnt:
+            d_slice[:cnt].copy_(src, non_blocking=True)
+        dist.all_gather_into_tensor(d_full.view(-1), d_slice.view(-1))
+    torch.cuda.current_stream().synchronize()      # the library runs on its own stream
+    rs = scalars_to_array([int(r) % R, int(s) % R])
+    out = np.zeros(L.GROTH16_PARTIAL_WORDS, dtype=np.uint32)
+    ctx = crs.ctx
+    P = ctypes.c_void_p
+    ctx._check(ctx.lib.zkmsm_groth16_prove_partial(ctx.h, crs.handle, P(bufs[0][3].data_ptr()), P(bufs[1][3].data_ptr()),
+                                                   P(bufs[2][3].data_ptr()), P(bufs[3][3].data_ptr()), L.dptr(rs[0:1]), L.dptr(rs[1:2]),
+                                                   rank, world, L.dptr(out)))
+    return out
+
+
+Prover._prove_partial_gathered = _prove_partial_gathered
+
+
 def combine_partials(partials, ctx=None) -> Proof:
     """sum of the per-rank shares of prove_partial, in rank order (zkmsm_groth16_combine)"""
     ctx = ctx or default_context()
@@ -212,8 +247,12 @@ def prove_distributed(prover: Prover, crs: DeviceCRS, r: int, s: int, timings=No
     if world == 1:
         return prover.prove(crs, r, s)
     t0 = time.perf_counter()
-    mine = prover.prove_partial(crs, r, s, rank, world)
-    t1 = time.perf_counter()
+    if dist.get_backend() == "nccl":
+        # every rank uploads 1/world of each coefficient vector and the slices are all-gathered over NVLink: the
+        # scalars cross PCIe once per proof instead of once per GPU (8 concurrent 32 MB uploads measured 1.7 ms each)
+        mine = prover._prove_partial_gathered(crs, r, s, rank, world)
+    else:
+        mine = prover.prove_partial(crs, r, s, rank, world)
     if dist.get_backend() == "nccl":
         # the blob is already on the host (the share call waits for its three MSMs): pinned staging both ways
         st = getattr(crs, "_xchg", None)
