@@ -242,6 +242,9 @@ static constexpr uint32_t NO_KEY = 0xffffffffu;
 // work for ordinary buckets and are latency-bound at ~13 us per addition (fan 2); above that only giant buckets
 // (skewed scalars) have anything left, so the tree closes quickly (fan 16).
 inline uint32_t fix_fan(uint32_t level) { return level == 0 ? 4u : (level <= 2 ? 2u : 16u); }
+// the same tree as the gated fallback of AccumulateBuckets / FixupDirect: it runs for skewed inputs only, so fewer,
+// wider levels (every launch that finds the gate closed still costs a few microseconds)
+inline uint32_t fix_fan_fallback(uint32_t) { return 32u; }
 
 template <class C> struct Accumulate {
   typedef typename C::F F;
@@ -540,8 +543,185 @@ template <class C, bool FIRST> struct BatchedAddRound {
 #else
   static constexpr bool kNoDStore = FIRST;
 #endif
+#if defined(__CUDA_ARCH__) && defined(ZK_BATCH_RING)
+  // ---- first round with the operands staged through shared memory (cp.async ring), G1 only -------------------
+  // The first round gathers its operands from the precomputed tables at random; with the operands of ONE output
+  // ahead in registers the warps sit on the long scoreboard (27 % of the stall samples, profiles/).  Here every
+  // thread keeps a private ring in shared memory that cp.async fills 4 outputs ahead on the way forward (x1, x2: 6
+  // 16-byte chunks per output) and 2 outputs ahead on the way back (x1, y1, x2, y2: 12 chunks), no registers held.
+  // Layout: chunk slot cs of thread t at ((cs * 128 + t) * 16) bytes: 24 chunk slots = 48 KB per block.
+  static __device__ __forceinline__ void cp16(uint32_t smem_addr, const void* g) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(g));
+  }
+  static __device__ __forceinline__ void cp48(uint32_t smem_base, uint32_t cs, const void* g) {
+    const char* c = (const char*)g;
+    cp16(smem_base + (cs * 128u) * 16u, c);
+    cp16(smem_base + ((cs + 1) * 128u) * 16u, c + 16);
+    cp16(smem_base + ((cs + 2) * 128u) * 16u, c + 32);
+  }
+  static __device__ __forceinline__ void ld48(F& r, const uint4* ring, uint32_t cs) {
+    uint4 a = ring[cs * 128u + threadIdx.x], b = ring[(cs + 1) * 128u + threadIdx.x], c = ring[(cs + 2) * 128u + threadIdx.x];
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+    r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+    r.v[8] = c.x; r.v[9] = c.y; r.v[10] = c.z; r.v[11] = c.w;
+  }
+  static __device__ void run_ring(uint32_t tid, MsmPlan p, const uint32_t* off_in, const uint32_t* off_out, const Entry* entries,
+                                  const Affine<F>* src, Affine<F>* dst, F* prefix) {
+    __shared__ uint4 ring[24 * 128];
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(ring) + threadIdx.x * 16u;
+    const uint32_t total = off_out[p.nb], T = p.batch_T;
+    const uint64_t beg64 = (uint64_t)tid * T;
+    if (beg64 >= total) return;
+    const uint32_t beg = (uint32_t)beg64, end = beg + T < total ? beg + T : total;
+    uint32_t lo = 0, hi = p.nb;
+    while (hi - lo > 1) { uint32_t mid = (lo + hi) / 2; if (off_out[mid] <= beg) lo = mid; else hi = mid; }
+    const uint32_t b_first = lo;
+    constexpr uint32_t DF = 4, DB = 2;
+    // meta bits of the outputs in flight: slot j holds has2 | neg1 << 1 | neg2 << 2 at bits [4 j, 4 j + 3)
+    uint32_t meta = 0;
+    auto set_meta = [&](uint32_t slot, const Loc& l) {
+      const uint32_t m = (l.has2 ? 1u : 0u) | ((l.e1.val >> 31) << 1) | ((l.e2.val >> 31) << 2);
+      meta = (meta & ~(7u << (4 * slot))) | (m << (4 * slot));
+    };
+    // ---------------- forward
+    uint32_t bi = b_first;        // bucket cursor of the issue stage
+    Loc loc;
+    for (uint32_t j = 0; j < DF; j++) {
+      if (beg + j < end) {
+        while (beg + j >= off_out[bi + 1]) bi++;
+        find(loc, beg + j, bi, off_in, off_out, entries);
+        cp48(sbase, j * 6, &src[loc.e1.val & 0x7fffffffu].x);
+        cp48(sbase, j * 6 + 3, &src[loc.e2.val & 0x7fffffffu].x);
+        set_meta(j, loc);
+      }
+      asm volatile("cp.async.commit_group;");
+    }
+    if (beg + DF < end) {
+      while (beg + DF >= off_out[bi + 1]) bi++;
+      find(loc, beg + DF, bi, off_in, off_out, entries);
+    }
+    F prod;
+    fset_one(prod);
+    uint32_t bc = b_first;        // bucket cursor of the consume stage (rare cases re-read their entries)
+    uint64_t rare_lo = 0, rare_hi = 0;
+    for (uint32_t o = beg; o < end; o++) {
+      const uint32_t slot = (o - beg) % DF;
+      asm volatile("cp.async.wait_group %0;" ::"n"(DF - 1));
+      F x1, x2;
+      ld48(x1, ring, slot * 6);
+      ld48(x2, ring, slot * 6 + 3);
+      const uint32_t m = (meta >> (4 * slot)) & 7u;
+      if (o + DF < end) {
+        cp48(sbase, slot * 6, &src[loc.e1.val & 0x7fffffffu].x);
+        cp48(sbase, slot * 6 + 3, &src[loc.e2.val & 0x7fffffffu].x);
+        set_meta(slot, loc);
+        if (o + DF + 1 < end) {
+          while (o + DF + 1 >= off_out[bi + 1]) bi++;
+          find(loc, o + DF + 1, bi, off_in, off_out, entries);
+        }
+      }
+      asm volatile("cp.async.commit_group;");
+      const bool has2 = (m & 1u) != 0;
+      F d;
+      fsub(d, x2, x1);
+      const bool rare = !common_case(has2, x1, x2, d);
+      rare_hi = (rare_hi << 1) | (rare_lo >> 63);
+      rare_lo = (rare_lo << 1) | (rare ? 1u : 0u);
+      if (rare) {
+        while (o >= off_out[bc + 1]) bc++;
+        Loc lr;
+        find(lr, o, bc, off_in, off_out, entries);
+        F y1 = src[lr.e1.val & 0x7fffffffu].y, y2 = src[lr.e2.val & 0x7fffffffu].y;
+        fcneg(y1, y1, (m & 2u) != 0);
+        fcneg(y2, y2, (m & 4u) != 0);
+        classify_rare(d, has2, x1, y1, x2, y2);
+      }
+      prefix[prefix_at(tid, T, o - beg)] = prod;
+      fmul(prod, prod, d);
+    }
+    asm volatile("cp.async.wait_group 0;");
+    F inv;
+    finv(inv, prod);
+    // ---------------- backward: outputs end - 1 .. beg; slot of output o is (end - 1 - o) % DB, 12 chunks each
+    while (end - 1 >= off_out[bi + 1]) bi++;          // bucket of the last output
+    while (end - 1 < off_out[bi]) bi--;
+    for (uint32_t j = 0; j < DB; j++) {
+      if (end >= beg + 1 + j) {
+        const uint32_t o = end - 1 - j;
+        while (o < off_out[bi]) bi--;
+        find(loc, o, bi, off_in, off_out, entries);
+        const Affine<F>* p1 = &src[loc.e1.val & 0x7fffffffu];
+        const Affine<F>* p2 = &src[loc.e2.val & 0x7fffffffu];
+        cp48(sbase, j * 12, &p1->x); cp48(sbase, j * 12 + 3, &p1->y);
+        cp48(sbase, j * 12 + 6, &p2->x); cp48(sbase, j * 12 + 9, &p2->y);
+        set_meta(j, loc);
+      }
+      asm volatile("cp.async.commit_group;");
+    }
+    if (end >= beg + 1 + DB) {
+      const uint32_t o = end - 1 - DB;
+      while (o < off_out[bi]) bi--;
+      find(loc, o, bi, off_in, off_out, entries);
+    }
+    F pk = prefix[prefix_at(tid, T, end - 1 - beg)];
+    for (uint32_t o = end; o-- > beg;) {
+      const uint32_t slot = (end - 1 - o) % DB;
+      asm volatile("cp.async.wait_group %0;" ::"n"(DB - 1));
+      F x1, y1, x2, y2, dinv, lam, t, d;
+      ld48(x1, ring, slot * 12); ld48(y1, ring, slot * 12 + 3);
+      ld48(x2, ring, slot * 12 + 6); ld48(y2, ring, slot * 12 + 9);
+      const uint32_t m = (meta >> (4 * slot)) & 7u;
+      if (o >= beg + DB) {                              // output o - DB takes this slot
+        const Affine<F>* p1 = &src[loc.e1.val & 0x7fffffffu];
+        const Affine<F>* p2 = &src[loc.e2.val & 0x7fffffffu];
+        cp48(sbase, slot * 12, &p1->x); cp48(sbase, slot * 12 + 3, &p1->y);
+        cp48(sbase, slot * 12 + 6, &p2->x); cp48(sbase, slot * 12 + 9, &p2->y);
+        set_meta(slot, loc);
+        if (o >= beg + DB + 1) {
+          const uint32_t on = o - DB - 1;
+          while (on < off_out[bi]) bi--;
+          find(loc, on, bi, off_in, off_out, entries);
+        }
+      }
+      asm volatile("cp.async.commit_group;");
+      fmul(dinv, inv, pk);
+      if (o > beg) pk = prefix[prefix_at(tid, T, o - 1 - beg)];
+      const bool has2 = (m & 1u) != 0;
+      fcneg(y1, y1, (m & 2u) != 0);
+      fcneg(y2, y2, (m & 4u) != 0);
+      int kind = 0;
+      const bool rare = (rare_lo & 1u) != 0;
+      rare_lo = (rare_lo >> 1) | (rare_hi << 63);
+      rare_hi >>= 1;
+      fsub(d, x2, x1);
+      if (rare) kind = classify_rare(d, has2, x1, y1, x2, y2);
+      fsub(t, y2, y1);
+      if (kind == 1) { fmul(t, x1, x1); fdbl(lam, t); fadd(t, lam, t); x2 = x1; }
+      fmul(lam, t, dinv);
+      fmul(inv, inv, d);
+      Affine<F> r;
+      fmul(t, lam, lam);
+      fsub(t, t, x1);
+      fsub(r.x, t, x2);
+      fsub(t, x1, r.x);
+      fmul(t, lam, t);
+      fsub(r.y, t, y1);
+      if (kind >= 2) {
+        if (kind == 2) { r.x = x1; r.y = y1; }
+        else if (kind == 3) { r.x = x2; r.y = y2; }
+        else set_inf(r);
+      }
+      dst[o] = r;
+    }
+    asm volatile("cp.async.wait_group 0;");
+  }
+#endif
+
   static ZK_HD void run(uint32_t tid, MsmPlan p, const uint32_t* off_in, const uint32_t* off_out, const Entry* entries,
                         const Affine<F>* src, Affine<F>* dst, F* prefix, size_t dstride, Entry* entries_out) {
+#if defined(__CUDA_ARCH__) && defined(ZK_BATCH_RING)
+    if (FIRST && sizeof(F) == 48 && entries_out == nullptr) { run_ring(tid, p, off_in, off_out, entries, src, dst, prefix); return; }
+#endif
     const uint32_t total = off_out[p.nb], T = p.batch_T;
     const uint64_t beg64 = (uint64_t)tid * T;
     if (beg64 >= total) return;
@@ -1259,7 +1439,7 @@ void msm_launch(Exec& ex, const MsmPlan& p, const MsmTuning& tune, const MsmBuff
     XYZZ<F>* pin = b.partials;
     uint32_t* kin = b.partial_keys;
     while (count > 1) {
-      uint32_t fan = fix_fan(level++), next = (count + fan - 1) / fan;
+      uint32_t fan = fix_fan_fallback(level++), next = (count + fan - 1) / fan;   // (always gated since FixupDirect exists)
       ex.template launch_capped<FixupLevel<C>>(cap_blocks, next, count, fan, (const uint32_t*)kin, (const XYZZ<F>*)pin, kin + count,
                                                pin + count, b.bucket_sums, gate);
       pin += count;

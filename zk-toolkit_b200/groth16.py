@@ -253,6 +253,7 @@ def prove_distributed(prover: Prover, crs: DeviceCRS, r: int, s: int, timings=No
         mine = prover._prove_partial_gathered(crs, r, s, rank, world)
     else:
         mine = prover.prove_partial(crs, r, s, rank, world)
+    t1 = time.perf_counter()
     if dist.get_backend() == "nccl":
         # the blob is already on the host (the share call waits for its three MSMs): pinned staging both ways
         st = getattr(crs, "_xchg", None)
