@@ -69,7 +69,9 @@ struct Groth16Scalars {
     (void)t;
     return ptx::subc(0, 0) != 0;   // borrow: a < r
   }
-  static ZK_HD void run(uint32_t tid, uint32_t n, const uint32_t* rs, uint32_t* su, uint32_t* sv, uint32_t* sc3, uint32_t* err) {
+  // write_b_tail = 0: sv's trailing [1, s] was already written by Groth16TailB (the G2 MSM started on it)
+  static ZK_HD void run(uint32_t tid, uint32_t n, const uint32_t* rs, uint32_t* su, uint32_t* sv, uint32_t* sc3, uint32_t write_b_tail,
+                        uint32_t* err) {
     if (tid > n) return;
     uint32_t rc[8], sc[8];
 #pragma unroll
@@ -100,9 +102,20 @@ struct Groth16Scalars {
 #pragma unroll
     for (int i = 0; i < 8; i++) {
       a_tail[i] = i == 0 ? 1u : 0u; a_tail[8 + i] = rc[i];
-      b_tail[i] = i == 0 ? 1u : 0u; b_tail[8 + i] = sc[i];
+      if (write_b_tail) { b_tail[i] = i == 0 ? 1u : 0u; b_tail[8 + i] = sc[i]; }
       c_tail[i] = sc[i]; c_tail[8 + i] = rc[i]; c_tail[16 + i] = prod.v[i];
     }
+  }
+};
+
+// sv's trailing slots alone, so that B's MSM can start as soon as v has arrived (before u, h and the witness)
+struct Groth16TailB {
+  static const char* name() { return "groth16_tail_b"; }
+  static ZK_HD void run(uint32_t tid, uint32_t n, const uint32_t* rs, uint32_t* sv) {
+    if (tid != 0) return;
+    uint32_t* b_tail = sv + (size_t)n * 8;
+#pragma unroll
+    for (int i = 0; i < 8; i++) { b_tail[i] = i == 0 ? 1u : 0u; b_tail[8 + i] = rs[8 + i]; }
   }
 };
 

@@ -7,6 +7,7 @@ ZK_INSTANTIATE_KERNEL(zk::FrToMont);
 ZK_INSTANTIATE_KERNEL(zk::FrAggregate);
 ZK_INSTANTIATE_KERNEL(zk::FrVecToMont);
 ZK_INSTANTIATE_KERNEL(zk::Groth16Scalars);
+ZK_INSTANTIATE_KERNEL(zk::Groth16TailB);
 ZK_INSTANTIATE_KERNEL(zk::FrPolyMulSub);
 ZK_INSTANTIATE_KERNEL(zk::FrTStep);
 ZK_INSTANTIATE_KERNEL(zk::FrDivStep);

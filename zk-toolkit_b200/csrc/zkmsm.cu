@@ -1088,28 +1088,29 @@ static int groth16_enqueue(zkmsm_ctx* ctx, zkmsm_crs* crs, const uint32_t* u, co
   memcpy(crs->h_rs, r, 32);
   memcpy(crs->h_rs + 8, s, 32);
   const size_t row = sizeof(uint32_t) * 8;
-  if (n) {
-    // (cudaMemcpyDefault: the four vectors may live in host memory or already on this device)
-    CU(ctx, cudaMemcpyAsync(su, u, row * n, cudaMemcpyDefault, st));
-    CU(ctx, cudaMemcpyAsync(sv, v, row * n, cudaMemcpyDefault, st));
-  }
+  zkmsm_ctx* cb = crs->lane[0];
+  zkmsm_ctx* cc = crs->lane[1];
+  CudaExec ex(st);
+  // v first: B (the G2 MSM, the longest) reads only sv = v ++ [1, s] and starts while u, h and the witness are still
+  // on their way (cudaMemcpyDefault: the four vectors may live in host memory or already on this device)
+  CU(ctx, cudaMemcpyAsync(d_rs, crs->h_rs, 64, cudaMemcpyHostToDevice, st));
+  if (n) CU(ctx, cudaMemcpyAsync(sv, v, row * n, cudaMemcpyDefault, st));
+  ex.template launch<Groth16TailB>(1u, (uint32_t)n, (const uint32_t*)d_rs, sv);
+  if (ex.err != cudaSuccess) return fail(ctx, ZKMSM_ERR_CUDA, "groth16 scalars: %s", cudaGetErrorString(ex.err));
+  CU(ctx, cudaEventRecord(crs->ready, st));
+  CU(ctx, cudaStreamWaitEvent(cb->stream, crs->ready, 0));
+  int rc;
+  if ((rc = msm_enqueue_impl<G2>(cb, crs->set_B, sv, nA, 2, want_affine, nullptr, rank, world))) { strcpy(ctx->err, cb->err); return rc; }
+  CU(ctx, cudaEventRecord(crs->done[0], cb->stream));
+  if (n) CU(ctx, cudaMemcpyAsync(su, u, row * n, cudaMemcpyDefault, st));
   if (crs->n_wit) CU(ctx, cudaMemcpyAsync(sc, wit, row * crs->n_wit, cudaMemcpyDefault, st));
   if (crs->n_xt) CU(ctx, cudaMemcpyAsync(sc + 8 * crs->n_wit, h, row * crs->n_xt, cudaMemcpyDefault, st));
-  CU(ctx, cudaMemcpyAsync(d_rs, crs->h_rs, 64, cudaMemcpyHostToDevice, st));
   CU(ctx, cudaMemsetAsync(&ctx->d_res->aux_err, 0, sizeof(uint32_t), st));
-  CudaExec ex(st);
-  ex.template launch<Groth16Scalars>((uint32_t)n + 1, (uint32_t)n, (const uint32_t*)d_rs, su, sv, sc + 8 * (crs->n_wit + crs->n_xt),
+  ex.template launch<Groth16Scalars>((uint32_t)n + 1, (uint32_t)n, (const uint32_t*)d_rs, su, sv, sc + 8 * (crs->n_wit + crs->n_xt), 0u,
                                      &ctx->d_res->aux_err);
   if (ex.err != cudaSuccess) return fail(ctx, ZKMSM_ERR_CUDA, "groth16 scalars: %s", cudaGetErrorString(ex.err));
   CU(ctx, cudaEventRecord(crs->ready, st));
-  int rc;
-  zkmsm_ctx* cb = crs->lane[0];
-  zkmsm_ctx* cc = crs->lane[1];
-  CU(ctx, cudaStreamWaitEvent(cb->stream, crs->ready, 0));
   CU(ctx, cudaStreamWaitEvent(cc->stream, crs->ready, 0));
-  // the G2 MSM is the longest: first in the queue
-  if ((rc = msm_enqueue_impl<G2>(cb, crs->set_B, sv, nA, 2, want_affine, nullptr, rank, world))) { strcpy(ctx->err, cb->err); return rc; }
-  CU(ctx, cudaEventRecord(crs->done[0], cb->stream));
   if ((rc = msm_enqueue_impl<G1>(cc, crs->set_C, sc, nC, 1, want_affine, nullptr, rank, world))) { strcpy(ctx->err, cc->err); return rc; }
   CU(ctx, cudaEventRecord(crs->done[1], cc->stream));
   if ((rc = msm_enqueue_impl<G1>(ctx, crs->set_A, su, nA, 1, want_affine, nullptr, rank, world))) return rc;
