@@ -46,6 +46,10 @@ struct HostExec {
     launch<Finish<C>>(1u, nwin, pitch, c, arr, out_xyzz, out_affine, out_inf);
   }
   bool ntt_fused(bool, Fr*, uint32_t, uint32_t, uint32_t, const Fr*, uint32_t) { return false; }   // per-stage bodies
+  void scan_pair_counts(uint32_t nb, const uint32_t* off_in, uint32_t* cnt, uint32_t* off_out, uint32_t* segsum) {
+    launch<PairCount>(nb, nb, off_in, cnt);      // the unfused formulation; the CUDA build forms the counts inside its scan
+    exclusive_scan(nb, cnt, off_out, segsum);
+  }
   void exclusive_scan(uint32_t nb, uint32_t* hist_cursor, uint32_t* offsets, uint32_t* segsum) {
     uint32_t nseg = (nb + SCAN_SEG - 1) / SCAN_SEG;
     launch<ScanLocal>(nseg, nb, (const uint32_t*)hist_cursor, segsum);

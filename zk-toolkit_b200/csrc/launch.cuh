@@ -68,6 +68,9 @@ template <class Body> struct Launch : LaunchBase<Body, decltype(Body::run)> {};
 // Exec policy for msm_launch (msm.cuh): stream-ordered CUDA launches
 // block-cooperative exclusive scan (tu_sort.cu): offsets[0..n] = scan(hist), hist <- offsets (cursors)
 cudaError_t zk_exclusive_scan(cudaStream_t st, uint32_t n, uint32_t* hist_cursor, uint32_t* offsets, uint32_t* blocksums);
+// off_out[0..n] = scan of the per-bucket output counts ceil(size / 2) of a batched-affine round (sizes from off_in)
+cudaError_t zk_exclusive_scan_pairs(cudaStream_t st, uint32_t n, const uint32_t* off_in, uint32_t* off_out, uint32_t* blocksums);
+int zk_scan_launches(uint32_t n);   // kernels one scan of n elements launches (1 up to 8192 elements, else 3)
 
 // block-cooperative G1 tail kernels (tu_g1_coop.cu)
 struct MsmPlan;
@@ -252,18 +255,12 @@ struct CudaExec {
     return true;
   }
   void exclusive_scan(uint32_t n, uint32_t* hist_cursor, uint32_t* offsets, uint32_t* blocksums) {
-    if (err != cudaSuccess) return;
-    int slot = -1;
-    if (prof && prof->n < LaunchProfile::MAX) {
-      slot = prof->n++;
-      prof->names[slot] = "exclusive_scan";
-      prof->threads[slot] = n;
-      cudaEventRecord(prof->beg[slot], st);
-    }
-    cudaError_t e = zk_exclusive_scan(st, n, hist_cursor, offsets, blocksums);
-    if (slot >= 0) cudaEventRecord(prof->end[slot], st);
-    launches += 3;
-    if (e != cudaSuccess) err = e;
+    timed("exclusive_scan", n, zk_scan_launches(n), [&] { return zk_exclusive_scan(st, n, hist_cursor, offsets, blocksums); });
+  }
+  // output offsets of a batched-affine round: scan of ceil(size / 2) per bucket, the counts formed inside the scan
+  // (cnt_scratch is what the unfused formulation -- PairCount, then a scan -- needs; unused here)
+  void scan_pair_counts(uint32_t n, const uint32_t* off_in, uint32_t* /*cnt_scratch*/, uint32_t* off_out, uint32_t* blocksums) {
+    timed("scan_pair_counts", n, zk_scan_launches(n), [&] { return zk_exclusive_scan_pairs(st, n, off_in, off_out, blocksums); });
   }
   void zero(void* p, size_t bytes) {
     if (err != cudaSuccess || bytes == 0) return;

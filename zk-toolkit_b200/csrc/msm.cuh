@@ -1385,8 +1385,7 @@ void msm_launch(Exec& ex, const MsmPlan& p, const MsmTuning& tune, const MsmBuff
       MsmPlan pr = p;
       pr.batch_T = msm_batch_T(p, expected, tune);
       const uint32_t threads = (uint32_t)((bound + pr.batch_T - 1) / pr.batch_T);
-      ex.template launch<PairCount>(p.nb, p.nb, off_in, b.pre_cnt);
-      ex.exclusive_scan(p.nb, b.pre_cnt, off_out, b.segsum);
+      ex.scan_pair_counts(p.nb, off_in, b.pre_cnt, off_out, b.segsum);   // off_out = scan of ceil(size_b / 2)
       if (r == 0)
         ex.template launch<BatchedAddRound<C, true>>(threads, pr, off_in, (const uint32_t*)off_out, (const Entry*)b.entries, src, dst,
                                                      b.pre_prefix, msm_prefix_slots(p), last ? b.pre_entries : (Entry*)nullptr);

@@ -193,6 +193,7 @@ extern "C" const char* zkmsm_last_error(const zkmsm_ctx* ctx) { return ctx ? ctx
 extern "C" int zkmsm_set_window(zkmsm_ctx* ctx, unsigned c) {
   if (!ctx || (c != 0 && (c < 3 || c > 22))) return ZKMSM_ERR_INVALID_ARG;
   ctx->window_override = c;
+  ctx->tune_epoch++;   // plain sets plan with it: cached launch graphs are keyed on the epoch
   return ZKMSM_OK;
 }
 
