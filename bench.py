@@ -60,7 +60,7 @@ class ClockSampler:
         self.rows, self.proc = [], None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200", "-i", str(index)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "20", "-i", str(index)], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -280,8 +280,6 @@ def main():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-        t_wall1 = time.time()
-        clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
         total_ms = e0.elapsed_time(e1)
         launches = args.steps * (ctx.last_launch_count() + (2 if world > 1 else 0))
         if not same_point(res, want_xy):
@@ -368,6 +366,9 @@ def main():
                "api": "zkmsm_g1_msm(ctx, resident CRS points, host scalars) -> host affine point" if world == 1 else
                       "per rank: H2D of 1/N of the scalars + NVLink all-gather of the slices (range split; all of its own under the points split), "
                       "zkmsm_g1_msm_partial_*_device, NCCL all-gather of the partials, zkmsm_g1_combine_enqueue + result"}
+        # clocks / throttle reasons: nvidia-smi samples every 20 ms from the start of the timed steps to the end of the
+        # end-to-end steps (the same workload under load throughout; K steps alone last only ~60 ms)
+        clocks = sampler.stop(t_wall0, time.time()) if sampler else None
         if world == 1:
             # the same steps issued through the asynchronous pair of calls on two contexts, so that the copy of step
             # k + 1 runs under the kernels of step k (what a prover with several MSMs per proof does);
