@@ -20,7 +20,7 @@ cudaError_t zk_coop_bucket_reduce_g1(cudaStream_t st, const MsmPlan& p, const ui
                                      XYZZ<Fp>* out, int tree) {
   const size_t smem = coop::smem_bytes<Fp>();
   uint32_t chains = p.nwin * (p.B / p.K);
-  coop::bucket_reduce_kernel<G1><<<(chains + 31) / 32, coop::kThreads, smem, st>>>(p, offsets, buckets, out, tree);
+  coop::bucket_reduce_kernel<G1><<<(chains + 31) / 32, coop::block_threads<Fp>(), smem, st>>>(p, offsets, buckets, out, tree);
   return cudaGetLastError();
 }
 
@@ -28,7 +28,7 @@ cudaError_t zk_coop_row_sum_g1(cudaStream_t st, uint32_t nwin, uint32_t pitch_in
                                const XYZZ<Fp>* in, uint32_t pitch_out, XYZZ<Fp>* out) {
   const size_t smem = coop::smem_bytes<Fp>();
   uint32_t blocks_per_row = (m + per_block - 1) / per_block;
-  coop::row_sum_kernel<G1><<<nwin * blocks_per_row, coop::kThreads, smem, st>>>(pitch_in, m, per_block, blocks_per_row, in,
+  coop::row_sum_kernel<G1><<<nwin * blocks_per_row, coop::block_threads<Fp>(), smem, st>>>(pitch_in, m, per_block, blocks_per_row, in,
                                                                                pitch_out, out);
   return cudaGetLastError();
 }
@@ -36,14 +36,14 @@ cudaError_t zk_coop_row_sum_g1(cudaStream_t st, uint32_t nwin, uint32_t pitch_in
 cudaError_t zk_coop_finish_g1(cudaStream_t st, uint32_t nwin, uint32_t pitch, uint32_t c, const XYZZ<Fp>* arr,
                               XYZZ<Fp>* out_xyzz, uint32_t* out_affine, uint32_t* out_inf) {
   const size_t smem = coop::smem_bytes<Fp>();
-  coop::finish_kernel<G1><<<1, coop::kThreads, smem, st>>>(nwin, pitch, c, arr, out_xyzz, out_affine, out_inf);
+  coop::finish_kernel<G1><<<1, coop::block_threads<Fp>(), smem, st>>>(nwin, pitch, c, arr, out_xyzz, out_affine, out_inf);
   return cudaGetLastError();
 }
 
 cudaError_t zk_coop_combine_g1(cudaStream_t st, uint32_t k, const XYZZ<Fp>* parts, uint32_t* out_affine, uint32_t* out_inf,
                                uint32_t* err) {
   const size_t smem = coop::smem_bytes<Fp>();
-  coop::combine_kernel<G1><<<1, coop::kThreads, smem, st>>>(k, parts, out_affine, out_inf, err);
+  coop::combine_kernel<G1><<<1, coop::block_threads<Fp>(), smem, st>>>(k, parts, out_affine, out_inf, err);
   return cudaGetLastError();
 }
 

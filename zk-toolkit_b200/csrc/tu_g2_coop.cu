@@ -19,7 +19,7 @@ cudaError_t zk_coop_bucket_reduce_g2(cudaStream_t st, const MsmPlan& p, const ui
                                      XYZZ<Fp2>* out, int tree) {
   const size_t smem = coop::smem_bytes<Fp2>();
   uint32_t chains = p.nwin * (p.B / p.K);
-  coop::bucket_reduce_kernel<G2><<<(chains + 31) / 32, coop::kThreads, smem, st>>>(p, offsets, buckets, out, tree);
+  coop::bucket_reduce_kernel<G2><<<(chains + 31) / 32, coop::block_threads<Fp2>(), smem, st>>>(p, offsets, buckets, out, tree);
   return cudaGetLastError();
 }
 
@@ -27,7 +27,7 @@ cudaError_t zk_coop_row_sum_g2(cudaStream_t st, uint32_t nwin, uint32_t pitch_in
                                const XYZZ<Fp2>* in, uint32_t pitch_out, XYZZ<Fp2>* out) {
   const size_t smem = coop::smem_bytes<Fp2>();
   uint32_t blocks_per_row = (m + per_block - 1) / per_block;
-  coop::row_sum_kernel<G2><<<nwin * blocks_per_row, coop::kThreads, smem, st>>>(pitch_in, m, per_block, blocks_per_row, in,
+  coop::row_sum_kernel<G2><<<nwin * blocks_per_row, coop::block_threads<Fp2>(), smem, st>>>(pitch_in, m, per_block, blocks_per_row, in,
                                                                                pitch_out, out);
   return cudaGetLastError();
 }
@@ -35,7 +35,7 @@ cudaError_t zk_coop_row_sum_g2(cudaStream_t st, uint32_t nwin, uint32_t pitch_in
 cudaError_t zk_coop_combine_g2(cudaStream_t st, uint32_t k, const XYZZ<Fp2>* parts, uint32_t* out_affine, uint32_t* out_inf,
                                uint32_t* err) {
   const size_t smem = coop::smem_bytes<Fp2>();
-  coop::combine_kernel<G2><<<1, coop::kThreads, smem, st>>>(k, parts, out_affine, out_inf, err);
+  coop::combine_kernel<G2><<<1, coop::block_threads<Fp2>(), smem, st>>>(k, parts, out_affine, out_inf, err);
   return cudaGetLastError();
 }
 
