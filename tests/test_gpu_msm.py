@@ -452,3 +452,13 @@ def test_msm_2p20_default_path_vs_oracle_closed_form(z, ctx):
     # the same through the two multi-GPU splits, all ranks on this device
     parts = [ctx.msm_partial_range(pts.set, arr, r, 8) for r in range(8)]
     assert U.g1_from_array(*ctx.combine(1, np.stack(parts))) == want
+
+
+def test_scalar_longer_than_256_bits(z):
+    """`&G1Point * n` takes any BigUint in the reference (macros.rs:10-21, no reduction): a 600-bit multiplier goes
+    through the 256-bit device entry in chunks and equals the multiple by n mod r (the generator has order r)"""
+    k = (1 << 599) + 0x123456789ABCDEF * (1 << 300) + 987654321
+    g = z.G1Point.g()
+    assert to_o1(g * k) == O.scalar_mul(O.G1_GEN, k % O.R)
+    assert to_o1(g * (1 << 256)) == O.scalar_mul(O.G1_GEN, (1 << 256) % O.R)
+    assert (z.G1Point.zero() * k).is_zero()

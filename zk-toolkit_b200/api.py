@@ -111,8 +111,24 @@ class _Point:
     def __mul__(self, k):
         """raw integer multiple, not reduced mod r (macros.rs:10-21)"""
         k = int(getattr(k, "e", k))
+        if k < 0:
+            raise ValueError("negative scalar")
         if self.coords is None:
             return type(self)(None)
+        if k >> 256:
+            # the reference multiplies by any BigUint (macros.rs:10-21); the device takes 256-bit raw integers, so a
+            # longer one goes in 256-bit chunks, Horner over 2^256 = 2 * 2^255
+            chunks = []
+            while k:
+                chunks.append(k & ((1 << 256) - 1))
+                k >>= 256
+            acc = None
+            for c in reversed(chunks):
+                if acc is not None:
+                    acc = (acc * (1 << 255)) * 2
+                t = self * c
+                acc = t if acc is None else acc + t
+            return acc
         out, inf = default_context().mul_base(self.GROUP, self.limbs(), scalars_to_array([k]))
         return self.from_limbs(out[0], inf[0])
 
