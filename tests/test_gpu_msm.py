@@ -462,3 +462,43 @@ def test_scalar_longer_than_256_bits(z):
     assert to_o1(g * k) == O.scalar_mul(O.G1_GEN, k % O.R)
     assert to_o1(g * (1 << 256)) == O.scalar_mul(O.G1_GEN, (1 << 256) % O.R)
     assert (z.G1Point.zero() * k).is_zero()
+
+
+def test_g2_batched_affine_rounds(z, ctx):
+    """G2 takes the batched-affine pre-reduction rounds as well (BatchedAddRound<G2>, Fq2 affine law of g2_point.rs /
+    macros.rs:35-163): forced on a small set with every rare case inside the rounds, and the default path at 2^17"""
+    g = z.G2Point.g()
+    P, Q = g * 11, g * 13
+    try:
+        ctx.set_option("batch_rounds", 2)
+        ctx.set_option("batch_T", 5)
+        for pre in (False, True):
+            dup = z.G2Points([g * 7] * 40, precompute=pre)
+            assert U.g2_from_array(*ctx.msm(dup.set, z.scalars_to_array([5] * 40))) == O.scalar_mul(O.G2_GEN, 7 * 5 * 40)
+            opp = z.G2Points([P, -P, Q, -Q, P, -P], precompute=pre)
+            assert U.g2_from_array(*ctx.msm(opp.set, z.scalars_to_array([9, 9, 11, 11, 3, 3]))) == O.INF
+            withinf = z.G2Points([P, z.G2Point.zero(), Q, z.G2Point.zero(), g * 17, P], precompute=pre)
+            assert U.g2_from_array(*ctx.msm(withinf.set, z.scalars_to_array([5] * 6))) == O.scalar_mul(O.G2_GEN, 5 * (11 + 13 + 17 + 11))
+        n = 3000
+        rnd = random.Random(222)
+        dlogs = [rnd.randrange(1, O.R) for _ in range(n)]
+        sc = U.rand_scalars(rnd, n)
+        pts = z.G2Points.generator_multiples(dlogs, precompute=True)
+        for rounds, T in ((1, 128), (3, 7)):
+            ctx.set_option("batch_rounds", rounds)
+            ctx.set_option("batch_T", T)
+            assert U.g2_from_array(*ctx.msm(pts.set, z.scalars_to_array(sc))) == U.expected_from_dlogs(O.G2_GEN, dlogs, sc)
+    finally:
+        ctx.set_option("batch_rounds", -1)
+        ctx.set_option("batch_T", 0)
+    n = 1 << 17
+    rnd = random.Random(217)
+    dlogs = [rnd.randrange(1, O.R) for _ in range(n)]
+    sc = U.rand_scalars(rnd, n)
+    pts = z.G2Points.generator_multiples(dlogs, precompute=True)
+    ctx.profile(True)
+    out, inf = ctx.msm(pts.set, z.scalars_to_array(sc))
+    names = [nm for nm, _, _ in ctx.profile_read()]
+    ctx.profile(False)
+    assert "batched_add_first" in names and "fixup_direct" in names
+    assert U.g2_from_array(out, inf) == O.scalar_mul(O.G2_GEN, sum(k * s for k, s in zip(dlogs, sc)) % O.R)

@@ -404,3 +404,19 @@ def test_sorted_pair_count_must_fit_32_bits(lib):
     assert lib.emu_fits(1 << 26, 17, 1) == 1 and lib.emu_fits(1 << 26, 5, 0) == 1      # 52 windows
     assert lib.emu_fits(1 << 26, 4, 0) == 0 and lib.emu_fits(1 << 26, 3, 0) == 0
     assert lib.emu_fits((1 << 26) - 1, 4, 0) == 1 and lib.emu_fits(50_000_000, 3, 0) == 0
+
+
+def test_emu_g2_batched_affine_rounds(lib, monkeypatch):
+    """the batched-affine rounds with Fq2 coordinates (what G2 sets now run by default on the device)"""
+    rnd = random.Random(12)
+    dlogs = [rnd.randrange(1, O.R) for _ in range(20)]
+    pts = [O.scalar_mul(O.G2_GEN, k) for k in dlogs]
+    pts[3] = pts[2]                       # P + P inside a bucket
+    dlogs[3] = dlogs[2]
+    sc = U.rand_scalars(rnd, len(pts))
+    sc[3] = sc[2]
+    monkeypatch.setenv("ZKMSM_BATCH_ROUNDS", "2")
+    monkeypatch.setenv("ZKMSM_BATCH_T", "3")
+    for precomp, c in ((1, 4), (3, 5)):
+        rc, got = emu_g2(lib, pts, sc, c=c, precomp=precomp)
+        assert rc == 0 and got == U.expected_from_dlogs(O.G2_GEN, dlogs, sc)

@@ -1106,7 +1106,7 @@ template <class C> struct StorePoints {
 struct MsmTuning {
   int batch_rounds = -1;   // ZKMSM_BATCH_ROUNDS: force the number of batched-affine rounds (0 = off)
   int batch_T = 0;         // ZKMSM_BATCH_T: additions sharing one inversion (2..128)
-  int batch_g2 = 0;        // ZKMSM_BATCH_G2: forced rounds also apply to G2
+  int batch_g2 = 1;        // ZKMSM_BATCH_G2=0: no batched-affine rounds for G2
   int batch_blocks = 0;    // ZKMSM_BATCH_BLOCKS: resident blocks per SM assumed for the batched kernel (A/B builds)
   int L = 0;               // ZKMSM_L: sorted pairs per accumulate thread
   int K = 0;               // ZKMSM_K: buckets per reduction chain (power of two)
@@ -1124,7 +1124,7 @@ struct MsmTuning {
     MsmTuning t;
     t.batch_rounds = env_int("ZKMSM_BATCH_ROUNDS", -1);
     t.batch_T = env_int("ZKMSM_BATCH_T", 0);
-    t.batch_g2 = getenv("ZKMSM_BATCH_G2") ? 1 : 0;
+    t.batch_g2 = env_int("ZKMSM_BATCH_G2", 1);
     t.batch_blocks = env_int("ZKMSM_BATCH_BLOCKS", 0);
     t.L = env_int("ZKMSM_L", 0);
     t.K = env_int("ZKMSM_K", 0);

@@ -9,5 +9,3 @@ ZK_INSTANTIATE_KERNEL(zk::PrecomputeSlabs<zk::G2>);
 ZK_INSTANTIATE_KERNEL(zk::BaseTableChain<zk::G2>);
 ZK_INSTANTIATE_KERNEL(zk::BaseTableAffine<zk::G2>);
 ZK_INSTANTIATE_KERNEL(zk::FixedBaseMul<zk::G2>);
-ZK_INSTANTIATE_KERNEL(zk::BatchedAddRound<zk::G2, true>);
-ZK_INSTANTIATE_KERNEL(zk::BatchedAddRound<zk::G2, false>);

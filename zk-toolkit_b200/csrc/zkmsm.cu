@@ -399,13 +399,22 @@ static int msm_enqueue_impl(zkmsm_ctx* ctx, const zkmsm_points* ps, const uint32
   // G2 keeps the chunked accumulation (+ the one-launch fix-up): its per-bucket kernel is bound by registers and by
   // the spread of the bucket sizes without pre-reduction rounds (measured 7.9 against 4.7 ms at 2^18)
   if (curve != 1 && tune.acc_G == 0) tune.no_bucket_acc = 1;
+  // the G2 batched-affine kernel keeps two blocks of 128 threads per SM (255 registers), not three
+  if (curve != 1 && tune.batch_blocks == 0) tune.batch_blocks = 2;
   unsigned c = ps->precomp ? ps->c : (ctx->window_override ? ctx->window_override : msm_pick_c((uint32_t)n, false, ps->half));
   if (!msm_fits(n, c, ps->half))
     return fail(ctx, ZKMSM_ERR_INVALID_ARG, "%zu terms at window %u exceed 2^32 sorted pairs; use a wider window", n, c);
   if (world > 1 && world > (1u << (c - 1))) return fail(ctx, ZKMSM_ERR_INVALID_ARG, "bucket-range split: more ranks than buckets");
   MsmPlan p = msm_plan((uint32_t)n, c, ps->precomp, (uint32_t)ps->n, ps->half, true, (uint32_t)ctx->sms * 256u, tune, rank, world);
-  if (curve != 1 && !tune.batch_g2) p.batch_rounds = 0;   // G2: off unless forced (the Fq2 kernel spills)
-  else if (tune.batch_rounds < 0) p.batch_rounds = msm_default_batch_rounds(p, tune);
+  // G2 takes the rounds too since its kernel has the field arithmetic inlined (tu_g2_batch.cu: 1.1 ns per affine
+  // addition against 1.2 ns per mixed addition, and far fewer chunk sums to fix up: 6.64 -> 6.14 ms at 2^18)
+  if (curve != 1 && !tune.batch_g2) p.batch_rounds = 0;
+  else if (tune.batch_rounds < 0) {
+    p.batch_rounds = msm_default_batch_rounds(p, tune);
+    // (G2 gains per addition are small; below three rounds' worth of work the rounds' fixed costs win: a half-size
+    // share at 2^18 measured 3.93 ms with two rounds against 3.74 ms without)
+    if (curve != 1 && p.batch_rounds < 3) p.batch_rounds = 0;
+  }
   int rc;
   uint32_t nseg = (p.nb + SCAN_SEG - 1) / SCAN_SEG + 1;
   if ((rc = ws_reserve(ctx, WS_HIST, sizeof(uint32_t) * p.nb)) || (rc = ws_reserve(ctx, WS_OFFSETS, sizeof(uint32_t) * (p.nb + 1))) ||
