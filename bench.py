@@ -60,7 +60,7 @@ class ClockSampler:
         self.rows, self.proc = [], None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "20", "-i", str(index)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "50", "-i", str(index)], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -366,7 +366,7 @@ def main():
                "api": "zkmsm_g1_msm(ctx, resident CRS points, host scalars) -> host affine point" if world == 1 else
                       "per rank: H2D of 1/N of the scalars + NVLink all-gather of the slices (range split; all of its own under the points split), "
                       "zkmsm_g1_msm_partial_*_device, NCCL all-gather of the partials, zkmsm_g1_combine_enqueue + result"}
-        # clocks / throttle reasons: nvidia-smi samples every 20 ms from the start of the timed steps to the end of the
+        # clocks / throttle reasons: nvidia-smi samples every 50 ms from the start of the timed steps to the end of the
         # end-to-end steps (the same workload under load throughout; K steps alone last only ~60 ms)
         clocks = sampler.stop(t_wall0, time.time()) if sampler else None
         if world == 1:

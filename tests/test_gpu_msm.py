@@ -466,7 +466,7 @@ def test_scalar_longer_than_256_bits(z):
 
 def test_g2_batched_affine_rounds(z, ctx):
     """G2 takes the batched-affine pre-reduction rounds as well (BatchedAddRound<G2>, Fq2 affine law of g2_point.rs /
-    macros.rs:35-163): forced on a small set with every rare case inside the rounds, and the default path at 2^17"""
+    macros.rs:35-163): forced on a small set with every rare case inside the rounds, and the default path at 2^18"""
     g = z.G2Point.g()
     P, Q = g * 11, g * 13
     try:
@@ -491,7 +491,7 @@ def test_g2_batched_affine_rounds(z, ctx):
     finally:
         ctx.set_option("batch_rounds", -1)
         ctx.set_option("batch_T", 0)
-    n = 1 << 17
+    n = 1 << 18                            # three rounds by default from here on (fewer do not pay for G2)
     rnd = random.Random(217)
     dlogs = [rnd.randrange(1, O.R) for _ in range(n)]
     sc = U.rand_scalars(rnd, n)
