@@ -43,6 +43,7 @@ extern "C" {
 #define ZKMSM_ERR_NO_DEVICE (-4)
 #define ZKMSM_ERR_TOO_FEW_POINTS (-5) /* n > points loaded; the reference panics, polynomial.rs:278 */
 #define ZKMSM_ERR_NOMEM (-6)
+#define ZKMSM_ERR_NOT_IN_SUBGROUP (-7) /* ZKMSM_CHECK_SUBGROUP: a loaded point does not have order r */
 
 /* zkmsm_*_load_points flags */
 #define ZKMSM_PRECOMPUTE 1u /* also store 2^(c w) P for every window w (CRS-style static sets) */
@@ -50,6 +51,10 @@ extern "C" {
                              * generator).  Scalars must then be < r; s > (r-1)/2 is evaluated as (r-s)(-P), which
                              * saves the carry window.  Without the flag scalars are raw integers < 2^255 and nothing
                              * is assumed about the points (curves/macros.rs:10-21). */
+
+#define ZKMSM_CHECK_SUBGROUP 4u /* verify r P = AtInfinity for every point at load (one 255-bit multiplication per point
+                                * on the device); a point outside the subgroup fails the load with
+                                * ZKMSM_ERR_NOT_IN_SUBGROUP.  Without it ZKMSM_SUBGROUP is the caller's unchecked claim. */
 
 typedef struct zkmsm_ctx zkmsm_ctx;       /* one CUDA device + stream + workspace */
 typedef struct zkmsm_points zkmsm_points; /* device-resident point set (G1 or G2) */

@@ -238,6 +238,15 @@ void emu_policy(uint32_t n, uint32_t c, int precomp, int half, uint32_t acc_slot
   out[0] = c; out[1] = p.L; out[2] = rounds; out[3] = T; out[4] = (uint32_t)((items + T - 1) / T); out[5] = p.K; out[6] = p.coop;
   out[7] = p.acc_G; out[8] = p.acc_cap; out[9] = p.nb;
 }
+// ZKMSM_CHECK_SUBGROUP: number of points with r P != AtInfinity
+uint32_t emu_g1_subgroup_check(const uint32_t* xy, const uint8_t* inf, uint32_t n) {
+  HostExec ex;
+  std::vector<Affine<Fp>> pts(n + 1);
+  ex.launch<LoadPoints<G1>>(n, n, xy, inf, pts.data());
+  uint32_t bad = 0;
+  ex.launch<SubgroupCheck<G1>>(n, n, (const Affine<Fp>*)pts.data(), &bad);
+  return bad;
+}
 // n * windows must stay below 2^32 sorted pairs (the kernels' positions are 32-bit): the product rejects the rest
 int emu_fits(uint64_t n, uint32_t c, int half) { return msm_fits(n, c, half != 0) ? 1 : 0; }
 void emu_plan(uint32_t n, uint32_t c, int precomp, uint32_t* out) {

@@ -502,3 +502,23 @@ def test_g2_batched_affine_rounds(z, ctx):
     ctx.profile(False)
     assert "batched_add_first" in names and "fixup_direct" in names
     assert U.g2_from_array(out, inf) == O.scalar_mul(O.G2_GEN, sum(k * s for k, s in zip(dlogs, sc)) % O.R)
+
+
+def test_subgroup_check_at_load(z, ctx):
+    """ZKMSM_CHECK_SUBGROUP: a ZKMSM_SUBGROUP set is the caller's claim that every point has order r; with the check
+    the device verifies it and refuses a curve point outside the subgroup (for which the folded scalars would give a
+    different point than the reference's raw multiple)"""
+    from tests.test_host_emu_msm import _g1_point_outside_subgroup
+    bad = _g1_point_outside_subgroup()
+    good = [O.scalar_mul(O.G1_GEN, k) for k in (3, 5, 7)]
+    xy, inf = U.g1_points_to_array(good)
+    pts = ctx.load_points(1, xy, None, precompute=True, in_subgroup=True, check_subgroup=True)
+    assert U.g1_from_array(*ctx.msm(pts, z.scalars_to_array([O.R - 1, 2, 3]))) == O.msm(good, [O.R - 1, 2, 3])
+    xy, inf = U.g1_points_to_array(good + [bad])
+    with pytest.raises(z.ZkmsmError) as e:
+        ctx.load_points(1, xy, None, precompute=True, in_subgroup=True, check_subgroup=True)
+    assert e.value.code == -7
+    # without the subgroup claim nothing is assumed and the raw multiple comes out, as in the reference
+    plain = ctx.load_points(1, xy, None)
+    sc = [5, 6, 7, (1 << 200) + 12345]
+    assert U.g1_from_array(*ctx.msm(plain, z.scalars_to_array(sc))) == O.msm(good + [bad], sc)

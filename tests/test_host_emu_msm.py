@@ -420,3 +420,30 @@ def test_emu_g2_batched_affine_rounds(lib, monkeypatch):
     for precomp, c in ((1, 4), (3, 5)):
         rc, got = emu_g2(lib, pts, sc, c=c, precomp=precomp)
         assert rc == 0 and got == U.expected_from_dlogs(O.G2_GEN, dlogs, sc)
+
+
+def _g1_point_outside_subgroup():
+    """a point of E(Fq): y^2 = x^3 + 4 that is not a multiple of the generator (the cofactor is ~2^126, so the first
+    x with a square right-hand side is outside the order-r subgroup with overwhelming probability; checked below)"""
+    q = O.Q
+    x = 5
+    while True:
+        rhs = (x ** 3 + 4) % q
+        y = pow(rhs, (q + 1) // 4, q)            # q = 3 (mod 4)
+        if y * y % q == rhs:
+            p = O.g1(x, y)
+            if O.scalar_mul(p, O.R) is not O.INF:
+                return p
+        x += 1
+
+
+def test_emu_subgroup_check(lib, g1_set):
+    """ZKMSM_CHECK_SUBGROUP's kernel: r P = AtInfinity for multiples of the generator and for AtInfinity itself, not
+    for a curve point outside the subgroup"""
+    dlogs, pts = g1_set
+    lib.emu_g1_subgroup_check.restype = ctypes.c_uint32
+    xy, inf = U.g1_points_to_array(pts[:6] + [O.INF])
+    assert lib.emu_g1_subgroup_check(ptr(xy), ptr(inf, u8p), 7) == 0
+    bad = _g1_point_outside_subgroup()
+    xy, inf = U.g1_points_to_array([pts[0], bad, pts[1], bad])
+    assert lib.emu_g1_subgroup_check(ptr(xy), ptr(inf, u8p), 4) == 2

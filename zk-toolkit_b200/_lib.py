@@ -11,10 +11,11 @@ LIB_PATH = os.environ.get("ZKMSM_LIB") or os.path.join(_HERE, "libzkmsm.so")   #
 OK = 0
 ERR_NAMES = {
     -1: "ZKMSM_ERR_INVALID_ARG", -2: "ZKMSM_ERR_CUDA", -3: "ZKMSM_ERR_SCALAR_RANGE",
-    -4: "ZKMSM_ERR_NO_DEVICE", -5: "ZKMSM_ERR_TOO_FEW_POINTS", -6: "ZKMSM_ERR_NOMEM",
+    -4: "ZKMSM_ERR_NO_DEVICE", -5: "ZKMSM_ERR_TOO_FEW_POINTS", -6: "ZKMSM_ERR_NOMEM", -7: "ZKMSM_ERR_NOT_IN_SUBGROUP",
 }
 PRECOMPUTE = 1
 SUBGROUP = 2
+CHECK_SUBGROUP = 4
 G1_WORDS, G2_WORDS = 24, 48
 G1_PARTIAL_WORDS, G2_PARTIAL_WORDS = 48, 96
 GROTH16_PARTIAL_WORDS = 192

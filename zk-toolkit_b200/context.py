@@ -100,10 +100,10 @@ class Context:
         return L.G1_WORDS if group == 1 else L.G2_WORDS
 
     @staticmethod
-    def _flags(precompute, in_subgroup):
-        return (L.PRECOMPUTE if precompute else 0) | (L.SUBGROUP if in_subgroup else 0)
+    def _flags(precompute, in_subgroup, check_subgroup=False):
+        return (L.PRECOMPUTE if precompute else 0) | (L.SUBGROUP if in_subgroup else 0) | (L.CHECK_SUBGROUP if check_subgroup else 0)
 
-    def load_points(self, group, xy, inf=None, precompute=False, in_subgroup=False):
+    def load_points(self, group, xy, inf=None, precompute=False, in_subgroup=False, check_subgroup=False):
         xy = L.as_u32(xy, self._words(group)).reshape(-1, self._words(group))
         n = xy.shape[0]
         if inf is not None:
@@ -111,7 +111,7 @@ class Context:
             assert inf.shape == (n,)
         fn = self.lib.zkmsm_g1_load_points if group == 1 else self.lib.zkmsm_g2_load_points
         h = ctypes.c_void_p()
-        self._check(fn(self.h, L.dptr(xy), L.dptr(inf), n, self._flags(precompute, in_subgroup), ctypes.byref(h)))
+        self._check(fn(self.h, L.dptr(xy), L.dptr(inf), n, self._flags(precompute, in_subgroup, check_subgroup), ctypes.byref(h)))
         return PointSet(self, h, group, n, precompute)
 
     def points_from_scalars(self, group, base_xy, scalars, precompute=False, in_subgroup=False):

@@ -1043,6 +1043,28 @@ template <class C> struct PrecomputeSlabs {
   }
 };
 
+// ---------------------------------------------------------------- subgroup membership (opt-in at load time)
+// ZKMSM_SUBGROUP sets fold a scalar s > (r-1)/2 to (r - s)(-P), which is s P only when P has order r; both curves
+// have cofactors, so a point that is on the curve but outside the subgroup would silently give another result than
+// the reference's raw multiple (macros.rs:10-21).  With ZKMSM_CHECK_SUBGROUP the load verifies r P = AtInfinity for
+// every point (MSB-first double-and-add over the 255 bits of r, mixed additions) and counts the failures.
+template <class C> struct SubgroupCheck {
+  typedef typename C::F F;
+  static const char* name() { return "subgroup_check"; }
+  static ZK_HD void run(uint32_t tid, uint32_t n, const Affine<F>* pts, uint32_t* bad) {
+    if (tid >= n) return;
+    const Affine<F> p = pts[tid];
+    if (is_inf(p)) return;
+    XYZZ<F> acc;
+    from_affine(acc, p);
+    for (int bit = 253; bit >= 0; bit--) {          // bit 254 is r's top bit: acc starts at P
+      xyzz_dbl(acc);
+      if ((FR_P[bit >> 5] >> (bit & 31)) & 1u) xyzz_madd(acc, p);
+    }
+    if (!is_inf(acc)) zk_atomic_add(bad, 1u);
+  }
+};
+
 // ---------------------------------------------------------------- fixed-base scalar multiplication
 // (the reference's `g * k`, impl_scalar_mul_point!, macros.rs:2-32, for many k at once; used for
 //  CRS-style point generation, crs.rs:88-116)

@@ -9,3 +9,4 @@ ZK_INSTANTIATE_KERNEL(zk::PrecomputeSlabs<zk::G1>);
 ZK_INSTANTIATE_KERNEL(zk::BaseTableChain<zk::G1>);
 ZK_INSTANTIATE_KERNEL(zk::BaseTableAffine<zk::G1>);
 ZK_INSTANTIATE_KERNEL(zk::FixedBaseMul<zk::G1>);
+ZK_INSTANTIATE_KERNEL(zk::SubgroupCheck<zk::G1>);

@@ -9,3 +9,4 @@ ZK_INSTANTIATE_KERNEL(zk::PrecomputeSlabs<zk::G2>);
 ZK_INSTANTIATE_KERNEL(zk::BaseTableChain<zk::G2>);
 ZK_INSTANTIATE_KERNEL(zk::BaseTableAffine<zk::G2>);
 ZK_INSTANTIATE_KERNEL(zk::FixedBaseMul<zk::G2>);
+ZK_INSTANTIATE_KERNEL(zk::SubgroupCheck<zk::G2>);

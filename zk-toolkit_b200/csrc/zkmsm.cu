@@ -258,8 +258,17 @@ extern "C" int zkmsm_profile_read(zkmsm_ctx* ctx, int max_entries, char* names, 
 // ------------------------------------------------------------------------------------------------
 // point sets
 template <class C>
-static int finish_point_set(zkmsm_ctx* ctx, zkmsm_points* ps, CudaExec& ex) {
+static int finish_point_set(zkmsm_ctx* ctx, zkmsm_points* ps, CudaExec& ex, unsigned flags = 0) {
   typedef typename C::F F;
+  if ((flags & ZKMSM_CHECK_SUBGROUP) && ps->n > 0) {   // on slab 0, before the other slabs are derived from it
+    CU(ctx, cudaMemsetAsync(&ctx->d_res->aux_err, 0, sizeof(uint32_t), ctx->stream));
+    ex.template launch<SubgroupCheck<C>>((uint32_t)ps->n, (uint32_t)ps->n, (const Affine<F>*)ps->d_pts, &ctx->d_res->aux_err);
+    if (ex.err != cudaSuccess) return fail(ctx, ZKMSM_ERR_CUDA, "subgroup check: %s", cudaGetErrorString(ex.err));
+    uint32_t bad = 0;
+    CU(ctx, cudaMemcpyAsync(&bad, &ctx->d_res->aux_err, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    if (bad) return fail(ctx, ZKMSM_ERR_NOT_IN_SUBGROUP, "%u of %zu points are not in the order-r subgroup", bad, ps->n);
+  }
   if (ps->precomp && ps->n > 0)
     ex.template launch<PrecomputeSlabs<C>>((uint32_t)ps->n, (uint32_t)ps->n, (uint32_t)ps->n, ps->c, ps->W,
                                            msm_wide_windows(ps->c, ps->W, ps->half, true), (Affine<F>*)ps->d_pts);
@@ -312,7 +321,7 @@ static int load_points_impl(zkmsm_ctx* ctx, const uint32_t* xy, const uint8_t* i
   CudaExec ex(ctx->stream);
   ex.template launch<LoadPoints<C>>((uint32_t)n, (uint32_t)n, (const uint32_t*)d_canon, (const uint8_t*)d_inf,
                                     (Affine<F>*)ps->d_pts);
-  rc = finish_point_set<C>(ctx, ps, ex);
+  rc = finish_point_set<C>(ctx, ps, ex, flags);
   if (rc) { zkmsm_points_free(ctx, ps); *out = nullptr; }
   return rc;
 }

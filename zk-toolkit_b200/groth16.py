@@ -37,12 +37,13 @@ def _proof_from_limbs(out, inf):
 
 
 class DeviceCRS:
-    """CRS vectors of crs.rs:17-43 resident on one GPU (zkmsm_crs_load).  in_subgroup=True asserts, unchecked, that
-    every CRS point has order r -- true for any CRS built as multiples of the generators (crs.rs:65-135); pass
-    False for points of unknown provenance (the device then assumes nothing, macros.rs:10-21)."""
+    """CRS vectors of crs.rs:17-43 resident on one GPU (zkmsm_crs_load).  in_subgroup=True asserts that every CRS point
+    has order r -- true for any CRS built as multiples of the generators (crs.rs:65-135); check_subgroup=True makes
+    the device verify it at load time (r P = AtInfinity for every point, ZkmsmError otherwise).  Pass
+    in_subgroup=False for points of unknown provenance: the device then assumes nothing (macros.rs:10-21)."""
 
     def __init__(self, g1_alpha, g1_beta, g1_delta, g1_xi, g1_uvw_wit, g1_xt_by_delta, g2_beta, g2_delta, g2_xi,
-                 precompute=True, ctx=None, in_subgroup=True):
+                 precompute=True, ctx=None, in_subgroup=True, check_subgroup=False):
         p1 = lambda pts: G1Point.pack(list(pts))
         xi, xi_inf = p1(g1_xi)
         wit, wit_inf = p1(g1_uvw_wit)
@@ -53,18 +54,19 @@ class DeviceCRS:
                 raise ValueError("alpha, beta, delta must not be AtInfinity")
         self._load(dict(g1_alpha=g1_alpha.limbs(), g1_beta=g1_beta.limbs(), g1_delta=g1_delta.limbs(), g1_xi=xi,
                         g1_uvw_wit=wit, g1_xt_by_delta=xt, g2_beta=g2_beta.limbs(), g2_delta=g2_delta.limbs(), g2_xi=xi2),
-                   dict(g1_xi=xi_inf, g1_uvw_wit=wit_inf, g1_xt_by_delta=xt_inf, g2_xi=xi2_inf), precompute, ctx, in_subgroup)
+                   dict(g1_xi=xi_inf, g1_uvw_wit=wit_inf, g1_xt_by_delta=xt_inf, g2_xi=xi2_inf), precompute, ctx, in_subgroup,
+                   check_subgroup)
 
     @classmethod
-    def from_arrays(cls, arrs, precompute=True, ctx=None, in_subgroup=True):
+    def from_arrays(cls, arrs, precompute=True, ctx=None, in_subgroup=True, check_subgroup=False):
         """arrs: dict of canonical limb arrays (for large synthetic instances built on the device):
         g1_xi (n,24), g1_uvw_wit, g1_xt_by_delta, g2_xi (n,48), and single points g1_alpha, g1_beta,
         g1_delta (24,), g2_beta, g2_delta (48,)."""
         self = cls.__new__(cls)
-        self._load(arrs, {}, precompute, ctx, in_subgroup)
+        self._load(arrs, {}, precompute, ctx, in_subgroup, check_subgroup)
         return self
 
-    def _load(self, arrs, infs, precompute, ctx, in_subgroup):
+    def _load(self, arrs, infs, precompute, ctx, in_subgroup, check_subgroup=False):
         self.ctx = ctx or default_context()
         self.handle = None
         keep = {}
@@ -84,7 +86,7 @@ class DeviceCRS:
         assert len(keep["g2_xi"]) == self.n
         d.n, d.n_wit, d.n_xt = self.n, self.n_wit, self.n_xt
         self.g1_delta = G1Point.from_limbs(keep["g1_delta"][0], False)
-        flags = (L.PRECOMPUTE if precompute else 0) | (L.SUBGROUP if in_subgroup else 0)
+        flags = (L.PRECOMPUTE if precompute else 0) | (L.SUBGROUP if in_subgroup else 0) | (L.CHECK_SUBGROUP if check_subgroup else 0)
         h = ctypes.c_void_p()
         self.ctx._check(self.ctx.lib.zkmsm_crs_load(self.ctx.h, ctypes.byref(d), flags, ctypes.byref(h)))
         self.handle = h
