@@ -3,6 +3,5 @@
 #define ZK_MIN_BLOCKS 3
 #include "launch.cuh"
 #include "msm.cuh"
-ZK_INSTANTIATE_KERNEL(zk::PairCount);
 ZK_INSTANTIATE_KERNEL(zk::BatchedAddRound<zk::G1, true>);
 ZK_INSTANTIATE_KERNEL(zk::BatchedAddRound<zk::G1, false>);

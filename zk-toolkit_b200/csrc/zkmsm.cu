@@ -128,7 +128,7 @@ static int ws_reserve(zkmsm_ctx* ctx, int slot, size_t bytes) {
   return ZKMSM_OK;
 }
 
-extern "C" const char* zkmsm_version(void) { return "zkmsm 0.1 (sm_100a; BLS12-381 G1/G2 Pippenger, XYZZ, 12x32-bit Montgomery)"; }
+extern "C" const char* zkmsm_version(void) { return "zkmsm 0.2 (sm_100a; BLS12-381 G1/G2 Pippenger, batched-affine + XYZZ, 12x32-bit Montgomery; Groth16 prove)"; }
 
 extern "C" int zkmsm_create(int device, zkmsm_ctx** out) {
   if (!out) return ZKMSM_ERR_INVALID_ARG;

@@ -2,7 +2,7 @@
 
 The reference's own pipeline cannot produce a 2^18-constraint instance: `QAP::build` is O(n^3) over the
 integer domain 1..n (qap/qap.rs:33-97).  SURVEY.md section 7 gives a construction the reference verifier
-(verifier.rs:36-53) still accepts; it only sees CRS points, so the proof verifies iff all five MSMs
+(verifier.rs:36-53) still accepts; it only sees CRS points, so the proof verifies iff all of the prover's MSMs
 are right:
 
   * random trapdoor (alpha, beta, gamma, delta, x), random coefficient vectors u, v (degree < n) and
