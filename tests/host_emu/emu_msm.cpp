@@ -129,7 +129,7 @@ int emu_g1_msm_sharded(const uint32_t* xy, const uint32_t* scalars, uint32_t n, 
   }
   HostExec ex;
   uint32_t err = 0;
-  ex.launch<CombinePartials<G1>>(1u, k, (const XYZZ<Fp>*)parts.data(), out_xy, out_inf, &err);
+  ex.launch<CombinePartials<G1>>(1u, k, (const XYZZ<Fp>*)parts.data(), (uint32_t)(sizeof(XYZZ<Fp>) / 4), out_xy, out_inf, &err);
   return err ? -3 : 0;
 }
 // bucket-range split: `world` ranks each see all n scalars and the whole precomputed set, own 1/world of the buckets
@@ -143,7 +143,7 @@ int emu_g1_msm_range(const uint32_t* xy, const uint32_t* scalars, uint32_t n, ui
   }
   HostExec ex;
   uint32_t err = 0;
-  ex.launch<CombinePartials<G1>>(1u, world, (const XYZZ<Fp>*)parts.data(), out_xy, out_inf, &err);
+  ex.launch<CombinePartials<G1>>(1u, world, (const XYZZ<Fp>*)parts.data(), (uint32_t)(sizeof(XYZZ<Fp>) / 4), out_xy, out_inf, &err);
   return err ? -3 : 0;
 }
 uint32_t emu_last_fallback() { return g_last_fallback; }
@@ -162,7 +162,7 @@ int emu_g1_msm_partial(const uint32_t* xy, const uint32_t* scalars, uint32_t n, 
 int emu_g1_combine(const uint32_t* partials, uint32_t k, uint32_t* out_xy, uint32_t* out_inf) {
   HostExec ex;
   uint32_t err = 0;
-  ex.launch<CombinePartials<G1>>(1u, k, (const XYZZ<Fp>*)partials, out_xy, out_inf, &err);
+  ex.launch<CombinePartials<G1>>(1u, k, (const XYZZ<Fp>*)partials, (uint32_t)(sizeof(XYZZ<Fp>) / 4), out_xy, out_inf, &err);
   return err ? -3 : 0;
 }
 // `base * k_i` for a vector of raw 256-bit scalars (FixedBaseMul path)

@@ -450,7 +450,7 @@ __global__ void __launch_bounds__(kMaxThreads) finish_kernel(uint32_t nwin, uint
 
 // sum of k <= 32 partial points (multi-GPU combine): lane i holds partial i, 5-level tree across lanes
 template <class C>
-__global__ void __launch_bounds__(kMaxThreads) combine_kernel(uint32_t k, const XYZZ<typename C::F>* parts,
+__global__ void __launch_bounds__(kMaxThreads) combine_kernel(uint32_t k, const XYZZ<typename C::F>* parts, uint32_t stride_words,
                                                            uint32_t* out_affine, uint32_t* out_inf, uint32_t* err) {
   typedef typename C::F F;
   extern __shared__ __align__(16) uint32_t smem[];
@@ -458,11 +458,14 @@ __global__ void __launch_bounds__(kMaxThreads) combine_kernel(uint32_t k, const 
   Flags* fl = flags_of<F>(smem);
   const int l = threadIdx.x & 31;
   bool present = (uint32_t)l < k;
-  if (present && is_poisoned(parts[l])) {   // a rank saw an out-of-range scalar (PoisonPartial, msm.cuh)
+  // partial l sits stride_words 32-bit words after partial l - 1 (packed arrays: sizeof(XYZZ) / 4; the per-rank
+  // blobs of a distributed proof: ZKMSM_GROTH16_PARTIAL_WORDS)
+  const XYZZ<F>* mine = reinterpret_cast<const XYZZ<F>*>(reinterpret_cast<const uint32_t*>(parts) + (size_t)(present ? l : 0) * stride_words);
+  if (present && is_poisoned(*mine)) {   // a rank saw an out-of-range scalar (PoisonPartial, msm.cuh)
     if (threadIdx.x < 32) atomicOr(err, ERR_SCALAR_RANGE);
     present = false;
   }
-  point_load_global(S, S_ACC, parts + l, present);
+  point_load_global(S, S_ACC, mine, present);
   __syncthreads();
   lane_tree(S, fl, k);
   if (threadIdx.x == 0) {

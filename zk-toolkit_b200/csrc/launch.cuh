@@ -83,7 +83,7 @@ cudaError_t zk_coop_row_sum_g1(cudaStream_t st, uint32_t nwin, uint32_t pitch_in
                                const XYZZ<Mont<FqCfg>>* in, uint32_t pitch_out, XYZZ<Mont<FqCfg>>* out);
 cudaError_t zk_coop_finish_g1(cudaStream_t st, uint32_t nwin, uint32_t pitch, uint32_t c, const XYZZ<Mont<FqCfg>>* arr,
                               XYZZ<Mont<FqCfg>>* out_xyzz, uint32_t* out_affine, uint32_t* out_inf);
-cudaError_t zk_coop_combine_g1(cudaStream_t st, uint32_t k, const XYZZ<Mont<FqCfg>>* parts, uint32_t* out_affine,
+cudaError_t zk_coop_combine_g1(cudaStream_t st, uint32_t k, const XYZZ<Mont<FqCfg>>* parts, uint32_t stride_words, uint32_t* out_affine,
                                uint32_t* out_inf, uint32_t* err);
 template <class C> struct Finish;
 struct Fp2;
@@ -102,8 +102,8 @@ cudaError_t zk_opt_in_shared_memory_coop_g2();
 cudaError_t zk_opt_in_shared_memory_ntt();
 cudaError_t zk_coop_bucket_reduce_g2(cudaStream_t st, const MsmPlan& p, const uint32_t* offsets, const XYZZ<Fp2>* buckets,
                                      XYZZ<Fp2>* out, int tree);
-cudaError_t zk_coop_combine_g2(cudaStream_t st, uint32_t k, const XYZZ<Fp2>* parts, uint32_t* out_affine, uint32_t* out_inf,
-                               uint32_t* err);
+cudaError_t zk_coop_combine_g2(cudaStream_t st, uint32_t k, const XYZZ<Fp2>* parts, uint32_t stride_words, uint32_t* out_affine,
+                               uint32_t* out_inf, uint32_t* err);
 cudaError_t zk_coop_row_sum_g2(cudaStream_t st, uint32_t nwin, uint32_t pitch_in, uint32_t m, uint32_t per_block,
                                const XYZZ<Fp2>* in, uint32_t pitch_out, XYZZ<Fp2>* out);
 struct FrCfg;

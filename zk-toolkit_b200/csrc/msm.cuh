@@ -992,12 +992,14 @@ template <class C> struct PoisonPartial {   // after Finish, when the partial le
 template <class C> struct CombinePartials {
   typedef typename C::F F;
   static const char* name() { return "combine_partials"; }
-  static ZK_HD void run(uint32_t tid, uint32_t k, const XYZZ<F>* parts, uint32_t* out_affine, uint32_t* out_inf, uint32_t* err) {
+  // stride_words: distance between consecutive partials in 32-bit words (sizeof(XYZZ<F>) / 4 for a packed array)
+  static ZK_HD void run(uint32_t tid, uint32_t k, const XYZZ<F>* parts, uint32_t stride_words, uint32_t* out_affine, uint32_t* out_inf,
+                        uint32_t* err) {
     if (tid != 0) return;
     XYZZ<F> acc;
     set_inf(acc);
     for (uint32_t i = 0; i < k; i++) {
-      XYZZ<F> q = parts[i];
+      XYZZ<F> q = *reinterpret_cast<const XYZZ<F>*>(reinterpret_cast<const uint32_t*>(parts) + (size_t)i * stride_words);
       if (is_poisoned(q)) { zk_atomic_or(err, ERR_SCALAR_RANGE); continue; }
       xyzz_add_ilp(acc, q);
     }

@@ -40,10 +40,10 @@ cudaError_t zk_coop_finish_g1(cudaStream_t st, uint32_t nwin, uint32_t pitch, ui
   return cudaGetLastError();
 }
 
-cudaError_t zk_coop_combine_g1(cudaStream_t st, uint32_t k, const XYZZ<Fp>* parts, uint32_t* out_affine, uint32_t* out_inf,
-                               uint32_t* err) {
+cudaError_t zk_coop_combine_g1(cudaStream_t st, uint32_t k, const XYZZ<Fp>* parts, uint32_t stride_words, uint32_t* out_affine,
+                               uint32_t* out_inf, uint32_t* err) {
   const size_t smem = coop::smem_bytes<Fp>();
-  coop::combine_kernel<G1><<<1, coop::block_threads<Fp>(), smem, st>>>(k, parts, out_affine, out_inf, err);
+  coop::combine_kernel<G1><<<1, coop::block_threads<Fp>(), smem, st>>>(k, parts, stride_words, out_affine, out_inf, err);
   return cudaGetLastError();
 }
 

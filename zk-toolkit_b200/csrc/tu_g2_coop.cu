@@ -32,10 +32,10 @@ cudaError_t zk_coop_row_sum_g2(cudaStream_t st, uint32_t nwin, uint32_t pitch_in
   return cudaGetLastError();
 }
 
-cudaError_t zk_coop_combine_g2(cudaStream_t st, uint32_t k, const XYZZ<Fp2>* parts, uint32_t* out_affine, uint32_t* out_inf,
-                               uint32_t* err) {
+cudaError_t zk_coop_combine_g2(cudaStream_t st, uint32_t k, const XYZZ<Fp2>* parts, uint32_t stride_words, uint32_t* out_affine,
+                               uint32_t* out_inf, uint32_t* err) {
   const size_t smem = coop::smem_bytes<Fp2>();
-  coop::combine_kernel<G2><<<1, coop::block_threads<Fp2>(), smem, st>>>(k, parts, out_affine, out_inf, err);
+  coop::combine_kernel<G2><<<1, coop::block_threads<Fp2>(), smem, st>>>(k, parts, stride_words, out_affine, out_inf, err);
   return cudaGetLastError();
 }
 

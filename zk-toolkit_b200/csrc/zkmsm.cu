@@ -30,6 +30,8 @@ struct alignas(16) ResultBlock {      // device + pinned host mirror
   uint32_t err;
   uint32_t big;           // AccumulateBuckets' "a bucket is over the cap" flag (device side only)
   uint32_t aux_err;       // zkmsm_groth16_prove: r or s out of range
+  uint32_t proof[96];     // zkmsm_groth16_combine: A | B | C
+  uint32_t proof_inf[4];
 };
 
 // one captured MSM launch sequence (CUDA graph): replayed while the same point set, sizes, buffers and options recur
@@ -693,6 +695,19 @@ extern "C" int zkmsm_g2_msm_partial_range_device(zkmsm_ctx* ctx, const zkmsm_poi
   return partial_device_impl<G2>(ctx, ps, ds, n, 2, d_out, rank, world);
 }
 
+// one combine kernel: k partials, stride_words apart, summed in order and converted to canonical affine; a poisoned
+// partial raises d_res->err
+template <class C>
+static void combine_launch(zkmsm_ctx* ctx, CudaExec& ex, const XYZZ<typename C::F>* d_parts, uint32_t k, uint32_t stride_words,
+                           uint32_t* out_affine, uint32_t* out_inf) {
+  if (std::is_same<C, G1>::value && k > 2 && k <= 32 && !ctx->tune.no_coop)
+    ex.timed("combine_partials", k, 1, [&] { return zk_coop_combine_g1(ctx->stream, k, (const XYZZ<Fp>*)d_parts, stride_words, out_affine, out_inf, &ctx->d_res->err); });
+  else if (std::is_same<C, G2>::value && k > 1 && k <= 32 && !ctx->tune.no_coop)   // a lone thread needs ~0.1 ms per G2 addition
+    ex.timed("combine_partials", k, 1, [&] { return zk_coop_combine_g2(ctx->stream, k, (const XYZZ<Fp2>*)d_parts, stride_words, out_affine, out_inf, &ctx->d_res->err); });
+  else
+    ex.template launch<CombinePartials<C>>(1u, k, d_parts, stride_words, out_affine, out_inf, &ctx->d_res->err);
+}
+
 // enqueue_only: stream-ordered, the result is fetched later with zkmsm_g{1,2}_msm_result
 template <class C>
 static int combine_impl(zkmsm_ctx* ctx, const uint32_t* parts, bool on_device, size_t k, uint32_t* out_xy, int* out_is_inf,
@@ -709,12 +724,7 @@ static int combine_impl(zkmsm_ctx* ctx, const uint32_t* parts, bool on_device, s
   }
   CU(ctx, cudaMemsetAsync(&ctx->d_res->err, 0, sizeof(uint32_t), ctx->stream));
   CudaExec ex(ctx->stream, nullptr, ctx->tune.no_coop != 0);
-  if (std::is_same<C, G1>::value && k > 2 && k <= 32 && !ctx->tune.no_coop)
-    ex.timed("combine_partials", (uint32_t)k, 1, [&] { return zk_coop_combine_g1(ctx->stream, (uint32_t)k, (const XYZZ<Fp>*)d_parts, ctx->d_res->affine, &ctx->d_res->inf, &ctx->d_res->err); });
-  else if (std::is_same<C, G2>::value && k > 1 && k <= 32 && !ctx->tune.no_coop)   // a lone thread needs ~0.1 ms per G2 addition
-    ex.timed("combine_partials", (uint32_t)k, 1, [&] { return zk_coop_combine_g2(ctx->stream, (uint32_t)k, (const XYZZ<Fp2>*)d_parts, ctx->d_res->affine, &ctx->d_res->inf, &ctx->d_res->err); });
-  else
-    ex.template launch<CombinePartials<C>>(1u, (uint32_t)k, d_parts, ctx->d_res->affine, &ctx->d_res->inf, &ctx->d_res->err);
+  combine_launch<C>(ctx, ex, d_parts, (uint32_t)k, (uint32_t)(sizeof(XYZZ<F>) / 4), ctx->d_res->affine, &ctx->d_res->inf);
   if (ex.err != cudaSuccess) return fail(ctx, ZKMSM_ERR_CUDA, "combine: %s", cudaGetErrorString(ex.err));
   ctx->pending = 1;
   ctx->pending_words = C::AFF_LIMBS;
@@ -1177,17 +1187,31 @@ extern "C" int zkmsm_groth16_prove_partial(zkmsm_ctx* ctx, zkmsm_crs* crs, const
 
 extern "C" int zkmsm_groth16_combine(zkmsm_ctx* ctx, const uint32_t* partials, size_t world, uint32_t* proof_out, int* inf_out) {
   if (!ctx || !partials || !proof_out || !inf_out || world == 0 || world > 4096) return fail(ctx, ZKMSM_ERR_INVALID_ARG, "bad argument");
-  uint32_t* tmp = (uint32_t*)malloc(sizeof(uint32_t) * 96 * world);
-  if (!tmp) return fail(ctx, ZKMSM_ERR_NOMEM, "host allocation");
-  int rc = ZKMSM_OK;
-  const int words[3] = {48, 96, 48}, src[3] = {0, 48, 144}, at[3] = {0, 24, 72};
-  for (int i = 0; i < 3 && !rc; i++) {
-    for (size_t k = 0; k < world; k++) memcpy(tmp + k * words[i], partials + k * ZKMSM_GROTH16_PARTIAL_WORDS + src[i], sizeof(uint32_t) * words[i]);
-    rc = i == 1 ? combine_impl<G2>(ctx, tmp, false, world, proof_out + at[i], &inf_out[i])
-                : combine_impl<G1>(ctx, tmp, false, world, proof_out + at[i], &inf_out[i]);
+  CU(ctx, cudaSetDevice(ctx->device));
+  // one upload of the per-rank blobs, three combine kernels reading them in place (stride = one blob), one read-back
+  const size_t bytes = sizeof(uint32_t) * ZKMSM_GROTH16_PARTIAL_WORDS * world;
+  int rc = ws_reserve(ctx, WS_MISC, bytes);
+  if (rc) return rc;
+  uint32_t* d = (uint32_t*)ctx->ws[WS_MISC];
+  CU(ctx, cudaMemcpyAsync(d, partials, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  CU(ctx, cudaMemsetAsync(&ctx->d_res->err, 0, sizeof(uint32_t), ctx->stream));
+  CudaExec ex(ctx->stream, nullptr, ctx->tune.no_coop != 0);
+  ResultBlock* r = ctx->d_res;
+  combine_launch<G1>(ctx, ex, (const XYZZ<Fp>*)d, (uint32_t)world, ZKMSM_GROTH16_PARTIAL_WORDS, r->proof, &r->proof_inf[0]);
+  combine_launch<G2>(ctx, ex, (const XYZZ<Fp2>*)(d + 48), (uint32_t)world, ZKMSM_GROTH16_PARTIAL_WORDS, r->proof + 24, &r->proof_inf[1]);
+  combine_launch<G1>(ctx, ex, (const XYZZ<Fp>*)(d + 144), (uint32_t)world, ZKMSM_GROTH16_PARTIAL_WORDS, r->proof + 72, &r->proof_inf[2]);
+  if (ex.err != cudaSuccess) return fail(ctx, ZKMSM_ERR_CUDA, "groth16 combine: %s", cudaGetErrorString(ex.err));
+  CU(ctx, cudaMemcpyAsync(ctx->h_res, ctx->d_res, sizeof(ResultBlock), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->pending = 0;
+  if (ctx->h_res->err & ERR_SCALAR_RANGE) return fail(ctx, ZKMSM_ERR_SCALAR_RANGE, "a rank's share saw a scalar out of range");
+  const int words[3] = {24, 48, 24}, at[3] = {0, 24, 72};
+  for (int i = 0; i < 3; i++) {
+    inf_out[i] = ctx->h_res->proof_inf[i] ? 1 : 0;
+    if (inf_out[i]) memset(proof_out + at[i], 0, sizeof(uint32_t) * words[i]);
+    else memcpy(proof_out + at[i], ctx->h_res->proof + at[i], sizeof(uint32_t) * words[i]);
   }
-  free(tmp);
-  return rc;
+  return ZKMSM_OK;
 }
 
 // ------------------------------------------------------------------------------------------------
