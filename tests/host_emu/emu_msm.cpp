@@ -165,6 +165,13 @@ int emu_g1_combine(const uint32_t* partials, uint32_t k, uint32_t* out_xy, uint3
   ex.launch<CombinePartials<G1>>(1u, k, (const XYZZ<Fp>*)partials, (uint32_t)(sizeof(XYZZ<Fp>) / 4), out_xy, out_inf, &err);
   return err ? -3 : 0;
 }
+// the same over partials that sit stride_words apart (the per-rank blobs of a distributed proof, zkmsm_groth16_combine)
+int emu_g1_combine_strided(const uint32_t* partials, uint32_t k, uint32_t stride_words, uint32_t* out_xy, uint32_t* out_inf) {
+  HostExec ex;
+  uint32_t err = 0;
+  ex.launch<CombinePartials<G1>>(1u, k, (const XYZZ<Fp>*)partials, stride_words, out_xy, out_inf, &err);
+  return err ? -3 : 0;
+}
 // `base * k_i` for a vector of raw 256-bit scalars (FixedBaseMul path)
 int emu_g1_mul_base(const uint32_t* base_xy, const uint32_t* scalars, uint32_t n, uint32_t* out_xy, uint8_t* out_inf) {
   HostExec ex;

@@ -179,6 +179,13 @@ def test_emu_poisoned_partial_is_reported_by_combine(lib, g1_set):
     assert lib.emu_g1_combine(ptr(parts), 3, ptr(out), ctypes.byref(oinf)) == -3
     assert lib.emu_g1_combine(ptr(np.concatenate([good, good])), 2, ptr(out), ctypes.byref(oinf)) == 0
     assert U.g1_from_array(out, oinf.value) == O.scalar_mul(O.msm(pts[:4], [1, 2, 3, 4]), 2)
+    # partials inside larger per-rank blobs (zkmsm_groth16_combine reads A, B and C in place, 192 words apart)
+    blobs = np.full((3, 192), 0xDEADBEEF, dtype=np.uint32)
+    blobs[:, 144:192] = good
+    assert lib.emu_g1_combine_strided(ptr(blobs[0, 144:]), 3, 192, ptr(out), ctypes.byref(oinf)) == 0
+    assert U.g1_from_array(out, oinf.value) == O.scalar_mul(O.msm(pts[:4], [1, 2, 3, 4]), 3)
+    blobs[1, 144:192] = bad
+    assert lib.emu_g1_combine_strided(ptr(blobs[0, 144:]), 3, 192, ptr(out), ctypes.byref(oinf)) == -3
 
 
 def test_emu_bucket_accumulation_and_its_fallback(lib, g1_set, monkeypatch):
